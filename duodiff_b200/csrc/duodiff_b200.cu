@@ -1,0 +1,793 @@
+// Host side of libduodiff_b200.so: weight re-packing, workspace, TMA descriptors, the U-ViT launch sequence,
+// the DDPM sampler loop with CUDA-graph replay, and the extern "C" boundary declared in include/duodiff_b200.h.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/duodiff_b200.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+using namespace ddb;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(DDB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+#define DDB_TRY(expr)            \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != DDB_OK) return _r; \
+    } while (0)
+#define LAUNCH_CHECK()                                                                                      \
+    do {                                                                                                    \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                                 \
+        cudaError_t _e = cudaGetLastError();                                                                \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(DDB_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                        __LINE__);                                                                          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ device info
+struct DeviceInfo {
+    int num_sms = 0;
+    int cc_major = 0;
+    bool ok = false;
+};
+static int device_info(DeviceInfo& d) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (d.cc_major != 10)
+        return fail(DDB_ERR_CUDA, "duodiff_b200 needs an sm_100 (B200) device; found compute capability %d.x",
+                    d.cc_major);
+    d.ok = true;
+    return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int load_encode() {
+    if (g_encode) return DDB_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(DDB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return DDB_OK;
+}
+// bf16 row-major [rows, cols] with row pitch `pitch_elems`; box = 64 columns (128 B, SWIZZLE_128B) x box_rows
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                          uint32_t box_rows) {
+    DDB_TRY(load_encode());
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(DDB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu pitch=%llu box_rows=%u",
+                    (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_elems,
+                    box_rows);
+    return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM launch
+template <int BN, int EPI>
+static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = gemm_tcgen05_kernel<BN, EPI>;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ((a.M + 127) / 128) * (a.N / BN);
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (grid <= 0) return DDB_OK;
+    kfn<<<grid, 384, GemmCfg<BN>::SMEM_BYTES, st>>>(a);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+static int launch_gemm(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
+    switch (epi) {
+        case EPI_BIAS: return launch_gemm_t<256, EPI_BIAS>(a, num_sms, st);
+        case EPI_LN: return launch_gemm_t<256, EPI_LN>(a, num_sms, st);
+        case EPI_LN_GELU: return launch_gemm_t<256, EPI_LN_GELU>(a, num_sms, st);
+        case EPI_RES: return launch_gemm_t<256, EPI_RES>(a, num_sms, st);
+        case EPI_DECODE: return launch_gemm_t<64, EPI_DECODE>(a, num_sms, st);
+    }
+    return fail(DDB_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+}
+
+static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_dev, float2* stats, const float* pw,
+                           const float* pb, float* psig, cudaStream_t st) {
+    const int grid = (M + 7) / 8;
+    if (grid <= 0) return DDB_OK;
+    switch (D) {
+        case 256: ln_stats_kernel<256><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        case 512: ln_stats_kernel<512><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        case 768: ln_stats_kernel<768><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        case 1024: ln_stats_kernel<1024><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        case 2048: ln_stats_kernel<2048><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        default: return fail(DDB_ERR_INVALID, "embed_dim %d unsupported (need 256/512/768/1024/2048)", D);
+    }
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int L, int H, cudaStream_t st) {
+    static int configured_bytes = 0;
+    const int Lp = (L + 15) & ~15;
+    const int smem = 2 * Lp * 128;
+    if (smem > 227 * 1024) return fail(DDB_ERR_INVALID, "sequence length %d too long for the resident-KV kernel", L);
+    if (smem > configured_bytes) {
+        CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_bytes = smem;
+    }
+    if (B <= 0) return DDB_OK;
+    attention_mma_kernel<<<B * H, ATT_THREADS, smem, st>>>(qkv, out, L, H, 0.125f * 1.4426950408889634f);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ model
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        CUDA_TRY(cudaMalloc(&p, bytes));
+        return DDB_OK;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+typedef std::unique_ptr<DevMem> Buf;
+
+struct Linear {
+    Buf w, bias, colsum;
+    int N = 0, N_src = 0, K = 0;
+};
+struct BlockW {
+    Linear qkv, proj, fc1, fc2, skip;
+    bool has_skip = false;
+};
+struct HeadW {
+    Linear dec;  // LN folded, N padded to 64
+    Buf conv_w, conv_b;
+};
+struct BlockOps {
+    GemmArgs skip, qkv, proj, fc1, fc2;
+};
+
+struct ddb_model {
+    ddb_uvit_config cfg;
+    DeviceInfo dev;
+    int L = 0, Np = 0, extras = 0, pd = 0, D = 0, Hh = 0, Mmax = 0, Mpad = 0;
+    size_t chw = 0;
+    Buf pe_wt, pe_bias, pos, label_emb;
+    std::vector<BlockW> blocks;
+    HeadW final_head;
+    std::vector<HeadW> ee_heads;
+    std::vector<Buf> probe_w, probe_b;
+    // workspace
+    Buf x0, xs, xm, qkv, ao, hbuf, stats, img_pre, probe_sig, scores, outputs, exit_idx;
+    std::vector<Buf> xo;
+    // plan
+    std::vector<BlockOps> ops;
+    GemmArgs final_dec;
+    std::vector<GemmArgs> head_dec;
+    std::vector<Buf> keep;  // misc allocations
+};
+
+typedef std::map<std::string, const ddb_tensor*> TensorMap;
+
+static int get_tensor(const TensorMap& tm, const std::string& name, int64_t numel, const float** out,
+                      bool optional = false) {
+    auto it = tm.find(name);
+    if (it == tm.end()) {
+        *out = nullptr;
+        if (optional) return DDB_OK;
+        return fail(DDB_ERR_MISSING_KEY, "state_dict key '%s' missing", name.c_str());
+    }
+    if (numel >= 0 && it->second->numel != numel)
+        return fail(DDB_ERR_SHAPE, "state_dict key '%s' has %lld elements, expected %lld", name.c_str(),
+                    (long long)it->second->numel, (long long)numel);
+    *out = it->second->data_dev;
+    return DDB_OK;
+}
+
+static int pack_linear(Linear& lin, const float* W, const float* bias, const float* gamma, const float* beta,
+                       int N_src, int N_pad, int K, bool want_colsum) {
+    lin.N = N_pad, lin.N_src = N_src, lin.K = K;
+    lin.w.reset(new DevMem), lin.bias.reset(new DevMem), lin.colsum.reset(new DevMem);
+    DDB_TRY(lin.w->alloc((size_t)N_pad * K * 2));
+    DDB_TRY(lin.bias->alloc((size_t)N_pad * 4));
+    DDB_TRY(lin.colsum->alloc((size_t)N_pad * 4));
+    pack_linear_kernel<<<N_pad, 256>>>(W, bias, gamma, beta, N_src, K, lin.w->as<__nv_bfloat16>(),
+                                       want_colsum ? lin.colsum->as<float>() : nullptr, lin.bias->as<float>());
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+static int load_block(ddb_model* m, const TensorMap& tm, const std::string& pfx, bool skip, BlockW& bw) {
+    const int D = m->D, Hd = m->cfg.mlp_hidden;
+    const float *g1, *b1, *g2, *b2, *w, *b;
+    DDB_TRY(get_tensor(tm, pfx + "norm1.weight", D, &g1));
+    DDB_TRY(get_tensor(tm, pfx + "norm1.bias", D, &b1));
+    DDB_TRY(get_tensor(tm, pfx + "norm2.weight", D, &g2));
+    DDB_TRY(get_tensor(tm, pfx + "norm2.bias", D, &b2));
+    DDB_TRY(get_tensor(tm, pfx + "attn.qkv.weight", (int64_t)3 * D * D, &w));
+    DDB_TRY(get_tensor(tm, pfx + "attn.qkv.bias", 3 * D, &b, true));
+    DDB_TRY(pack_linear(bw.qkv, w, b, g1, b1, 3 * D, 3 * D, D, true));
+    DDB_TRY(get_tensor(tm, pfx + "attn.proj.weight", (int64_t)D * D, &w));
+    DDB_TRY(get_tensor(tm, pfx + "attn.proj.bias", D, &b));
+    DDB_TRY(pack_linear(bw.proj, w, b, nullptr, nullptr, D, D, D, false));
+    DDB_TRY(get_tensor(tm, pfx + "mlp.fc1.weight", (int64_t)Hd * D, &w));
+    DDB_TRY(get_tensor(tm, pfx + "mlp.fc1.bias", Hd, &b));
+    DDB_TRY(pack_linear(bw.fc1, w, b, g2, b2, Hd, Hd, D, true));
+    DDB_TRY(get_tensor(tm, pfx + "mlp.fc2.weight", (int64_t)D * Hd, &w));
+    DDB_TRY(get_tensor(tm, pfx + "mlp.fc2.bias", D, &b));
+    DDB_TRY(pack_linear(bw.fc2, w, b, nullptr, nullptr, D, D, Hd, false));
+    bw.has_skip = skip;
+    if (skip) {
+        DDB_TRY(get_tensor(tm, pfx + "skip_linear.weight", (int64_t)2 * D * D, &w));
+        DDB_TRY(get_tensor(tm, pfx + "skip_linear.bias", D, &b));
+        DDB_TRY(pack_linear(bw.skip, w, b, nullptr, nullptr, D, D, 2 * D, false));
+    }
+    return DDB_OK;
+}
+
+static int load_head(ddb_model* m, const TensorMap& tm, const std::string& pfx, HeadW& hw) {
+    const int D = m->D, C = m->cfg.in_chans;
+    const float *g, *b, *w, *wb, *cw, *cb;
+    DDB_TRY(get_tensor(tm, pfx + "norm.weight", D, &g));
+    DDB_TRY(get_tensor(tm, pfx + "norm.bias", D, &b));
+    DDB_TRY(get_tensor(tm, pfx + "decoder_pred.weight", (int64_t)m->pd * D, &w));
+    DDB_TRY(get_tensor(tm, pfx + "decoder_pred.bias", m->pd, &wb));
+    DDB_TRY(pack_linear(hw.dec, w, wb, g, b, m->pd, 64, D, true));
+    DDB_TRY(get_tensor(tm, pfx + "final_layer.weight", (int64_t)C * C * 9, &cw));
+    DDB_TRY(get_tensor(tm, pfx + "final_layer.bias", C, &cb));
+    hw.conv_w.reset(new DevMem), hw.conv_b.reset(new DevMem);
+    DDB_TRY(hw.conv_w->alloc((size_t)C * C * 9 * 4));
+    DDB_TRY(hw.conv_b->alloc((size_t)C * 4));
+    CUDA_TRY(cudaMemcpy(hw.conv_w->p, cw, (size_t)C * C * 9 * 4, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(hw.conv_b->p, cb, (size_t)C * 4, cudaMemcpyDeviceToDevice));
+    return DDB_OK;
+}
+
+static int new_buf(Buf& b, size_t bytes, bool zero = true) {
+    b.reset(new DevMem);
+    DDB_TRY(b->alloc(bytes));
+    if (zero) CUDA_TRY(cudaMemset(b->p, 0, bytes));
+    return DDB_OK;
+}
+
+// Fill the shape/pointer fields + descriptors of one GEMM of the plan.
+static int plan_gemm(GemmArgs& g, const ddb_model* m, const void* A0, int K0, const void* A1, int K1, const Linear& W,
+                     int BN, const void* out, const void* res, const float2* stats) {
+    memset(&g, 0, sizeof(g));
+    g.M = m->Mmax, g.N = W.N, g.K0 = K0, g.K1 = K1;
+    g.bias = W.bias->as<float>();
+    g.colsum = W.colsum->as<float>();
+    g.stats = stats;
+    g.nparts = 1, g.ln_dim = m->D, g.ln_eps = m->cfg.ln_eps;
+    DDB_TRY(make_tmap_bf16(&g.tmA0, A0, m->Mpad, K0, K0, 128));
+    if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, A1, m->Mpad, K1, K1, 128));
+    DDB_TRY(make_tmap_bf16(&g.tmB, W.w->p, W.N, K0 + K1, K0 + K1, BN));
+    if (out) DDB_TRY(make_tmap_bf16(&g.tmOut, out, m->Mpad, W.N, W.N, 128));
+    if (res) DDB_TRY(make_tmap_bf16(&g.tmRes, res, m->Mpad, W.N, W.N, 128));
+    return DDB_OK;
+}
+static void plan_decode_geometry(GemmArgs& g, const ddb_model* m, float* img) {
+    g.img = img;
+    g.L = m->L, g.extras = m->extras, g.C = m->cfg.in_chans, g.P = m->cfg.patch_size;
+    g.Wp = m->cfg.img_size / m->cfg.patch_size, g.H = m->cfg.img_size, g.W = m->cfg.img_size;
+    g.patch_dim = m->pd;
+}
+
+static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tensors, int n_tensors, ddb_model* m) {
+    m->cfg = *cfg;
+    DDB_TRY(device_info(m->dev));
+    const int D = cfg->embed_dim, P = cfg->patch_size, C = cfg->in_chans;
+    if (cfg->img_size % P) return fail(DDB_ERR_INVALID, "img_size %% patch_size != 0");
+    if (cfg->img_size / P != EMB_TOK)
+        return fail(DDB_ERR_INVALID, "img_size/patch_size must be 16 (every reference config), got %d",
+                    cfg->img_size / P);
+    if (cfg->img_size % CONV_BAND) return fail(DDB_ERR_INVALID, "img_size must be a multiple of 16");
+    if (D % 256 || D / cfg->num_heads != 64 || D % cfg->num_heads)
+        return fail(DDB_ERR_INVALID, "embed_dim must be a multiple of 256 with head_dim 64 (got %d / %d heads)", D,
+                    cfg->num_heads);
+    if (cfg->mlp_hidden % 256) return fail(DDB_ERR_INVALID, "mlp_hidden must be a multiple of 256");
+    if (cfg->depth < 1 || cfg->depth % 2 == 0) return fail(DDB_ERR_INVALID, "depth must be odd");
+    if (cfg->max_batch < 1) return fail(DDB_ERR_INVALID, "max_batch must be >= 1");
+    m->D = D, m->Hh = cfg->num_heads;
+    m->Np = (cfg->img_size / P) * (cfg->img_size / P);
+    m->extras = cfg->num_classes > 0 ? 2 : 1;
+    m->L = m->Np + m->extras;
+    m->pd = P * P * C;
+    if (m->pd > 64) return fail(DDB_ERR_INVALID, "patch_dim %d > 64 unsupported", m->pd);
+    m->chw = (size_t)C * cfg->img_size * cfg->img_size;
+    if (m->chw % 4) return fail(DDB_ERR_INVALID, "C*H*W must be a multiple of 4");
+    m->Mmax = cfg->max_batch * m->L;
+    m->Mpad = (m->Mmax + 127) / 128 * 128;
+
+    TensorMap tm;
+    const std::string up = cfg->early_exit ? "uvit." : "";
+    for (int i = 0; i < n_tensors; ++i) tm[tensors[i].name] = &tensors[i];
+
+    // ---- embeddings
+    const float *pw, *pb, *pos, *lab;
+    DDB_TRY(get_tensor(tm, up + "patch_embed.proj.weight", (int64_t)D * m->pd, &pw));
+    DDB_TRY(get_tensor(tm, up + "patch_embed.proj.bias", D, &pb));
+    DDB_TRY(get_tensor(tm, up + "pos_embed", (int64_t)m->L * D, &pos));
+    DDB_TRY(new_buf(m->pe_wt, (size_t)m->pd * D * 4));
+    transpose_pe_kernel<<<(D * m->pd + 255) / 256, 256>>>(pw, D, m->pd, m->pe_wt->as<float>());
+    LAUNCH_CHECK();
+    DDB_TRY(new_buf(m->pe_bias, (size_t)D * 4));
+    CUDA_TRY(cudaMemcpy(m->pe_bias->p, pb, (size_t)D * 4, cudaMemcpyDeviceToDevice));
+    DDB_TRY(new_buf(m->pos, (size_t)m->L * D * 4));
+    CUDA_TRY(cudaMemcpy(m->pos->p, pos, (size_t)m->L * D * 4, cudaMemcpyDeviceToDevice));
+    if (cfg->num_classes > 0) {
+        DDB_TRY(get_tensor(tm, up + "label_emb.weight", (int64_t)cfg->num_classes * D, &lab));
+        DDB_TRY(new_buf(m->label_emb, (size_t)cfg->num_classes * D * 4));
+        CUDA_TRY(cudaMemcpy(m->label_emb->p, lab, (size_t)cfg->num_classes * D * 4, cudaMemcpyDeviceToDevice));
+    }
+    // ---- blocks
+    const int half = cfg->depth / 2;
+    m->blocks.resize(cfg->depth);
+    for (int i = 0; i < half; ++i)
+        DDB_TRY(load_block(m, tm, up + "in_blocks." + std::to_string(i) + ".", false, m->blocks[i]));
+    DDB_TRY(load_block(m, tm, up + "mid_block.", false, m->blocks[half]));
+    for (int i = 0; i < half; ++i)
+        DDB_TRY(load_block(m, tm, up + "out_blocks." + std::to_string(i) + ".", true, m->blocks[half + 1 + i]));
+    DDB_TRY(load_head(m, tm, up, m->final_head));
+    if (cfg->early_exit) {
+        m->ee_heads.resize(cfg->depth);
+        m->probe_w.resize(cfg->depth), m->probe_b.resize(cfg->depth);
+        for (int i = 0; i < cfg->depth; ++i) {
+            std::string hp = i < half    ? "in_blocks_heads." + std::to_string(i) + "."
+                             : i == half ? std::string("mid_block_head.")
+                                         : "out_blocks_heads." + std::to_string(i - half - 1) + ".";
+            DDB_TRY(load_head(m, tm, hp, m->ee_heads[i]));
+            const float *w, *b;
+            const std::string pp = "matrix." + std::to_string(i) + ".classifier.0.";
+            DDB_TRY(get_tensor(tm, pp + "weight", D, &w));
+            DDB_TRY(get_tensor(tm, pp + "bias", 1, &b));
+            DDB_TRY(new_buf(m->probe_w[i], (size_t)D * 4));
+            DDB_TRY(new_buf(m->probe_b[i], 4));
+            CUDA_TRY(cudaMemcpy(m->probe_w[i]->p, w, (size_t)D * 4, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(m->probe_b[i]->p, b, 4, cudaMemcpyDeviceToDevice));
+        }
+    }
+    // ---- workspace
+    const size_t act = (size_t)m->Mpad * D * 2;
+    DDB_TRY(new_buf(m->x0, act));
+    DDB_TRY(new_buf(m->xs, act));
+    DDB_TRY(new_buf(m->xm, act));
+    DDB_TRY(new_buf(m->ao, act));
+    DDB_TRY(new_buf(m->qkv, act * 3));
+    DDB_TRY(new_buf(m->hbuf, (size_t)m->Mpad * cfg->mlp_hidden * 2));
+    DDB_TRY(new_buf(m->stats, (size_t)m->Mpad * sizeof(float2)));
+    DDB_TRY(new_buf(m->img_pre, (size_t)cfg->max_batch * m->chw * 4));
+    m->xo.resize(cfg->depth);
+    for (int i = 0; i < cfg->depth; ++i) DDB_TRY(new_buf(m->xo[i], act));
+    if (cfg->early_exit) {
+        DDB_TRY(new_buf(m->probe_sig, (size_t)m->Mpad * 4));
+        DDB_TRY(new_buf(m->scores, (size_t)cfg->depth * cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->outputs, (size_t)(cfg->depth + 1) * cfg->max_batch * m->chw * 4));
+        DDB_TRY(new_buf(m->exit_idx, (size_t)cfg->max_batch * 4));
+    }
+    // ---- plan (buffer routing of models/uvit.py:367-375)
+    m->ops.resize(cfg->depth);
+    const float2* st = m->stats->as<float2>();
+    const void* cur = m->x0->p;
+    std::vector<const void*> skips;
+    for (int i = 0; i < cfg->depth; ++i) {
+        BlockW& bw = m->blocks[i];
+        BlockOps& op = m->ops[i];
+        if (bw.has_skip) {
+            const void* sk = skips.back();
+            skips.pop_back();
+            DDB_TRY(plan_gemm(op.skip, m, cur, D, sk, D, bw.skip, 256, m->xs->p, nullptr, nullptr));
+            cur = m->xs->p;
+        }
+        DDB_TRY(plan_gemm(op.qkv, m, cur, D, nullptr, 0, bw.qkv, 256, m->qkv->p, nullptr, st));
+        DDB_TRY(plan_gemm(op.proj, m, m->ao->p, D, nullptr, 0, bw.proj, 256, m->xm->p, cur, nullptr));
+        DDB_TRY(plan_gemm(op.fc1, m, m->xm->p, D, nullptr, 0, bw.fc1, 256, m->hbuf->p, nullptr, st));
+        DDB_TRY(plan_gemm(op.fc2, m, m->hbuf->p, cfg->mlp_hidden, nullptr, 0, bw.fc2, 256, m->xo[i]->p, m->xm->p,
+                          nullptr));
+        cur = m->xo[i]->p;
+        if (i < half) skips.push_back(cur);
+    }
+    DDB_TRY(plan_gemm(m->final_dec, m, cur, D, nullptr, 0, m->final_head.dec, 64, nullptr, nullptr, st));
+    plan_decode_geometry(m->final_dec, m, m->img_pre->as<float>());
+    if (cfg->early_exit) {
+        m->head_dec.resize(cfg->depth);
+        for (int i = 0; i < cfg->depth; ++i) {
+            // head i reads the input of block i (models/early_exit.py:291-313)
+            const void* in = (i == 0) ? m->x0->p : m->xo[i - 1]->p;
+            DDB_TRY(plan_gemm(m->head_dec[i], m, in, D, nullptr, 0, m->ee_heads[i].dec, 64, nullptr, nullptr, st));
+            plan_decode_geometry(m->head_dec[i], m, m->img_pre->as<float>());
+        }
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    return DDB_OK;
+}
+
+static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st) {
+    const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
+    const int smem = (C * (CONV_BAND + 2) * (W + 2) + C * C * 9 + C) * 4;
+    conv3x3_kernel<<<B * (H / CONV_BAND), 256, smem, st>>>(in, hw.conv_w->as<float>(), hw.conv_b->as<float>(), out,
+                                                            C, H, W);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+// The launch sequence of one forward.  ee: evaluate probes + heads (simulate mode) into m->scores / m->outputs.
+static int forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float* eps, bool ee,
+                        cudaStream_t st) {
+    const ddb_uvit_config& c = m->cfg;
+    if (B < 1 || B > c.max_batch) return fail(DDB_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, c.max_batch);
+    if (m->extras == 2 && !y) return fail(DDB_ERR_INVALID, "class-conditional model needs y (models/uvit.py:361)");
+    if (ee && !c.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
+    const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
+    float2* st2 = m->stats->as<float2>();
+
+    embed_tokens_kernel<<<B * (c.img_size / c.patch_size), 256, m->pd * EMB_TOK * 4, st>>>(
+        x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),
+        m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(), c.in_chans,
+        c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps);
+    LAUNCH_CHECK();
+
+    const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
+    for (int i = 0; i < c.depth; ++i) {
+        BlockOps op = m->ops[i];
+        const BlockW& bw = m->blocks[i];
+        bool have_stats = false;
+        if (ee) {
+            // probe i + head i look at the block input (models/early_exit.py:294-296)
+            DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
+                                    m->probe_sig->as<float>(), st));
+            probe_mean_kernel<<<B, 128, 0, st>>>(m->probe_sig->as<float>(), m->L,
+                                                 m->scores->as<float>() + (size_t)i * B);
+            LAUNCH_CHECK();
+            GemmArgs hd = m->head_dec[i];
+            hd.M = M;
+            DDB_TRY(launch_gemm(hd, EPI_DECODE, nsm, st));
+            DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(),
+                             m->outputs->as<float>() + (size_t)i * B * m->chw, B, st));
+            have_stats = true;
+        }
+        if (bw.has_skip) {
+            op.skip.M = M;
+            DDB_TRY(launch_gemm(op.skip, EPI_BIAS, nsm, st));
+            cur = m->xs->as<__nv_bfloat16>();
+            have_stats = false;
+        }
+        if (!have_stats) DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+        op.qkv.M = M;
+        DDB_TRY(launch_gemm(op.qkv, EPI_LN, nsm, st));
+        DDB_TRY(launch_attention(m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), B, m->L, m->Hh, st));
+        op.proj.M = M;
+        DDB_TRY(launch_gemm(op.proj, EPI_RES, nsm, st));
+        DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+        op.fc1.M = M;
+        DDB_TRY(launch_gemm(op.fc1, EPI_LN_GELU, nsm, st));
+        op.fc2.M = M;
+        DDB_TRY(launch_gemm(op.fc2, EPI_RES, nsm, st));
+        cur = m->xo[i]->as<__nv_bfloat16>();
+    }
+    (void)half;
+    DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+    GemmArgs fd = m->final_dec;
+    fd.M = M;
+    DDB_TRY(launch_gemm(fd, EPI_DECODE, nsm, st));
+    DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
+    return DDB_OK;
+}
+
+static int ee_forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float threshold,
+                           int mode, float* eps, int32_t* exit_idx, float* scores_out, float* outputs_out,
+                           cudaStream_t st) {
+    if (!m->cfg.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
+    if (mode != 0) return fail(DDB_ERR_INVALID, "ee mode %d not implemented yet (0 = simulate)", mode);
+    const int depth = m->cfg.depth;
+    float* full = m->outputs->as<float>() + (size_t)depth * B * m->chw;
+    DDB_TRY(forward_impl(m, x, t, y, B, full, true, st));
+    int32_t* idx = exit_idx ? exit_idx : m->exit_idx->as<int32_t>();
+    dim3 grid((unsigned)((m->chw / 4 + 255) / 256), (unsigned)B);
+    ee_select_kernel<<<grid, 256, 0, st>>>(m->scores->as<float>(), m->outputs->as<float>(), depth, B, m->chw,
+                                           threshold, eps, idx);
+    LAUNCH_CHECK();
+    if (scores_out)
+        CUDA_TRY(cudaMemcpyAsync(scores_out, m->scores->p, (size_t)depth * B * 4, cudaMemcpyDeviceToDevice, st));
+    if (outputs_out)
+        CUDA_TRY(cudaMemcpyAsync(outputs_out, m->outputs->p, (size_t)(depth + 1) * B * m->chw * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+    return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sampler
+struct ddb_sampler {
+    ddb_model* early = nullptr;
+    ddb_model* late = nullptr;
+    int switch_t = -1, B = 0, step_mode = 0, ee_mode = 0;
+    float ee_threshold = -1.f;
+    size_t n = 0;
+    Buf coef, t_dev, t_vec, eps, score_mean;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    const void* graph_key[2][4] = {{nullptr}};
+    unsigned long long graph_seed[2] = {0, 0};
+};
+
+__global__ void set_t_kernel(int* t_dev, int t) { *t_dev = t; }
+// eesampler.py:71  error_prediction_by_timestep[t] = classifier_outputs.mean(axis=1)[:depth]
+__global__ void score_mean_kernel(const float* __restrict__ scores, int depth, int B, float* __restrict__ out) {
+    const int i = blockIdx.x;
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 32) s += scores[(size_t)i * B + b];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[i] = s / (float)B;
+}
+
+// one sampling step on the stream: forward + update (+ bookkeeping). t comes from s->t_dev (device).
+static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y, const float* z_all,
+                        unsigned long long seed, int t_host, float* eps_save, float* x_save, int32_t* exit_save,
+                        float* score_save, cudaStream_t st) {
+    const int B = s->B;
+    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->t_dev->as<int>(), s->t_vec->as<float>(), B);
+    LAUNCH_CHECK();
+    float* eps = eps_save ? eps_save : s->eps->as<float>();
+    if (s->ee_threshold >= 0.f && m->cfg.early_exit) {
+        DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, exit_save,
+                                nullptr, nullptr, st));
+        if (score_save) {
+            score_mean_kernel<<<m->cfg.depth, 32, 0, st>>>(m->scores->as<float>(), m->cfg.depth, B, score_save);
+            LAUNCH_CHECK();
+        }
+    } else {
+        DDB_TRY(forward_impl(m, x, s->t_vec->as<float>(), y, B, eps, false, st));
+    }
+    (void)t_host;
+    ddpm_step_kernel<<<(unsigned)((s->n / 4 + 255) / 256), 256, 0, st>>>(x, eps, z_all, s->n, s->n,
+                                                                         s->coef->as<float>(), s->t_dev->as<int>(), 0,
+                                                                         s->step_mode, seed, x_save);
+    LAUNCH_CHECK();
+    dec_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>());
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* ddb_version(void) { return "duodiff_b200 0.1.0 (sm_100a)"; }
+const char* ddb_last_error(void) { return g_err; }
+int64_t ddb_launch_count(void) { return g_launches.load(); }
+
+int ddb_model_create(const ddb_uvit_config* cfg, const ddb_tensor* tensors, int32_t n_tensors, ddb_model** out) {
+    if (!cfg || !tensors || !out) return fail(DDB_ERR_INVALID, "null argument");
+    ddb_model* m = new ddb_model();
+    int r = model_create_impl(cfg, tensors, n_tensors, m);
+    if (r != DDB_OK) {
+        delete m;
+        *out = nullptr;
+        return r;
+    }
+    *out = m;
+    return DDB_OK;
+}
+void ddb_model_destroy(ddb_model* m) {
+    if (m) {
+        cudaDeviceSynchronize();
+        delete m;
+    }
+}
+
+int ddb_uvit_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                     float* eps_dev, void* stream) {
+    if (!m || !x_dev || !t_dev || !eps_dev) return fail(DDB_ERR_INVALID, "null argument");
+    return forward_impl(m, x_dev, t_dev, y_dev, B, eps_dev, false, (cudaStream_t)stream);
+}
+
+int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                   float threshold, int32_t mode, float* eps_dev, int32_t* exit_idx_dev, float* scores_dev,
+                   float* outputs_dev, void* stream) {
+    if (!m || !x_dev || !t_dev || !eps_dev) return fail(DDB_ERR_INVALID, "null argument");
+    return ee_forward_impl(m, x_dev, t_dev, y_dev, B, threshold, mode, eps_dev, exit_idx_dev, scores_dev, outputs_dev,
+                           (cudaStream_t)stream);
+}
+
+int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, const float* coef_dev, int32_t t,
+                  int32_t mode, uint64_t seed, int64_t n, void* stream) {
+    if (!x_dev || !model_out_dev || !coef_dev) return fail(DDB_ERR_INVALID, "null argument");
+    if (t < 0 || t > 999 || n <= 0 || n % 4) return fail(DDB_ERR_INVALID, "bad t=%d or n=%lld", t, (long long)n);
+    // z_dev is this step's tensor: stride 0 makes z_all + t*stride land on it
+    ddpm_step_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x_dev, model_out_dev, z_dev, (size_t)n, (size_t)0, coef_dev, nullptr, t, mode, seed, nullptr);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int32_t B, const float* coef_host,
+                       int32_t step_mode, float ee_threshold, int32_t ee_mode, ddb_sampler** out) {
+    if (!early || !coef_host || !out) return fail(DDB_ERR_INVALID, "null argument");
+    if (B < 1 || B > early->cfg.max_batch || (late && B > late->cfg.max_batch))
+        return fail(DDB_ERR_INVALID, "batch %d exceeds a model's max_batch", B);
+    if (late && late->chw != early->chw) return fail(DDB_ERR_SHAPE, "early/late models disagree on C*H*W");
+    std::unique_ptr<ddb_sampler> s(new ddb_sampler());
+    s->early = early, s->late = late, s->switch_t = switch_t, s->B = B, s->step_mode = step_mode;
+    s->ee_threshold = ee_threshold, s->ee_mode = ee_mode;
+    s->n = (size_t)B * early->chw;
+    DDB_TRY(new_buf(s->coef, 1000 * 4 * 4));
+    CUDA_TRY(cudaMemcpy(s->coef->p, coef_host, 1000 * 4 * 4, cudaMemcpyHostToDevice));
+    DDB_TRY(new_buf(s->t_dev, 4));
+    DDB_TRY(new_buf(s->t_vec, (size_t)B * 4));
+    DDB_TRY(new_buf(s->eps, s->n * 4));
+    *out = s.release();
+    return DDB_OK;
+}
+void ddb_sampler_destroy(ddb_sampler* s) {
+    if (!s) return;
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+    delete s;
+}
+
+int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                    int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
+                    int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream) {
+    if (!s || !x_dev) return fail(DDB_ERR_INVALID, "null argument");
+    if (t_first > 999 || t_last < 0 || t_last > t_first) return fail(DDB_ERR_INVALID, "bad step range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tracing = eps_trace_dev || x_trace_dev || exit_idx_trace_dev || score_mean_trace_dev;
+    if (use_graph && tracing) return fail(DDB_ERR_INVALID, "per-step traces need use_graph=0");
+    set_t_kernel<<<1, 1, 0, st>>>(s->t_dev->as<int>(), t_first);
+    LAUNCH_CHECK();
+    if (!use_graph) {
+        for (int t = t_first, k = 0; t >= t_last; --t, ++k) {
+            ddb_model* m = (s->late && t < s->switch_t) ? s->late : s->early;
+            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, t,
+                                 eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
+                                 x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr,
+                                 exit_idx_trace_dev ? exit_idx_trace_dev + (size_t)k * s->B : nullptr,
+                                 score_mean_trace_dev ? score_mean_trace_dev + (size_t)k * s->early->cfg.depth : nullptr,
+                                 st));
+        }
+        return DDB_OK;
+    }
+    // ---- graph replay: one captured step per backbone, t read from device memory
+    for (int which = 0; which < 2; ++which) {
+        ddb_model* m = which == 0 ? s->early : s->late;
+        if (!m) continue;
+        const void* key[4] = {x_dev, y_dev, z_all_dev, st};
+        if (s->graph[which] && (memcmp(key, s->graph_key[which], sizeof(key)) != 0 || s->graph_seed[which] != seed)) {
+            cudaGraphExecDestroy(s->graph[which]);
+            s->graph[which] = nullptr;
+        }
+        if (!s->graph[which]) {
+            cudaStream_t cs;
+            CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+            cudaGraph_t g = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+            int r = sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, 0, nullptr, nullptr, nullptr, nullptr, cs);
+            cudaError_t e = cudaStreamEndCapture(cs, &g);
+            if (r != DDB_OK) {
+                if (g) cudaGraphDestroy(g);
+                cudaStreamDestroy(cs);
+                return r;
+            }
+            if (e != cudaSuccess) {
+                cudaStreamDestroy(cs);
+                return fail(DDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+            }
+            e = cudaGraphInstantiate(&s->graph[which], g, 0);
+            cudaGraphDestroy(g);
+            cudaStreamDestroy(cs);
+            if (e != cudaSuccess) return fail(DDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+            memcpy(s->graph_key[which], key, sizeof(key));
+            s->graph_seed[which] = seed;
+        }
+    }
+    for (int t = t_first; t >= t_last; --t) {
+        const int which = (s->late && t < s->switch_t) ? 1 : 0;
+        CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
+    }
+    return DDB_OK;
+}
+
+int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+    if (!x_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
+    const size_t n = (size_t)B * C * H * W;
+    finalize_nhwc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_dev, out_dev, B, C, H, W);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+// ---- single-operator entry points
+int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const float* bias_dev,
+                const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
+                const void* residual_dev, void* out_dev, int32_t M, int32_t N, int32_t K0, int32_t K1, int32_t epi,
+                void* stream) {
+    if (!a0_dev || !w_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
+    if (epi < 0 || epi > EPI_RES) return fail(DDB_ERR_INVALID, "epi must be 0..3");
+    if (N % 256 || K0 % 64 || K1 % 64 || M < 1) return fail(DDB_ERR_INVALID, "need N%%256==0, K%%64==0, M>=1");
+    if ((epi == EPI_LN || epi == EPI_LN_GELU) && (!colsum_dev || !stats_dev))
+        return fail(DDB_ERR_INVALID, "LN epilogue needs colsum and stats");
+    if (epi == EPI_RES && !residual_dev) return fail(DDB_ERR_INVALID, "residual epilogue needs residual");
+    DeviceInfo di;
+    DDB_TRY(device_info(di));
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = M, g.N = N, g.K0 = K0, g.K1 = K1;
+    g.bias = bias_dev, g.colsum = colsum_dev, g.stats = reinterpret_cast<const float2*>(stats_dev);
+    g.nparts = nparts > 0 ? nparts : 1, g.ln_dim = ln_dim, g.ln_eps = 1e-5f;
+    DDB_TRY(make_tmap_bf16(&g.tmA0, a0_dev, M, K0, K0, 128));
+    if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, a1_dev, M, K1, K1, 128));
+    DDB_TRY(make_tmap_bf16(&g.tmB, w_dev, N, K0 + K1, K0 + K1, 256));
+    DDB_TRY(make_tmap_bf16(&g.tmOut, out_dev, M, N, N, 128));
+    if (residual_dev) DDB_TRY(make_tmap_bf16(&g.tmRes, residual_dev, M, N, N, 128));
+    return launch_gemm(g, epi, di.num_sms, (cudaStream_t)stream);
+}
+
+int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, void* stream) {
+    if (!qkv_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
+    DeviceInfo di;
+    DDB_TRY(device_info(di));
+    return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
+                            reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H, (cudaStream_t)stream);
+}
+
+int ddb_op_ln_stats(const void* x_dev, int32_t M, int32_t D, float* stats_dev, void* stream) {
+    if (!x_dev || !stats_dev) return fail(DDB_ERR_INVALID, "null argument");
+    return launch_ln_stats(reinterpret_cast<const __nv_bfloat16*>(x_dev), M, D, nullptr,
+                           reinterpret_cast<float2*>(stats_dev), nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ddb_op_pack_linear(const float* w_dev, const float* bias_dev, const float* gamma_dev, const float* beta_dev,
+                       int32_t N, int32_t K, void* wp_dev, float* colsum_dev, float* bias_out_dev, void* stream) {
+    if (!w_dev || !wp_dev) return fail(DDB_ERR_INVALID, "null argument");
+    pack_linear_kernel<<<N, 256, 0, (cudaStream_t)stream>>>(w_dev, bias_dev, gamma_dev, beta_dev, N, K,
+                                                            reinterpret_cast<__nv_bfloat16*>(wp_dev), colsum_dev,
+                                                            bias_out_dev);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// HBM-bound kernels of the sampling path: token assembly + patch embed, LayerNorm row statistics (+ early-exit
+// probe), 3x3 final conv, DDPM update, weight re-packing, early-exit selection / compaction, output layout.
+#pragma once
+#include "ptx.cuh"
+
+namespace ddb {
+
+// =====================================================================================================
+// Weight re-packing (once per model load)
+// =====================================================================================================
+// W'[n,k] = bf16(W[n,k] * gamma[k]);  colsum[n] = sum_k float(W'[n,k]);  bias'[n] = bias[n] + sum_k W[n,k]*beta[k]
+// gamma/beta may be null (plain cast).  Rows n >= N_src are zero-filled (decoder padding).
+__global__ void pack_linear_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int N_src, int K,
+                                   __nv_bfloat16* __restrict__ Wp, float* __restrict__ colsum,
+                                   float* __restrict__ bias_out) {
+    const int n = blockIdx.x;
+    float cs = 0.f, bs = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float w = (n < N_src) ? W[(size_t)n * K + k] : 0.f;
+        float wg = gamma ? w * gamma[k] : w;
+        __nv_bfloat16 q = __float2bfloat16_rn(wg);
+        Wp[(size_t)n * K + k] = q;
+        cs += __bfloat162float(q);
+        if (beta) bs += w * beta[k];
+    }
+    __shared__ float red[2][32];
+    for (int o = 16; o > 0; o >>= 1) {
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        bs += __shfl_xor_sync(0xffffffffu, bs, o);
+    }
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = cs, red[1][threadIdx.x >> 5] = bs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) a += red[0][i], b += red[1][i];
+        if (colsum) colsum[n] = a;
+        if (bias_out) bias_out[n] = ((bias && n < N_src) ? bias[n] : 0.f) + b;
+    }
+}
+
+// patch-embed conv weight [D, C, p, p] -> transposed fp32 [pd, D] (k = (c, p1, p2) as in the conv weight)
+__global__ void transpose_pe_kernel(const float* __restrict__ W, int D, int pd, float* __restrict__ Wt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D * pd) {
+        int e = i / pd, k = i % pd;
+        Wt[(size_t)k * D + e] = W[i];
+    }
+}
+
+// =====================================================================================================
+// Token assembly: patch embed (models/uvit.py:221-225) + time token (:95-115, :352-360) + label (:361-364)
+// + pos_embed (:365).  One CTA per (sample, patch row); the CTA with patch row 0 also writes the extras.
+// x_img [B,C,H,W] fp32 -> tokens [B*L, D] bf16.   Requires W/p == 16 patches per row (true for every config).
+// =====================================================================================================
+constexpr int EMB_TOK = 16;
+__global__ void __launch_bounds__(256) embed_tokens_kernel(
+    const float* __restrict__ x_img, const float* __restrict__ tsteps, const long long* __restrict__ y,
+    const float* __restrict__ Wt /*[pd,D]*/, const float* __restrict__ pe_bias, const float* __restrict__ pos /*[L,D]*/,
+    const float* __restrict__ label_emb /*[classes,D] or null*/, __nv_bfloat16* __restrict__ tokens, int C, int H,
+    int W, int P, int D, int L, int extras, int normalize_t) {
+    extern __shared__ float emb_smem[];  // patchT[pd][16]
+    const int Hp = H / P;
+    const int b = blockIdx.x / Hp, hh = blockIdx.x % Hp;
+    const int pd = C * P * P;
+    // gather: k = (c*P + p1)*P + p2 ; token ww ; pixel (c, hh*P+p1, ww*P+p2)
+    for (int i = threadIdx.x; i < C * P * W; i += blockDim.x) {
+        const int col = i % W, rp = i / W;  // rp = c*P + p1
+        const int c = rp / P, p1 = rp % P;
+        const float v = x_img[(((size_t)b * C + c) * H + hh * P + p1) * W + col];
+        const int ww = col / P, p2 = col % P;
+        emb_smem[(rp * P + p2) * EMB_TOK + ww] = v;
+    }
+    __syncthreads();
+    for (int e2 = threadIdx.x; e2 < D / 2; e2 += blockDim.x) {
+        const int e = e2 * 2;
+        float acc0[EMB_TOK], acc1[EMB_TOK];
+        const float b0 = pe_bias[e], b1 = pe_bias[e + 1];
+#pragma unroll
+        for (int t = 0; t < EMB_TOK; ++t) acc0[t] = b0, acc1[t] = b1;
+        for (int k = 0; k < pd; ++k) {
+            const float2 w = *reinterpret_cast<const float2*>(Wt + (size_t)k * D + e);
+            const float4* pr = reinterpret_cast<const float4*>(emb_smem + k * EMB_TOK);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 pv = pr[q];
+                acc0[q * 4 + 0] = fmaf(w.x, pv.x, acc0[q * 4 + 0]);
+                acc0[q * 4 + 1] = fmaf(w.x, pv.y, acc0[q * 4 + 1]);
+                acc0[q * 4 + 2] = fmaf(w.x, pv.z, acc0[q * 4 + 2]);
+                acc0[q * 4 + 3] = fmaf(w.x, pv.w, acc0[q * 4 + 3]);
+                acc1[q * 4 + 0] = fmaf(w.y, pv.x, acc1[q * 4 + 0]);
+                acc1[q * 4 + 1] = fmaf(w.y, pv.y, acc1[q * 4 + 1]);
+                acc1[q * 4 + 2] = fmaf(w.y, pv.z, acc1[q * 4 + 2]);
+                acc1[q * 4 + 3] = fmaf(w.y, pv.w, acc1[q * 4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < EMB_TOK; ++t) {
+            const int l = extras + hh * EMB_TOK + t;
+            const float2 pp = *reinterpret_cast<const float2*>(pos + (size_t)l * D + e);
+            *reinterpret_cast<uint32_t*>(tokens + ((size_t)b * L + l) * D + e) =
+                pack_bf16(acc0[t] + pp.x, acc1[t] + pp.y);
+        }
+    }
+    if (hh == 0) {
+        // time token: [cos(tau f_i) | sin(tau f_i)], f_i = exp(-ln(1e4) i / half)
+        const int half = D / 2;
+        float tau = tsteps[b];
+        if (normalize_t) tau = tau / 1000.f;
+        const int lt = extras - 1;
+        for (int e = threadIdx.x; e < D; e += blockDim.x) {
+            const int i = (e < half) ? e : e - half;
+            const float f = expf((-9.210340371976184f * (float)i) / (float)half);
+            const float arg = tau * f;
+            const float v = (e < half) ? cosf(arg) : sinf(arg);
+            tokens[((size_t)b * L + lt) * D + e] = __float2bfloat16_rn(v + pos[(size_t)lt * D + e]);
+            if (extras == 2) {
+                const long long cls = y[b];
+                tokens[((size_t)b * L) * D + e] = __float2bfloat16_rn(label_emb[(size_t)cls * D + e] + pos[e]);
+            }
+        }
+    }
+}
+
+// =====================================================================================================
+// LayerNorm row statistics (nn.LayerNorm, eps 1e-5; models/uvit.py:206-207,377) as (mean, M2) per row, and --
+// optionally -- the early-exit MLP probe's per-token sigmoid(w.x + b) (models/early_exit.py:34-37).
+// One warp per row, 16-byte loads, exact two-pass statistics in registers.
+// =====================================================================================================
+template <int D>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __restrict__ x, int M,
+                                                       const int* __restrict__ m_dev, float2* __restrict__ stats,
+                                                       const float* __restrict__ probe_w,
+                                                       const float* __restrict__ probe_b,
+                                                       float* __restrict__ probe_sig) {
+    constexpr int CH = D / 256;  // 16-byte chunks per lane
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int Mr = m_dev ? *m_dev : M;
+    if (row >= Mr) return;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
+    float v[CH][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const uint4 u = __ldg(xr + c * 32 + lane);
+        v[c][0] = bf16_lo(u.x), v[c][1] = bf16_hi(u.x), v[c][2] = bf16_lo(u.y), v[c][3] = bf16_hi(u.y);
+        v[c][4] = bf16_lo(u.z), v[c][5] = bf16_hi(u.z), v[c][6] = bf16_lo(u.w), v[c][7] = bf16_hi(u.w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[c][e];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)D;
+    float m2 = 0.f, dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float d = v[c][e] - mean;
+            m2 = fmaf(d, d, m2);
+        }
+        if (probe_w) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(probe_w) + (c * 32 + lane) * 2);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(probe_w) + (c * 32 + lane) * 2 + 1);
+            dot += v[c][0] * w0.x + v[c][1] * w0.y + v[c][2] * w0.z + v[c][3] * w0.w + v[c][4] * w1.x +
+                   v[c][5] * w1.y + v[c][6] * w1.z + v[c][7] * w1.w;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if (lane == 0) {
+        stats[row] = make_float2(mean, m2);
+        if (probe_w) probe_sig[row] = 1.f / (1.f + expf(-(dot + probe_b[0])));
+    }
+}
+
+// =====================================================================================================
+// final_layer: 3x3 conv, pad 1 (models/uvit.py:329-333,382).  in/out [B,C,H,W] fp32.  One CTA per
+// (sample, 16-row band).  Optional fused DDPM update (see ddpm_step_kernel) when x_io != null.
+// =====================================================================================================
+constexpr int CONV_BAND = 16;
+__global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
+                                                      const float* __restrict__ bias, float* __restrict__ out, int C,
+                                                      int H, int W) {
+    extern __shared__ float conv_smem[];  // [C][CONV_BAND+2][W+2] then weights [C*C*9] + bias[C]
+    const int bands = H / CONV_BAND;
+    const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
+    const int SW = W + 2, SH = CONV_BAND + 2;
+    float* sw = conv_smem + C * SH * SW;
+    for (int i = threadIdx.x; i < C * SH * SW; i += blockDim.x) {
+        const int xx = i % SW - 1, yy = (i / SW) % SH - 1 + y0, c = i / (SW * SH);
+        conv_smem[i] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? in[(((size_t)b * C + c) * H + yy) * W + xx] : 0.f;
+    }
+    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x) sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * CONV_BAND * W; i += blockDim.x) {
+        const int xx = i % W, yy = (i / W) % CONV_BAND, co = i / (W * CONV_BAND);
+        float acc = sw[C * C * 9 + co];
+        for (int ci = 0; ci < C; ++ci) {
+            const float* sp = conv_smem + (ci * SH + yy) * SW + xx;
+            const float* wp = sw + (co * C + ci) * 9;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) acc = fmaf(wp[dy * 3 + dx], sp[dy * SW + dx], acc);
+        }
+        out[(((size_t)b * C + co) * H + y0 + yy) * W + xx] = acc;
+    }
+}
+
+// =====================================================================================================
+// DDPM update (sampler.py:47-79, eesampler.py:74-82, ddpm_core.py:190-193), one kernel, 128-bit accesses:
+//   x' = ca[t]*x + cb[t]*model_out + cs[t]*z        (z ~ N(0,I), absent at t == 0)
+// The three per-timestep coefficients are tabulated on the host with the reference's own torch expressions:
+//   predict_noise:    x' = sqrt(1/a)*(x - ((1-a)/sqrt(1-abar))*eps) + sigma*z is evaluated in that exact order
+//   (mode 0) to stay within 1 ulp of the reference; mode 1 uses the generic two-term form for the other rules.
+// coef layout: [1000][4] = {c0, c1, sigma, unused}
+// Noise: injected tensor z_all[t] (parity) or Philox4x32-10 + Box-Muller keyed by (seed, t, element).
+// =====================================================================================================
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+__device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float& n0, float& n1) {
+    const float a = ((float)u0 + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+    const float b = ((float)u1 + 0.5f) * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.f * logf(a));
+    float s, c;
+    sincosf(6.283185307179586f * b, &s, &c);
+    n0 = r * c, n1 = r * s;
+}
+
+__global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ model_out,
+                                                        const float* __restrict__ z_all, size_t n, size_t z_stride,
+                                                        const float* __restrict__ coef, const int* __restrict__ t_dev,
+                                                        int t_host, int mode, unsigned long long seed,
+                                                        float* __restrict__ x_save) {
+    const int t = t_dev ? *t_dev : t_host;
+    const float c0 = coef[t * 4 + 0], c1 = coef[t * 4 + 1], sg = coef[t * 4 + 2];
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 * 4 >= n) return;
+    float4 xv = reinterpret_cast<const float4*>(x)[i4];
+    const float4 ev = reinterpret_cast<const float4*>(model_out)[i4];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t > 0) {
+        if (z_all) {
+            zv = reinterpret_cast<const float4*>(z_all + (size_t)t * z_stride)[i4];
+        } else {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)t, 0x5eedu, (uint32_t)seed,
+                          (uint32_t)(seed >> 32), r);
+            box_muller(r[0], r[1], zv.x, zv.y);
+            box_muller(r[2], r[3], zv.z, zv.w);
+        }
+    }
+    float4 o;
+    if (mode == 0) {
+        // sqrt(1/alpha) * (x - coeff*eps) + sigma*z, evaluated like the reference (no contraction across the adds)
+        o.x = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.x, __fmul_rn(c1, ev.x))), __fmul_rn(sg, zv.x));
+        o.y = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.y, __fmul_rn(c1, ev.y))), __fmul_rn(sg, zv.y));
+        o.z = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.z, __fmul_rn(c1, ev.z))), __fmul_rn(sg, zv.z));
+        o.w = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.w, __fmul_rn(c1, ev.w))), __fmul_rn(sg, zv.w));
+    } else {
+        // (c1*out + c0*x) + sigma*z   -- predict_original (sampler.py:69-72) / predict_previous (c0=0, c1=1)
+        o.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.x), __fmul_rn(c0, xv.x)), __fmul_rn(sg, zv.x));
+        o.y = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.y), __fmul_rn(c0, xv.y)), __fmul_rn(sg, zv.y));
+        o.z = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.z), __fmul_rn(c0, xv.z)), __fmul_rn(sg, zv.z));
+        o.w = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.w), __fmul_rn(c0, xv.w)), __fmul_rn(sg, zv.w));
+    }
+    reinterpret_cast<float4*>(x)[i4] = o;
+    if (x_save) reinterpret_cast<float4*>(x_save)[i4] = o;
+}
+
+// step bookkeeping for graph replay: t_vec[b] = float(*t_dev) for the next forward; (*t_dev) -= 1 after a step
+__global__ void fill_t_kernel(const int* __restrict__ t_dev, float* __restrict__ t_vec, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) t_vec[i] = (float)(*t_dev);
+}
+__global__ void dec_t_kernel(int* t_dev) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev -= 1;
+}
+
+// samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146)
+__global__ void finalize_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int C, int H,
+                                     int W) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)B * C * H * W;
+    if (i >= n) return;
+    const int c = i % C;
+    size_t r = i / C;
+    const int w = r % W;
+    r /= W;
+    const int h = r % H;
+    const int b = r / H;
+    out[i] = (x[(((size_t)b * C + c) * H + h) * W + w] + 1.f) / 2.f;
+}
+
+// =====================================================================================================
+// Early exit (eesampler.py:62-72): probe score per (layer, sample) = mean over tokens of the per-token sigmoid.
+// =====================================================================================================
+// probe_sig [M] (one layer) -> score[b] = mean_l sig[b*L + l]; deterministic tree order.
+__global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict__ sig, int L,
+                                                         float* __restrict__ score /*[B]*/) {
+    const int b = blockIdx.x;
+    float s = 0.f;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) s += sig[(size_t)b * L + l];
+    __shared__ float red[4];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) score[b] = (red[0] + red[1] + red[2] + red[3]) / (float)L;
+}
+
+// simulate mode: scores [depth][B], heads [depth+1][B][chw] (last = full model) -> exit index + selected eps
+__global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict__ scores,
+                                                        const float* __restrict__ outputs, int depth, int B,
+                                                        size_t chw, float threshold, float* __restrict__ eps,
+                                                        int* __restrict__ exit_idx) {
+    const int b = blockIdx.y;
+    int idx = depth;
+    for (int i = 0; i < depth; ++i) {
+        if (scores[(size_t)i * B + b] <= threshold) {
+            idx = i;
+            break;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) exit_idx[b] = idx;
+    const float4* src = reinterpret_cast<const float4*>(outputs + ((size_t)idx * B + b) * chw);
+    float4* dst = reinterpret_cast<float4*>(eps + (size_t)b * chw);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw / 4; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+}  // namespace ddb

@@ -1,0 +1,126 @@
+/* duodiff_b200 — C ABI of the B200-native DuoDiff sampling path.
+ *
+ * The reference (razvanmatisan/duodiff) has no FFI layer: its "operator API" for this path is the Python
+ * module surface.  Each entry point below names the reference interface it replaces (file:line relative to
+ * the reference root).  The Python shims in duodiff_b200/ bind these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative ddb_status; ddb_last_error() returns a
+ * thread-local message for the last failure.  All pointers named *_dev are CUDA device pointers owned by the
+ * caller; the library never allocates caller-visible memory.  `stream` is a cudaStream_t passed as void*.
+ * One handle = one device = one stream at a time (handles are not re-entrant; distinct handles are independent).
+ * There is no CPU fallback: on a machine without an sm_100 device every compute call fails with DDB_ERR_CUDA.
+ */
+#ifndef DUODIFF_B200_H
+#define DUODIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DDB_OK = 0,
+    DDB_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    DDB_ERR_CUDA = -2,        /* CUDA runtime or driver error */
+    DDB_ERR_MISSING_KEY = -3, /* a state_dict tensor required by the config was not supplied */
+    DDB_ERR_SHAPE = -4        /* tensor size does not match the config */
+} ddb_status;
+
+/* UViT(**model_params) — models/uvit.py:229-247 (+ EarlyExitUViT, models/early_exit.py:206-266). */
+typedef struct {
+    int32_t img_size;
+    int32_t patch_size;
+    int32_t in_chans;
+    int32_t embed_dim;            /* multiple of 256; head_dim = embed_dim / num_heads must be 64 */
+    int32_t depth;                /* odd: depth/2 in-blocks + mid + depth/2 out-blocks */
+    int32_t num_heads;
+    int32_t mlp_hidden;           /* int(embed_dim * mlp_ratio) */
+    int32_t num_classes;          /* <= 0: unconditional (extras = 1), else class-conditional (extras = 2) */
+    int32_t normalize_timesteps;  /* models/uvit.py:352-353 */
+    int32_t early_exit;           /* 1: weights carry the EarlyExitUViT prefix `uvit.` + probes + heads */
+    int32_t max_batch;            /* workspace is sized for this many samples */
+    float ln_eps;                 /* nn.LayerNorm default 1e-5 */
+} ddb_uvit_config;
+
+/* One entry of the reference state_dict (Q16 of SURVEY.md): fp32, contiguous, on the device. */
+typedef struct {
+    const char* name;    /* state_dict key, e.g. "in_blocks.0.attn.qkv.weight" */
+    const float* data_dev;
+    int64_t numel;
+} ddb_tensor;
+
+typedef struct ddb_model ddb_model;
+typedef struct ddb_sampler ddb_sampler;
+
+const char* ddb_version(void);
+const char* ddb_last_error(void);
+
+/* Re-packs the fp32 state_dict into bf16 GEMM layouts (LayerNorm folded), allocates the workspace and encodes
+ * the TMA descriptors.  Replaces: UViT.__init__ + load_state_dict + .to(device) (sampler.py:271-302). */
+int ddb_model_create(const ddb_uvit_config* cfg, const ddb_tensor* tensors, int32_t n_tensors, ddb_model** out);
+void ddb_model_destroy(ddb_model* m);
+
+/* UViT.forward(x, timesteps, y) -> eps   (models/uvit.py:351-383)
+ *   x_dev [B,C,H,W] f32; t_dev [B] f32 (raw timesteps); y_dev [B] i64 or NULL; eps_dev [B,C,H,W] f32. */
+int ddb_uvit_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                     float* eps_dev, void* stream);
+
+/* EarlyExitUViT.forward (models/early_exit.py:268-320) fused with the selection of eesampler.py:62-68.
+ *   eps_dev      [B,C,H,W] f32   eps of the first layer whose probe <= threshold (full model if none)
+ *   exit_idx_dev [B] i32         that layer index (depth = no exit)
+ *   scores_dev   [depth,B] f32   classifier_outputs (NULL to skip)
+ *   outputs_dev  [depth+1,B,C,H,W] f32 all head outputs + full-model output (NULL to skip)
+ * mode 0 = simulate (reference semantics: every layer, probe and head is evaluated);
+ * mode 1 = compact (exited samples stop consuming work; scores/outputs past a sample's exit are not produced). */
+int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                   float threshold, int32_t mode, float* eps_dev, int32_t* exit_idx_dev, float* scores_dev,
+                   float* outputs_dev, void* stream);
+
+/* One DDPM update (sampler.py:47-79 / eesampler.py:74-82 / ddpm_core.py:190-193), in place on x_dev.
+ *   coef_dev [1000,4] f32 per-timestep {c0, c1, sigma, 0}; mode 0: c0*(x - c1*out) + sigma*z (predict_noise),
+ *   mode 1: (c1*out + c0*x) + sigma*z (predict_original / predict_previous).
+ *   z_dev: this step's noise [n] or NULL (Philox from `seed`); ignored at t == 0 (z = 0). */
+int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, const float* coef_dev, int32_t t,
+                  int32_t mode, uint64_t seed, int64_t n, void* stream);
+
+/* get_samples() DDPM loop (sampler.py:128-139 incl. the model hand-off :135-136; eesampler.py:57-82).
+ *   late may be NULL.  switch_t = 1000 - t_switch when the hand-off can trigger (1 <= t_switch <= 1000), else -1:
+ *   `early` runs the steps with t >= switch_t, `late` the rest.
+ *   ee_threshold < 0: plain U-ViT forward; otherwise `early` is an early-exit model (ee_mode as above). */
+int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int32_t B, const float* coef_host,
+                       int32_t step_mode, float ee_threshold, int32_t ee_mode, ddb_sampler** out);
+void ddb_sampler_destroy(ddb_sampler* s);
+/* Runs steps t = t_first, t_first-1, ..., t_last in place on x_dev.
+ *   z_all_dev: injected noise [1000, n] indexed by t, or NULL (Philox, `seed`).
+ *   eps_trace_dev / x_trace_dev: optional [n_steps, n] per-step model output / x_{t-1} (parity tests).
+ *   exit_idx_trace_dev [n_steps, B] i32, score_mean_trace_dev [n_steps, depth] f32 (eesampler.py:71-72 logs).
+ *   use_graph != 0 replays one captured CUDA graph per backbone (traces must be NULL). */
+int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                    int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
+                    int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream);
+/* samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146). */
+int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t ddb_launch_count(void);
+
+/* ---- single-operator entry points (used by the parity tests; same kernels as the model path) ---- */
+/* out[M,N] = epi([A0|A1] W^T); bf16 row-major operands.  epi: 0 bias, 1 LN-fold, 2 LN-fold+GELU, 3 bias+residual */
+int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const float* bias_dev,
+                const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
+                const void* residual_dev, void* out_dev, int32_t M, int32_t N, int32_t K0, int32_t K1, int32_t epi,
+                void* stream);
+/* softmax(q k^T / 8) v over qkv [B*L, 3*H*64] bf16 -> out [B*L, H*64] bf16 (models/uvit.py:159-164) */
+int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, void* stream);
+/* per-row (mean, M2) of x [M, D] bf16 -> stats [M,2] f32 */
+int ddb_op_ln_stats(const void* x_dev, int32_t M, int32_t D, float* stats_dev, void* stream);
+/* W' = bf16(W*gamma), colsum, bias' (LayerNorm folding) for W [N,K] f32 */
+int ddb_op_pack_linear(const float* w_dev, const float* bias_dev, const float* gamma_dev, const float* beta_dev,
+                       int32_t N, int32_t K, void* wp_dev, float* colsum_dev, float* bias_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUODIFF_B200_H */
