@@ -34,6 +34,7 @@ _SIGS = {
     "ddb_model_create": (C.c_int, [C.POINTER(UViTConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
     "ddb_model_destroy": (None, [_P]),
     "ddb_uvit_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
+    "ddb_profile_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "ddb_ee_forward": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P, _P]),
     "ddb_ddpm_step": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_uint64, C.c_int64, _P]),
     "ddb_sampler_create": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_float, C.c_int32,

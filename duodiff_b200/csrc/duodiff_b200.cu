@@ -51,6 +51,42 @@ static int fail(int code, const char* fmt, ...) {
                         __LINE__);                                                                          \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------ profiling
+// Optional per-launch CUDA-event timing of one forward (ddb_profile_forward): events are recorded on the launching
+// stream around every kernel and accumulated per category.
+enum ProfCat : int {
+    PC_EMBED = 0, PC_LN_STATS, PC_GEMM_QKV, PC_ATTENTION, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_SKIP,
+    PC_GEMM_DECODE, PC_CONV, PC_EE_OTHER, PC_DDPM, PC_COUNT
+};
+struct Profiler {
+    bool active = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> pool;
+    std::vector<int> cats;
+    size_t used = 0;
+    cudaEvent_t next() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void begin(int cat) {
+        if (!active) return;
+        cats.push_back(cat);
+        cudaEventRecord(next(), st);
+    }
+    void end() {
+        if (active) cudaEventRecord(next(), st);
+    }
+};
+static Profiler g_prof;
+struct ProfScope {
+    explicit ProfScope(int cat) { g_prof.begin(cat); }
+    ~ProfScope() { g_prof.end(); }
+};
+
 // ------------------------------------------------------------------------------------------------ device info
 struct DeviceInfo {
     int num_sms = 0;
@@ -133,6 +169,7 @@ static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_de
                            const float* pb, float* psig, cudaStream_t st) {
     const int grid = (M + 7) / 8;
     if (grid <= 0) return DDB_OK;
+    ProfScope ps(PC_LN_STATS);
     switch (D) {
         case 256: ln_stats_kernel<256><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
         case 512: ln_stats_kernel<512><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
@@ -452,6 +489,7 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
 static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st) {
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
     const int smem = (C * (CONV_BAND + 2) * (W + 2) + C * C * 9 + C) * 4;
+    ProfScope ps(PC_CONV);
     conv3x3_kernel<<<B * (H / CONV_BAND), 256, smem, st>>>(in, hw.conv_w->as<float>(), hw.conv_b->as<float>(), out,
                                                             C, H, W);
     LAUNCH_CHECK();
@@ -468,11 +506,14 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
     float2* st2 = m->stats->as<float2>();
 
-    embed_tokens_kernel<<<B * (c.img_size / c.patch_size), 256, m->pd * EMB_TOK * 4, st>>>(
-        x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),
-        m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(), c.in_chans,
-        c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps);
-    LAUNCH_CHECK();
+    {
+        ProfScope ps(PC_EMBED);
+        embed_tokens_kernel<<<B * (c.img_size / c.patch_size), 256, m->pd * EMB_TOK * 4, st>>>(
+            x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),
+            m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(),
+            c.in_chans, c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps);
+        LAUNCH_CHECK();
+    }
 
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     for (int i = 0; i < c.depth; ++i) {
@@ -483,47 +524,74 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             // probe i + head i look at the block input (models/early_exit.py:294-296)
             DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
                                     m->probe_sig->as<float>(), st));
-            probe_mean_kernel<<<B, 128, 0, st>>>(m->probe_sig->as<float>(), m->L,
-                                                 m->scores->as<float>() + (size_t)i * B);
-            LAUNCH_CHECK();
+            {
+                ProfScope ps(PC_EE_OTHER);
+                probe_mean_kernel<<<B, 128, 0, st>>>(m->probe_sig->as<float>(), m->L,
+                                                     m->scores->as<float>() + (size_t)i * B);
+                LAUNCH_CHECK();
+            }
             GemmArgs hd = m->head_dec[i];
             hd.M = M;
-            DDB_TRY(launch_gemm(hd, EPI_DECODE, nsm, st));
+            {
+                ProfScope ps(PC_GEMM_DECODE);
+                DDB_TRY(launch_gemm(hd, EPI_DECODE, nsm, st));
+            }
             DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(),
                              m->outputs->as<float>() + (size_t)i * B * m->chw, B, st));
             have_stats = true;
         }
         if (bw.has_skip) {
             op.skip.M = M;
-            DDB_TRY(launch_gemm(op.skip, EPI_BIAS, nsm, st));
+            {
+                ProfScope ps(PC_GEMM_SKIP);
+                DDB_TRY(launch_gemm(op.skip, EPI_BIAS, nsm, st));
+            }
             cur = m->xs->as<__nv_bfloat16>();
             have_stats = false;
         }
         if (!have_stats) DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
         op.qkv.M = M;
-        DDB_TRY(launch_gemm(op.qkv, EPI_LN, nsm, st));
-        DDB_TRY(launch_attention(m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), B, m->L, m->Hh, st));
+        {
+            ProfScope ps(PC_GEMM_QKV);
+            DDB_TRY(launch_gemm(op.qkv, EPI_LN, nsm, st));
+        }
+        {
+            ProfScope ps(PC_ATTENTION);
+            DDB_TRY(launch_attention(m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), B, m->L, m->Hh, st));
+        }
         op.proj.M = M;
-        DDB_TRY(launch_gemm(op.proj, EPI_RES, nsm, st));
+        {
+            ProfScope ps(PC_GEMM_PROJ);
+            DDB_TRY(launch_gemm(op.proj, EPI_RES, nsm, st));
+        }
         DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
         op.fc1.M = M;
-        DDB_TRY(launch_gemm(op.fc1, EPI_LN_GELU, nsm, st));
+        {
+            ProfScope ps(PC_GEMM_FC1);
+            DDB_TRY(launch_gemm(op.fc1, EPI_LN_GELU, nsm, st));
+        }
         op.fc2.M = M;
-        DDB_TRY(launch_gemm(op.fc2, EPI_RES, nsm, st));
+        {
+            ProfScope ps(PC_GEMM_FC2);
+            DDB_TRY(launch_gemm(op.fc2, EPI_RES, nsm, st));
+        }
         cur = m->xo[i]->as<__nv_bfloat16>();
     }
     (void)half;
     DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
     GemmArgs fd = m->final_dec;
     fd.M = M;
-    DDB_TRY(launch_gemm(fd, EPI_DECODE, nsm, st));
+    {
+        ProfScope ps(PC_GEMM_DECODE);
+        DDB_TRY(launch_gemm(fd, EPI_DECODE, nsm, st));
+    }
     DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
     return DDB_OK;
 }
 
 static int ee_forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float threshold,
                            int mode, float* eps, int32_t* exit_idx, float* scores_out, float* outputs_out,
-                           cudaStream_t st) {
+                           const int* t_dev, int32_t* exit_log, cudaStream_t st) {
     if (!m->cfg.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
     if (mode != 0) return fail(DDB_ERR_INVALID, "ee mode %d not implemented yet (0 = simulate)", mode);
     const int depth = m->cfg.depth;
@@ -532,7 +600,7 @@ static int ee_forward_impl(ddb_model* m, const float* x, const float* t, const i
     int32_t* idx = exit_idx ? exit_idx : m->exit_idx->as<int32_t>();
     dim3 grid((unsigned)((m->chw / 4 + 255) / 256), (unsigned)B);
     ee_select_kernel<<<grid, 256, 0, st>>>(m->scores->as<float>(), m->outputs->as<float>(), depth, B, m->chw,
-                                           threshold, eps, idx);
+                                           threshold, eps, idx, t_dev, exit_log);
     LAUNCH_CHECK();
     if (scores_out)
         CUDA_TRY(cudaMemcpyAsync(scores_out, m->scores->p, (size_t)depth * B * 4, cudaMemcpyDeviceToDevice, st));
@@ -551,18 +619,20 @@ struct ddb_sampler {
     size_t n = 0;
     Buf coef, t_dev, t_vec, eps, score_mean;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    const void* graph_key[2][4] = {{nullptr}};
+    long long graph_nodes[2] = {0, 0};
+    const void* graph_key[2][5] = {{nullptr}};
     unsigned long long graph_seed[2] = {0, 0};
 };
 
 __global__ void set_t_kernel(int* t_dev, int t) { *t_dev = t; }
 // eesampler.py:71  error_prediction_by_timestep[t] = classifier_outputs.mean(axis=1)[:depth]
-__global__ void score_mean_kernel(const float* __restrict__ scores, int depth, int B, float* __restrict__ out) {
+__global__ void score_mean_kernel(const float* __restrict__ scores, int depth, int B, const int* __restrict__ t_dev,
+                                  float* __restrict__ out /*[1000,depth] by t*/) {
     const int i = blockIdx.x;
     float s = 0.f;
     for (int b = threadIdx.x; b < B; b += 32) s += scores[(size_t)i * B + b];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) out[i] = s / (float)B;
+    if (threadIdx.x == 0) out[(size_t)(*t_dev) * depth + i] = s / (float)B;
 }
 
 // one sampling step on the stream: forward + update (+ bookkeeping). t comes from s->t_dev (device).
@@ -574,10 +644,11 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y
     LAUNCH_CHECK();
     float* eps = eps_save ? eps_save : s->eps->as<float>();
     if (s->ee_threshold >= 0.f && m->cfg.early_exit) {
-        DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, exit_save,
-                                nullptr, nullptr, st));
+        DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, nullptr,
+                                nullptr, nullptr, s->t_dev->as<int>(), exit_save, st));
         if (score_save) {
-            score_mean_kernel<<<m->cfg.depth, 32, 0, st>>>(m->scores->as<float>(), m->cfg.depth, B, score_save);
+            score_mean_kernel<<<m->cfg.depth, 32, 0, st>>>(m->scores->as<float>(), m->cfg.depth, B,
+                                                           s->t_dev->as<int>(), score_save);
             LAUNCH_CHECK();
         }
     } else {
@@ -625,12 +696,32 @@ int ddb_uvit_forward(ddb_model* m, const float* x_dev, const float* t_dev, const
     return forward_impl(m, x_dev, t_dev, y_dev, B, eps_dev, false, (cudaStream_t)stream);
 }
 
+int ddb_profile_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                        float* eps_dev, int32_t ee, float* ms_host, int32_t* launches_host, void* stream) {
+    if (!m || !x_dev || !t_dev || !eps_dev || !ms_host || !launches_host) return fail(DDB_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    g_prof.active = true, g_prof.st = st, g_prof.used = 0;
+    g_prof.cats.clear();
+    int r = forward_impl(m, x_dev, t_dev, y_dev, B, eps_dev, ee != 0, st);
+    g_prof.active = false;
+    if (r != DDB_OK) return r;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < PC_COUNT; ++i) ms_host[i] = 0.f, launches_host[i] = 0;
+    for (size_t i = 0; i < g_prof.cats.size(); ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]));
+        ms_host[g_prof.cats[i]] += ms;
+        launches_host[g_prof.cats[i]] += 1;
+    }
+    return DDB_OK;
+}
+
 int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
                    float threshold, int32_t mode, float* eps_dev, int32_t* exit_idx_dev, float* scores_dev,
                    float* outputs_dev, void* stream) {
     if (!m || !x_dev || !t_dev || !eps_dev) return fail(DDB_ERR_INVALID, "null argument");
     return ee_forward_impl(m, x_dev, t_dev, y_dev, B, threshold, mode, eps_dev, exit_idx_dev, scores_dev, outputs_dev,
-                           (cudaStream_t)stream);
+                           nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, const float* coef_dev, int32_t t,
@@ -676,8 +767,8 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
     if (!s || !x_dev) return fail(DDB_ERR_INVALID, "null argument");
     if (t_first > 999 || t_last < 0 || t_last > t_first) return fail(DDB_ERR_INVALID, "bad step range");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool tracing = eps_trace_dev || x_trace_dev || exit_idx_trace_dev || score_mean_trace_dev;
-    if (use_graph && tracing) return fail(DDB_ERR_INVALID, "per-step traces need use_graph=0");
+    if (use_graph && (eps_trace_dev || x_trace_dev))
+        return fail(DDB_ERR_INVALID, "per-step eps/x traces need use_graph=0");
     set_t_kernel<<<1, 1, 0, st>>>(s->t_dev->as<int>(), t_first);
     LAUNCH_CHECK();
     if (!use_graph) {
@@ -686,9 +777,7 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
             DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, t,
                                  eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
                                  x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr,
-                                 exit_idx_trace_dev ? exit_idx_trace_dev + (size_t)k * s->B : nullptr,
-                                 score_mean_trace_dev ? score_mean_trace_dev + (size_t)k * s->early->cfg.depth : nullptr,
-                                 st));
+                                 exit_idx_trace_dev, score_mean_trace_dev, st));
         }
         return DDB_OK;
     }
@@ -696,7 +785,7 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
     for (int which = 0; which < 2; ++which) {
         ddb_model* m = which == 0 ? s->early : s->late;
         if (!m) continue;
-        const void* key[4] = {x_dev, y_dev, z_all_dev, st};
+        const void* key[5] = {x_dev, y_dev, z_all_dev, exit_idx_trace_dev, score_mean_trace_dev};
         if (s->graph[which] && (memcmp(key, s->graph_key[which], sizeof(key)) != 0 || s->graph_seed[which] != seed)) {
             cudaGraphExecDestroy(s->graph[which]);
             s->graph[which] = nullptr;
@@ -706,7 +795,10 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
             CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
             CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-            int r = sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, 0, nullptr, nullptr, nullptr, nullptr, cs);
+            const long long before = g_launches.load();
+            int r = sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, 0, nullptr, nullptr, exit_idx_trace_dev,
+                                 score_mean_trace_dev, cs);
+            g_launches.store(before);  // captured, not executed: replays are counted below
             cudaError_t e = cudaStreamEndCapture(cs, &g);
             if (r != DDB_OK) {
                 if (g) cudaGraphDestroy(g);
@@ -717,6 +809,9 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
                 cudaStreamDestroy(cs);
                 return fail(DDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
             }
+            size_t n_nodes = 0;
+            cudaGraphGetNodes(g, nullptr, &n_nodes);
+            s->graph_nodes[which] = (long long)n_nodes;
             e = cudaGraphInstantiate(&s->graph[which], g, 0);
             cudaGraphDestroy(g);
             cudaStreamDestroy(cs);
@@ -728,6 +823,7 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
     for (int t = t_first; t >= t_last; --t) {
         const int which = (s->late && t < s->switch_t) ? 1 : 0;
         CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
+        g_launches.fetch_add(s->graph_nodes[which], std::memory_order_relaxed);
     }
     return DDB_OK;
 }

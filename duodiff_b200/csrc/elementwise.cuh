@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict__ scores,
                                                         const float* __restrict__ outputs, int depth, int B,
                                                         size_t chw, float threshold, float* __restrict__ eps,
-                                                        int* __restrict__ exit_idx) {
+                                                        int* __restrict__ exit_idx, const int* __restrict__ t_dev,
+                                                        int* __restrict__ exit_log /*[1000,B] by t, or null*/) {
     const int b = blockIdx.y;
     int idx = depth;
     for (int i = 0; i < depth; ++i) {
@@ -334,7 +335,10 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
             break;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) exit_idx[b] = idx;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        exit_idx[b] = idx;
+        if (exit_log) exit_log[(size_t)(t_dev ? *t_dev : 0) * B + b] = idx;
+    }
     const float4* src = reinterpret_cast<const float4*>(outputs + ((size_t)idx * B + b) * chw);
     float4* dst = reinterpret_cast<float4*>(eps + (size_t)b * chw);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw / 4; i += (size_t)gridDim.x * blockDim.x)

@@ -1,0 +1,109 @@
+"""DDPM schedule + the Python owner of a ``ddb_sampler`` handle (the whole t-loop runs inside the C library)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .engine import Engine
+
+RULES = ("predict_noise", "predict_original", "predict_previous")
+
+
+def schedule() -> dict:
+    """The five schedule vectors, built with the reference's own torch calls (sampler.py:40-44) on the host so the
+    coefficient table is bit-identical to a CPU run of the reference."""
+    betas = torch.linspace(1e-4, 0.02, 1000)
+    alphas = 1 - betas
+    alphas_bar = torch.cumprod(alphas, dim=0)
+    alphas_bar_previous = torch.cat([torch.tensor([1.0]), alphas_bar[:-1]])
+    betas_tilde = betas * (1 - alphas_bar_previous) / (1 - alphas_bar)
+    return dict(betas=betas, alphas=alphas, alphas_bar=alphas_bar, alphas_bar_previous=alphas_bar_previous,
+                betas_tilde=betas_tilde)
+
+
+def step_coefficients(rule: str = "predict_noise", variance: str = "beta_tilde"):
+    """[1000,4] fp32 table {c0, c1, sigma, 0} and the kernel's evaluation mode for a post-processing rule.
+
+    predict_noise    (sampler.py:47-56):  mode 0  x' = c0*(x - c1*eps) + sigma*z, c0 = sqrt(1/a), c1 = (1-a)/sqrt(1-abar)
+    predict_original (sampler.py:59-72):  mode 1  x' = (c1*out + c0*x) + sigma*z
+    predict_previous (sampler.py:75-79):  mode 1  with c0 = 0, c1 = 1
+    variance: 'beta_tilde' (sampler.py:50, eesampler.py:76) or 'beta' (ddpm_core.py:56-79 default)."""
+    s = schedule()
+    var = s["betas_tilde"] if variance == "beta_tilde" else s["betas"]
+    sigma = torch.sqrt(var)
+    if rule == "predict_noise":
+        c0 = torch.sqrt(1 / s["alphas"])
+        c1 = (1 - s["alphas"]) / torch.sqrt(1 - s["alphas_bar"])
+        mode = 0
+    elif rule == "predict_original":
+        c1 = torch.sqrt(s["alphas_bar_previous"]) * s["betas"] / (1 - s["alphas_bar"])
+        c0 = torch.sqrt(s["alphas"]) * (1 - s["alphas_bar_previous"]) / (1 - s["alphas_bar"])
+        mode = 1
+    elif rule == "predict_previous":
+        c0, c1, mode = torch.zeros(1000), torch.ones(1000), 1
+    else:
+        raise ValueError(f"unknown parametrization {rule!r}; expected one of {RULES}")
+    table = torch.stack([c0, c1, sigma, torch.zeros(1000)], dim=1).to(torch.float32).contiguous()
+    return table, mode
+
+
+def switch_step(t_switch) -> int:
+    """sampler.py:135-136: the swap happens after the step at t == 1000 - t_switch, i.e. `early` runs t >= 1000 -
+    t_switch.  The equality can only trigger for integral 1 <= t_switch <= 1000; otherwise the early model runs
+    the whole trajectory (the reference default t_switch=inf)."""
+    try:
+        ts = float(t_switch)
+    except (TypeError, ValueError):
+        return -1
+    if ts != ts or ts in (float("inf"), float("-inf")) or ts != int(ts):
+        return -1
+    ts = int(ts)
+    return 1000 - ts if 1 <= ts <= 1000 else -1
+
+
+class Sampler:
+    """get_samples()' inner loop (sampler.py:128-139 / eesampler.py:57-82) as one C call."""
+
+    def __init__(self, early: Engine, late: Engine | None, t_switch, batch: int, rule: str = "predict_noise",
+                 variance: str = "beta_tilde", ee_threshold: float | None = None, ee_mode: int = 0):
+        self.lib = _lib.load()
+        self.early, self.late, self.batch = early, late, batch
+        table, mode = step_coefficients(rule, variance)
+        self.coef = table
+        handle = C.c_void_p()
+        _lib.check(self.lib.ddb_sampler_create(
+            early.handle, late.handle if late is not None else None, switch_step(t_switch) if late is not None else -1,
+            batch, table.data_ptr(), mode, -1.0 if ee_threshold is None else float(ee_threshold), ee_mode,
+            C.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self.lib.ddb_sampler_destroy(h)
+            self.handle = None
+
+    def run(self, x, y=None, noise=None, seed: int = 0, t_first: int = 999, t_last: int = 0, eps_trace=None,
+            x_trace=None, exit_log=None, score_log=None, use_graph: bool = True):
+        """In place on x [B,C,H,W] f32 cuda.  noise: None (device Philox) or [1000, *x.shape] f32 cuda indexed by t."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.batch
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
+            assert noise.shape[0] == 1000 and noise[0].numel() == x.numel()
+        if y is not None:
+            y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        graph = bool(use_graph) and eps_trace is None and x_trace is None
+        _lib.check(self.lib.ddb_sampler_run(
+            self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), t_first, t_last,
+            _lib.ptr(eps_trace), _lib.ptr(x_trace), _lib.ptr(exit_log), _lib.ptr(score_log), int(graph),
+            _lib.current_stream_ptr()))
+        return x
+
+    def finalize(self, x):
+        """(x + 1) / 2, 'b c h w -> b h w c' (sampler.py:145-146)."""
+        B, Cc, H, W = x.shape
+        out = torch.empty(B, H, W, Cc, device=x.device, dtype=torch.float32)
+        _lib.check(self.lib.ddb_finalize_nhwc(x.data_ptr(), out.data_ptr(), B, Cc, H, W, _lib.current_stream_ptr()))
+        return out

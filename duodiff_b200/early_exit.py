@@ -1,0 +1,70 @@
+"""Drop-in for the reference's ``models/early_exit.py`` interface: ``EarlyExitUViT(uvit, classifier_type, exit_threshold)``
+with the checkpoint layout of SURVEY.md Q16 (``uvit.*``, ``matrix.{i}.classifier.0.*``, ``in_blocks_heads.*``,
+``mid_block_head.*``, ``out_blocks_heads.*``) and ``forward -> (eps, [probe_i], [head_output_i])``
+(models/early_exit.py:268-320).  Only ``mlp_probe_per_layer`` (the type of every configs/deediff_*.yaml) has kernels.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .engine import Engine
+from .uvit import UViT
+
+
+class OutputHead(nn.Module):  # parameter names of models/early_exit.py:9-20
+    def __init__(self, embed_dim: int, patch_dim: int, in_chans: int, conv: bool = True):
+        super().__init__()
+        if not conv:
+            raise NotImplementedError("OutputHead(conv=False) has no kernel")
+        self.in_chans = in_chans
+        self.norm = nn.LayerNorm(embed_dim)
+        self.decoder_pred = nn.Linear(embed_dim, patch_dim, bias=True)
+        self.final_layer = nn.Conv2d(in_chans, in_chans, 3, padding=1)
+
+
+class MLPProbe(nn.Module):  # models/early_exit.py:31-34
+    def __init__(self, embed_dim: int):
+        super().__init__()
+        self.classifier = nn.Sequential(nn.Linear(embed_dim, 1), nn.Sigmoid())
+
+
+class EarlyExitUViT(nn.Module):
+    def __init__(self, uvit: UViT, classifier_type="attention_probe", exit_threshold=0.2):
+        super().__init__()
+        if classifier_type != "mlp_probe_per_layer":
+            raise NotImplementedError(
+                f"classifier_type={classifier_type!r}: only 'mlp_probe_per_layer' (configs/deediff_*.yaml) is on "
+                "the B200 path; the other probe variants are out of scope (SURVEY.md §2.1)")
+        self.uvit = uvit
+        self.exit_threshold = exit_threshold
+        self.classifier_type = classifier_type
+        d, half = uvit.embed_dim, uvit.depth // 2
+        self.matrix = nn.ModuleDict({f"{i}": MLPProbe(d) for i in range(uvit.depth)})
+        head = lambda: OutputHead(d, uvit.patch_dim, uvit.in_chans)  # noqa: E731
+        self.in_blocks_heads = nn.ModuleList([head() for _ in range(half)])
+        self.mid_block_head = head()
+        self.out_blocks_heads = nn.ModuleList([head() for _ in range(half)])
+        self._engine: Engine | None = None
+        self._engine_key = None
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def engine(self, batch: int) -> Engine:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or self._engine_key != key or self._engine.max_batch < batch:
+            self._engine = None
+            cap = max(batch, self.uvit.max_batch or 0)
+            self._engine = Engine(self.state_dict(), max_batch=cap, **self.uvit.engine_kwargs(early_exit=True))
+            self._engine_key = key
+        return self._engine
+
+    def forward(self, x, timesteps, y=None):
+        """models/early_exit.py:268-320: every probe and every head is evaluated (simulate mode)."""
+        with torch.no_grad():
+            use_y = y if self.uvit.label_emb is not None else None
+            _, _, scores, outputs = self.engine(x.shape[0]).ee_forward(x, timesteps, use_y, threshold=0.0, mode=0)
+        depth = self.uvit.depth
+        return outputs[depth], [scores[i] for i in range(depth)], [outputs[i] for i in range(depth)]

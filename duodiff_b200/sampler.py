@@ -1,0 +1,174 @@
+"""Drop-in for the reference's ``sampler.py``: same ``get_samples`` signature and CLI flags (sampler.py:82-155,192-252),
+but the 1000-step loop — U-ViT forwards, the DuoDiff hand-off after ``t == 1000 - t_switch`` and the per-step DDPM
+update — runs inside libduodiff_b200.so as CUDA-graph replays of hand-written sm_100a kernels.
+
+    python -m duodiff_b200.sampler --checkpoint_path early.pth --config_path configs/uvit_celeba_3.yaml \
+        --checkpoint_path_late full.pth --config_path_late configs/uvit_celeba.yaml --t_switch 300 \
+        --batch_size 128 --parametrization predict_noise --output_folder out/
+"""
+from __future__ import annotations
+
+import time
+from argparse import ArgumentParser
+from pathlib import Path
+from typing import List
+
+import numpy as np
+import torch
+
+from . import _io
+from .ddpm import RULES, Sampler
+from .uvit import UViT
+
+
+class _Rule:
+    """Stand-in for the reference's post-processing callables (sampler.py:47-79): identifies the update rule the
+    fused DDPM kernel applies; it is not called per step."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __repr__(self):
+        return f"<{self.name}_postprocessing>"
+
+
+predict_noise_postprocessing = _Rule("predict_noise")
+predict_original_postprocessing = _Rule("predict_original")
+predict_previous_postprocessing = _Rule("predict_previous")
+_BY_NAME = {r.name: r for r in (predict_noise_postprocessing, predict_original_postprocessing,
+                                predict_previous_postprocessing)}
+
+
+def _rule_name(postprocessing) -> str:
+    if isinstance(postprocessing, _Rule):
+        return postprocessing.name
+    if isinstance(postprocessing, str) and postprocessing in RULES:
+        return postprocessing
+    name = getattr(postprocessing, "__name__", "")
+    for r in RULES:  # the reference's own function objects are accepted by name
+        if name == f"{r}_postprocessing":
+            return r
+    raise ValueError(f"unsupported postprocessing {postprocessing!r}; expected one of {RULES}")
+
+
+def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels: int, sample_height: int,
+                sample_width: int, use_ddim: bool = False, ddim_steps: int = 50, ddim_eta: float = 0.0,
+                timesteps_save: List[int] = (), y=None, autoencoder=None, late_model=None, t_switch=np.inf, *,
+                noise=None, use_graph: bool = True, device=None):
+    """sampler.py:82-155.  Returns (samples [B,H,W,C] f32 numpy un-clipped, [intermediate samples]).
+
+    x_T is drawn on the CPU generator after ``seed_everything(seed)`` exactly like the reference (sampler.py:99-100);
+    the per-step z comes from an in-kernel Philox stream keyed by ``seed`` unless ``noise`` [1000,B,C,H,W] is
+    injected (parity tests).  DDIM and the KL autoencoder are later rows of SURVEY.md §8(f)."""
+    if use_ddim:
+        raise NotImplementedError("the DDIM branch (sampler.py:103-126) is a 'next' row, not built yet")
+    if autoencoder is not None:
+        raise NotImplementedError("KL-autoencoder decode (sampler.py:141-143) is a 'next' row, not built yet")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    _io.seed_everything(seed)
+    x = torch.randn(batch_size, num_channels, sample_height, sample_width)
+    x = x.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else x.to(dev)
+    with torch.cuda.device(dev):
+        early = model.engine(batch_size)
+        late = late_model.engine(batch_size) if late_model is not None else None
+        sampler = Sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
+        if noise is not None:
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        # reference: `if 1000 - t in timesteps_save` after the update at t -> save x after step t = 1000 - s
+        save_at = sorted({1000 - int(s) for s in timesteps_save if 0 <= 1000 - int(s) <= 999}, reverse=True)
+        kept, t_first = {}, 999
+        for t_stop in save_at + [0]:
+            if t_stop > t_first:
+                continue
+            sampler.run(x, y=y, noise=noise, seed=seed, t_first=t_first, t_last=t_stop, use_graph=use_graph)
+            if t_stop in save_at:
+                kept[t_stop] = sampler.finalize(x)
+            t_first = t_stop - 1
+            if t_first < 0:
+                break
+        samples = sampler.finalize(x)
+        out = samples.cpu().numpy()
+        # the reference appends in loop order (descending t), one entry per matching step
+        inter = [kept[t].cpu().numpy() for t in sorted(kept, reverse=True)]
+    return out, inter
+
+
+def dump_samples(samples, output_folder: Path, timestep=1000):
+    _io.dump_samples(samples, output_folder, timestep)
+
+
+def dump_statistics(elapsed_time, output_folder: Path):
+    """sampler.py:187-189."""
+    with open(Path(output_folder) / "statistics.txt", "w") as f:
+        f.write(f"Elapsed time: {elapsed_time} s\n")
+
+
+def get_args(argv=None):
+    p = ArgumentParser()
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--checkpoint_path", type=str, required=True, help="Path to checkpoint of the model")
+    p.add_argument("--checkpoint_path_late", type=str, default=None,
+                   help="Path to checkpoint of the model to be used in the latest steps")
+    p.add_argument("--batch_size", type=int, required=True)
+    p.add_argument("--parametrization", type=str, choices=list(RULES), required=True)
+    p.add_argument("--output_folder", type=str, required=True)
+    p.add_argument("--config_path", type=str, required=True, help="Path to yaml config file")
+    p.add_argument("--config_path_late", type=str, default=None,
+                   help="Path to yaml config file of the model to be used in the latest steps")
+    p.add_argument("--t_switch", type=int, default=np.inf,
+                   help="Sampling timestep where the model should be replaced by the late model")
+    p.add_argument("--class_id", type=int, default=None, help="Number up to 1000 that corresponds to a class")
+    p.add_argument("--use_ddim", action="store_true")
+    p.add_argument("--ddim_steps", type=int, default=50)
+    p.add_argument("--ddim_eta", type=float, default=0.0)
+    p.add_argument("--timesteps_save", type=int, nargs="+", default=[])
+    return p.parse_args(argv)
+
+
+def _build(config_path, checkpoint_path, batch_size, device):
+    cfg = _io.load_config(config_path)
+    net = UViT(**_io.uvit_kwargs(cfg), max_batch=batch_size)
+    _io.load_checkpoint_into(net, checkpoint_path)
+    return net.eval().to(device), cfg
+
+
+def main(argv=None):
+    args = get_args(argv)
+    out_dir = Path(args.output_folder)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    if not torch.cuda.is_available():
+        raise RuntimeError("duodiff_b200.sampler needs a B200 (sm_100) GPU; there is no CPU path")
+    device = torch.device("cuda:0")
+    print(f"Using device {device}")
+    model, cfg = _build(args.config_path, args.checkpoint_path, args.batch_size, device)
+    late = None
+    if args.checkpoint_path_late:
+        late, cfg = _build(args.config_path_late, args.checkpoint_path_late, args.batch_size, device)
+    mp = cfg["model_params"]
+    _io.seed_everything(args.seed)
+    # sampler.py:314-318 draws a *random* label per sample whenever --class_id is given (Q14); labels are taken
+    # modulo num_classes here because the reference's randint(1, 1001) overflows a 1000-row embedding.
+    y = None
+    if args.class_id is not None:
+        y = torch.randint(1, 1001, (args.batch_size,))
+        if mp.get("num_classes", -1) > 0:
+            y = y % mp["num_classes"]
+        y = y.to(device)
+    if "autoencoder" in cfg:
+        raise NotImplementedError("latent (ImageNet-256) decode through the KL autoencoder is a 'next' row")
+    tic = time.time()
+    samples, inter = get_samples(
+        model=model, batch_size=args.batch_size, postprocessing=_BY_NAME[args.parametrization], seed=args.seed,
+        num_channels=mp["in_chans"], sample_height=mp["img_size"], sample_width=mp["img_size"],
+        use_ddim=args.use_ddim, ddim_steps=args.ddim_steps, ddim_eta=args.ddim_eta, y=y, autoencoder=None,
+        late_model=late, t_switch=args.t_switch, timesteps_save=args.timesteps_save)
+    tac = time.time()
+    dump_statistics(tac - tic, out_dir)
+    dump_samples(samples, out_dir)
+    if args.timesteps_save:
+        for ts, s in zip(args.timesteps_save, inter):
+            dump_samples(s, out_dir, ts)
+
+
+if __name__ == "__main__":
+    main()

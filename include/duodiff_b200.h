@@ -68,6 +68,14 @@ void ddb_model_destroy(ddb_model* m);
 int ddb_uvit_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
                      float* eps_dev, void* stream);
 
+/* Same forward with a CUDA-event pair recorded on `stream` around every kernel launch; per-category device time
+ * (ms) and launch counts are returned in host arrays of DDB_PROF_CATEGORIES entries, in the order
+ * embed, ln_stats, gemm_qkv, attention, gemm_proj, gemm_fc1, gemm_fc2, gemm_skip, gemm_decode, conv, ee_other, ddpm.
+ * ee != 0 also evaluates probes and heads (early-exit model).  Used by bench.py for the roofline figures. */
+#define DDB_PROF_CATEGORIES 12
+int ddb_profile_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
+                        float* eps_dev, int32_t ee, float* ms_host, int32_t* launches_host, void* stream);
+
 /* EarlyExitUViT.forward (models/early_exit.py:268-320) fused with the selection of eesampler.py:62-68.
  *   eps_dev      [B,C,H,W] f32   eps of the first layer whose probe <= threshold (full model if none)
  *   exit_idx_dev [B] i32         that layer index (depth = no exit)
@@ -96,8 +104,9 @@ void ddb_sampler_destroy(ddb_sampler* s);
 /* Runs steps t = t_first, t_first-1, ..., t_last in place on x_dev.
  *   z_all_dev: injected noise [1000, n] indexed by t, or NULL (Philox, `seed`).
  *   eps_trace_dev / x_trace_dev: optional [n_steps, n] per-step model output / x_{t-1} (parity tests).
- *   exit_idx_trace_dev [n_steps, B] i32, score_mean_trace_dev [n_steps, depth] f32 (eesampler.py:71-72 logs).
- *   use_graph != 0 replays one captured CUDA graph per backbone (traces must be NULL). */
+ *   exit_idx_trace_dev [1000, B] i32 and score_mean_trace_dev [1000, depth] f32 are indexed by t like the
+ *   reference's indices_by_timestep / error_prediction_by_timestep logs (eesampler.py:54-55,71-72).
+ *   use_graph != 0 replays one captured CUDA graph per backbone (eps/x traces must then be NULL). */
 int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
                     int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
                     int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream);

@@ -1,0 +1,157 @@
+"""Generates the golden fixtures that pin ``oracle/`` to the reference implementation.
+
+Run ONLY in the build container (needs the read-only reference checkout):
+
+    python tests/golden/make_golden.py [/root/reference]
+
+It imports the *unmodified* reference modules (``models.uvit``, ``models.early_exit``, ``sampler``, ``eesampler``)
+with a stub ``matplotlib`` (not installed; only the PNG dump uses it), builds tiny random-init models with the
+reference's own constructors, runs the reference forward / samplers on the CPU and stores weights + inputs + outputs
+as compressed ``.npz`` files next to this script.  Nothing here is read at test time except the ``.npz`` files.
+"""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REF = Path(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")
+OUT = Path(__file__).resolve().parent
+
+stub, pp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+stub.pyplot = pp
+sys.modules.setdefault("matplotlib", stub)
+sys.modules.setdefault("matplotlib.pyplot", pp)
+sys.path.insert(0, str(REF))
+
+import eesampler as ref_ee  # noqa: E402
+import sampler as ref_sampler  # noqa: E402
+from models.early_exit import EarlyExitUViT  # noqa: E402
+from models.uvit import UViT  # noqa: E402
+
+TINY = dict(img_size=8, patch_size=2, in_chans=3, embed_dim=32, depth=3, num_heads=2, mlp_ratio=4, qkv_bias=False,
+            mlp_time_embed=False, num_classes=-1, normalize_timesteps=True)
+TINY_FULL = dict(TINY, depth=5)
+TINY_CLS = dict(TINY, num_classes=10, normalize_timesteps=False, in_chans=4, depth=5)
+
+
+def heat(model, seed):
+    """Random-init (std 0.02, zero bias, unit LN) leaves LayerNorm affine and biases untested: perturb them."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.1)
+            elif "pos_embed" in name:
+                p.add_(torch.randn(p.shape, generator=g) * 0.2)
+            else:
+                p.mul_(4.0)
+
+
+def sd_np(model, prefix="w::"):
+    return {prefix + k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def params_np(params):
+    return {f"p::{k}": np.asarray(v) for k, v in params.items()}
+
+
+def uvit_forward_fixture(name, params, seed, with_y):
+    torch.manual_seed(seed)
+    m = UViT(**params).eval()
+    heat(m, seed + 1)
+    B = 3
+    x = torch.randn(B, params["in_chans"], params["img_size"], params["img_size"])
+    t = torch.tensor([999.0, 500.0, 3.0])
+    y = torch.tensor([0, 9, 4]) if with_y else None
+    hidden = []
+    hooks = [blk.register_forward_hook(lambda _m, _i, o: hidden.append(o.detach().numpy().copy()))
+             for blk in list(m.in_blocks) + [m.mid_block] + list(m.out_blocks)]
+    with torch.no_grad():
+        out = m(x, t, y)
+    for h in hooks:
+        h.remove()
+    fx = dict(x=x.numpy(), t=t.numpy(), out=out.numpy(), **params_np(params), **sd_np(m))
+    if with_y:
+        fx["y"] = y.numpy()
+    for i, h in enumerate(hidden):
+        fx[f"hidden_{i}"] = h
+    np.savez_compressed(OUT / f"{name}.npz", **fx)
+    print(name, "out", tuple(out.shape), float(out.abs().max()))
+
+
+def ee_forward_fixture():
+    torch.manual_seed(11)
+    m = EarlyExitUViT(UViT(**TINY_FULL), "mlp_probe_per_layer").eval()
+    heat(m, 12)
+    with torch.no_grad():  # spread the probes around the threshold so exits happen at different layers
+        for i in range(TINY_FULL["depth"]):
+            m.matrix[f"{i}"].classifier[0].weight.mul_(6.0)
+            m.matrix[f"{i}"].classifier[0].bias.fill_(0.3 - 0.7 * i)
+    B = 4
+    x = torch.randn(B, 3, 8, 8)
+    t = torch.full((B,), 321.0)
+    with torch.no_grad():
+        eps, cls, outs = m(x, t, None)
+    fx = dict(x=x.numpy(), t=t.numpy(), eps=eps.numpy(), cls=torch.stack(cls).numpy(), outs=torch.stack(outs).numpy(),
+              **params_np(TINY_FULL), **sd_np(m))
+    np.savez_compressed(OUT / "ee_forward_tiny.npz", **fx)
+    print("ee_forward", torch.stack(cls).numpy().round(3))
+    return m
+
+
+def duodiff_sampler_fixture():
+    """Unmodified sampler.get_samples: DuoDiff hand-off at t_switch=300, predict_noise, CPU RNG stream."""
+    torch.manual_seed(21)
+    early = UViT(**TINY).eval()
+    late = UViT(**TINY_FULL).eval()
+    heat(early, 22)
+    heat(late, 23)
+    calls = {"early": [], "late": []}
+    early.register_forward_hook(lambda _m, i, _o: calls["early"].append(int(i[1][0])))
+    late.register_forward_hook(lambda _m, i, _o: calls["late"].append(int(i[1][0])))
+    fx = dict(**params_np(TINY), **{f"q::{k}": np.asarray(v) for k, v in TINY_FULL.items()}, **sd_np(early, "we::"),
+              **sd_np(late, "wl::"))
+    for rule, fn in (("predict_noise", ref_sampler.predict_noise_postprocessing),
+                     ("predict_original", ref_sampler.predict_original_postprocessing),
+                     ("predict_previous", ref_sampler.predict_previous_postprocessing)):
+        calls["early"].clear(), calls["late"].clear()
+        samples, inter = ref_sampler.get_samples(
+            model=early, batch_size=2, postprocessing=fn, seed=5, num_channels=3, sample_height=8, sample_width=8,
+            use_ddim=False, ddim_steps=50, ddim_eta=0.0, timesteps_save=[1, 300, 990], y=None, autoencoder=None,
+            late_model=late, t_switch=300)
+        fx[f"samples_{rule}"] = samples
+        for i, s in enumerate(inter):
+            fx[f"inter_{rule}_{i}"] = s
+        if rule == "predict_noise":
+            fx["early_t_min"], fx["early_calls"] = min(calls["early"]), len(calls["early"])
+            fx["late_t_max"], fx["late_calls"] = max(calls["late"]), len(calls["late"])
+        print(rule, samples.shape, float(np.abs(samples).max()), len(inter), len(calls["early"]), len(calls["late"]))
+    np.savez_compressed(OUT / "duodiff_sampler_tiny.npz", **fx)
+
+
+def ee_sampler_fixture(m):
+    samples, err_log, idx_log = ref_ee.get_samples(model=m, batch_size=3, seed=9, num_channels=3, sample_height=8,
+                                                   sample_width=8, threshold=0.35, depth=TINY_FULL["depth"])
+    fx = dict(samples=samples, err_log=err_log.numpy(), idx_log=idx_log.numpy(), threshold=np.float32(0.35),
+              **params_np(TINY_FULL), **sd_np(m))
+    np.savez_compressed(OUT / "ee_sampler_tiny.npz", **fx)
+    print("ee_sampler", samples.shape, "mean exit", float(idx_log.mean()))
+
+
+def schedule_fixture():
+    np.savez_compressed(OUT / "schedule.npz", betas=ref_sampler.betas.numpy(), alphas=ref_sampler.alphas.numpy(),
+                        alphas_bar=ref_sampler.alphas_bar.numpy(),
+                        alphas_bar_previous=ref_sampler.alphas_bar_previous.numpy(),
+                        betas_tilde=ref_sampler.betas_tilde.numpy())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    schedule_fixture()
+    uvit_forward_fixture("uvit_forward_tiny", TINY, 1, False)
+    uvit_forward_fixture("uvit_forward_tiny_cls", TINY_CLS, 3, True)
+    ee_model = ee_forward_fixture()
+    duodiff_sampler_fixture()
+    ee_sampler_fixture(ee_model)

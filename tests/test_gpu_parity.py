@@ -1,0 +1,325 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against the oracle
+(oracle/uvit_oracle.py, fp32, TF32 off) on identical random-init weights, inputs and injected noise.
+
+Tolerances (bf16 storage / tensor-core inputs, fp32 accumulation; stated per SURVEY.md §8c after measurement):
+  * single operators vs fp32 math on the same bf16 inputs : rel-L2 <= 5e-3 (output bf16 rounding is 2^-9 ~ 2e-3)
+  * one U-ViT forward (eps), teacher-forced                : rel-L2 <= 2e-2, max-abs <= 5e-2 * ||eps||_inf
+  * free-running final images, identical x_T and z_t      : rel-L2 <= 5e-3
+  * DDPM update alone (fp32)                               : bit-exact vs the reference expression order
+  * early-exit indices: equal except where |probe - threshold| < 2e-3
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import uvit_oracle as O
+from tests.helpers import CONFIGS, heat_, load_fixture, rel_l2, split_fixture
+
+pytestmark = pytest.mark.gpu
+
+EPS_REL_L2 = 2e-2
+EPS_MAX_ABS = 5e-2
+IMG_REL_L2 = 5e-3
+PROBE_MARGIN = 2e-3
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _lib():
+    from duodiff_b200 import _lib
+    return _lib, _lib.load()
+
+
+def _model(name, seed, hot, dev, ee=False):
+    import duodiff_b200 as ddb
+    torch.manual_seed(seed)
+    net = ddb.UViT(**CONFIGS[name])
+    if ee:
+        net = ddb.EarlyExitUViT(net, "mlp_probe_per_layer")
+    if hot:
+        heat_(net, seed + 100)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net, sd, O.UViTSpec.from_params(CONFIGS[name])
+
+
+# ------------------------------------------------------------------------------------------------ operators
+@pytest.mark.parametrize("M,N,K0,K1,epi", [
+    (128, 256, 64, 0, 0), (300, 512, 512, 0, 0), (1000, 512, 512, 512, 0), (1000, 1536, 512, 0, 1),
+    (1000, 2048, 512, 0, 2), (1000, 512, 2048, 0, 3), (257 * 8, 768, 768, 0, 3), (1, 256, 64, 0, 0),
+])
+def test_op_gemm(dev, M, N, K0, K1, epi):
+    lib, L = _lib()
+    g = torch.Generator().manual_seed(M + N + epi)
+    a0 = (torch.randn(M, K0, generator=g) + 0.3).to(dev).bfloat16()
+    a1 = torch.randn(M, K1, generator=g).to(dev).bfloat16() if K1 else None
+    K = K0 + K1
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev).bfloat16() if epi == 3 else None
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    A = a0.float() if a1 is None else torch.cat([a0.float(), a1.float()], 1)
+    colsum = stats = None
+    if epi in (1, 2):
+        colsum = w.float().sum(1).contiguous()
+        mean = A.mean(1)
+        m2 = ((A - mean[:, None]) ** 2).sum(1)
+        stats = torch.stack([mean, m2], 1).contiguous()
+    lib.check(L.ddb_op_gemm(lib.ptr(a0), lib.ptr(a1), lib.ptr(w), lib.ptr(bias), lib.ptr(colsum), lib.ptr(stats), 1, K,
+                            lib.ptr(res), lib.ptr(out), M, N, K0, K1, epi, lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    acc = A @ w.float().t()
+    if epi == 0:
+        ref = acc + bias
+    elif epi in (1, 2):
+        ref = (acc - mean[:, None] * colsum[None]) * torch.rsqrt(m2 / K + 1e-5)[:, None] + bias
+        ref = torch.nn.functional.gelu(ref) if epi == 2 else ref
+    else:
+        ref = acc + bias + res.float()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out.float(), ref) <= 5e-3
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 257, 1), (2, 257, 8), (3, 258, 12), (2, 258, 16), (1, 17, 2)])
+def test_op_attention(dev, B, L, H):
+    lib, Lb = _lib()
+    g = torch.Generator().manual_seed(B * 31 + H)
+    D = H * 64
+    qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.5).to(dev).bfloat16()
+    out = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+    lib.check(Lb.ddb_op_attention(lib.ptr(qkv), lib.ptr(out), B, L, H, lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    x = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(x[0] @ x[1].transpose(-1, -2) * 0.125, -1) @ x[2]).permute(0, 2, 1, 3).reshape(B * L, D)
+    assert rel_l2(out.float(), ref) <= 5e-3
+
+
+def test_op_ddpm_step_bit_exact(dev):
+    """x' = sqrt(1/a)(x - (1-a)/sqrt(1-abar) eps) + sigma z in the reference's evaluation order (sampler.py:53-56)."""
+    lib, L = _lib()
+    from duodiff_b200.ddpm import step_coefficients
+    sch = O.ddpm_schedule()
+    g = torch.Generator().manual_seed(0)
+    n = 4 * 3 * 64 * 64
+    for rule, fn, exact in (("predict_noise", O.predict_noise_step, True),
+                            ("predict_original", O.predict_original_step, False),
+                            ("predict_previous", O.predict_previous_step, True)):
+        table, mode = step_coefficients(rule)
+        coef = table.to(dev)
+        for t in (999, 500, 1, 0):
+            x, e, z = (torch.randn(n, generator=g) for _ in range(3))
+            ref = fn(sch, e, x, t, z)
+            xd, ed, zd = x.to(dev), e.to(dev), z.to(dev)
+            lib.check(L.ddb_ddpm_step(xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), coef.data_ptr(), t, mode, 0, n,
+                                      lib.current_stream_ptr()))
+            got = xd.cpu()
+            if exact:
+                assert torch.equal(got, ref), (rule, t)
+            else:
+                assert rel_l2(got, ref) <= 1e-6, (rule, t)
+
+
+def test_ddpm_philox_noise_is_standard_normal(dev):
+    lib, L = _lib()
+    from duodiff_b200.ddpm import step_coefficients
+    table, mode = step_coefficients("predict_previous")  # x' = out + sigma z
+    coef = table.to(dev)
+    n = 1 << 22
+    x = torch.zeros(n, device=dev)
+    out = torch.zeros(n, device=dev)
+    lib.check(L.ddb_ddpm_step(x.data_ptr(), out.data_ptr(), None, coef.data_ptr(), 500, mode, 1234, n,
+                              lib.current_stream_ptr()))
+    z = x / table[500, 2].item()
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
+    assert abs((z ** 4).mean().item() - 3) < 5e-2
+    x2 = torch.zeros(n, device=dev)
+    lib.check(L.ddb_ddpm_step(x2.data_ptr(), out.data_ptr(), None, coef.data_ptr(), 499, mode, 1234, n,
+                              lib.current_stream_ptr()))
+    assert abs(torch.corrcoef(torch.stack([x, x2]))[0, 1].item()) < 5e-3  # fresh noise every step
+
+
+# ------------------------------------------------------------------------------------------------ U-ViT forward
+def _forward_case(dev, name, B, hot, seed, ts):
+    net, sd, spec = _model(name, seed, hot, dev)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, spec.in_chans, spec.img_size, spec.img_size, generator=g).to(dev)
+    t = torch.tensor(ts[:B], dtype=torch.float32, device=dev)
+    y = torch.randint(0, spec.num_classes, (B,), generator=g).to(dev) if spec.num_classes > 0 else None
+    got = net(x, t, y)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.uvit_forward(sd, spec, x, t, y)
+    assert got.shape == x.shape  # tests/models/test_uvit.py:82-93 of the reference
+    r, ma = rel_l2(got, ref), float((got - ref).abs().max() / ref.abs().max())
+    print(f"{name} hot={hot} B={B}: eps rel-L2 {r:.2e} max-abs/inf {ma:.2e}")
+    assert torch.isfinite(got).all()
+    assert r <= EPS_REL_L2 and ma <= EPS_MAX_ABS
+
+
+@pytest.mark.parametrize("name,B,hot", [
+    ("celeba_3", 4, False), ("celeba_3", 4, True), ("celeba", 3, False), ("celeba", 3, True),
+    ("cifar10", 2, True), ("imagenet64_3", 2, True), ("imagenet256_3", 2, True), ("celeba_3", 1, True),
+])
+def test_uvit_forward_matches_oracle(dev, name, B, hot):
+    _forward_case(dev, name, B, hot, seed=7, ts=[999.0, 431.0, 0.0, 17.0])
+
+
+def test_uvit_forward_golden_dims_rejected(dev):
+    """The tiny golden configs (head_dim 16) are outside the kernel envelope: the library must say so, loudly."""
+    import duodiff_b200 as ddb
+    from duodiff_b200._lib import DuoDiffError
+    net = ddb.UViT(img_size=8, patch_size=2, in_chans=3, embed_dim=32, depth=3, num_heads=2, mlp_ratio=4,
+                   qkv_bias=False, num_classes=-1, normalize_timesteps=True).to(dev)
+    with pytest.raises(DuoDiffError):
+        net(torch.zeros(1, 3, 8, 8, device=dev), torch.zeros(1, device=dev))
+
+
+def test_batch_invariance(dev):
+    """Row b of a batched forward equals the same sample run alone (needed for N-GPU == 1-GPU sharding parity)."""
+    net, sd, spec = _model("celeba_3", 3, True, dev)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 3, 64, 64, generator=g).to(dev)
+    t = torch.full((5,), 250.0, device=dev)
+    full = net(x, t)
+    for b in (0, 4):
+        assert torch.equal(full[b:b + 1], net(x[b:b + 1].contiguous(), t[b:b + 1].contiguous()))
+
+
+# ------------------------------------------------------------------------------------------------ early exit
+def _spread_probes(net, depth):
+    with torch.no_grad():
+        for i in range(depth):
+            net.matrix[f"{i}"].classifier[0].weight.mul_(40.0)
+            net.matrix[f"{i}"].classifier[0].bias.fill_(1.5 - 3.0 * i / depth)
+
+
+def test_ee_forward_matches_oracle(dev):
+    import duodiff_b200 as ddb
+    torch.manual_seed(5)
+    net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["celeba"]), "mlp_probe_per_layer")
+    heat_(net, 6)
+    _spread_probes(net, 13)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(CONFIGS["celeba"])
+    g = torch.Generator().manual_seed(2)
+    B = 6
+    x = torch.randn(B, 3, 64, 64, generator=g).to(dev)
+    t = torch.full((B,), 640.0, device=dev)
+    eps, cls, outs = net(x, t)
+    assert len(cls) == len(outs) == 13 and cls[0].shape == (B,)
+    with torch.no_grad():
+        r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t)
+    assert rel_l2(eps, r_eps) <= EPS_REL_L2
+    cls_t, r_cls_t = torch.stack(cls), torch.stack(r_cls)
+    assert (cls_t - r_cls_t).abs().max().item() <= PROBE_MARGIN
+    for i in range(13):
+        assert rel_l2(outs[i], r_outs[i]) <= EPS_REL_L2, i
+    # selection (eesampler.py:67-68): identical indices except for probes within the margin of the threshold
+    for thr in (0.0, 0.3, 0.5, 0.7, 1.0):
+        e_sel, idx, _, _ = net.engine(B).ee_forward(x, t, None, threshold=thr, mode=0)
+        r_sel, r_idx, scores = O.ee_select(r_eps, r_cls, r_outs, thr)
+        near = ((scores[:-1] - thr).abs() < PROBE_MARGIN).any(0)
+        same = idx.long() == r_idx
+        assert bool((same | near).all()), (thr, idx.tolist(), r_idx.tolist())
+        ok = same.nonzero().flatten()
+        assert rel_l2(e_sel[ok], r_sel[ok]) <= EPS_REL_L2
+    assert net.engine(B).ee_forward(x, t, None, threshold=1.0)[1].eq(0).all()
+    assert net.engine(B).ee_forward(x, t, None, threshold=0.0)[1].eq(13).all()
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
+    from duodiff_b200.ddpm import Sampler
+    early, sde, se = _model("cifar10_3", 11, True, dev)
+    late, sdl, sl = _model("cifar10", 12, True, dev)
+    B = 2
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(B, 3, 32, 32, generator=g).to(dev)
+    noise = torch.randn(1000, B, 3, 32, 32, generator=g).to(dev)
+    f_early = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    f_late = lambda x, t, y: O.uvit_forward(sdl, sl, x, t, y)  # noqa: E731
+    # reference trajectory on the oracle (fp32 on the GPU, TF32 off)
+    trace = {}
+    ref_x0 = O.sample_ddpm(f_early, f_late, 300, x_T.clone(), noise, trace=trace)
+    # (1) free-running, CUDA graphs, whole loop in one C call
+    smp = Sampler(early.engine(B), late.engine(B), 300, B)
+    x = x_T.clone()
+    smp.run(x, noise=noise, use_graph=True)
+    torch.cuda.synchronize()
+    r = rel_l2(x, ref_x0)
+    print(f"free-running final x rel-L2 {r:.2e}")
+    assert r <= IMG_REL_L2
+    # (2) eager launches give the same bits as graph replay
+    x2 = x_T.clone()
+    eps_tr = torch.zeros(1000, B, 3, 32, 32, device=dev)
+    smp.run(x2, noise=noise, use_graph=False, eps_trace=eps_tr)
+    assert torch.equal(x, x2)
+    # (3) per-step eps, teacher-forced on the oracle's x_t, around the hand-off (t = 701, 700 early; 699 late)
+    for t in (999, 701, 700, 699, 350, 1, 0):
+        k = 999 - t
+        net = early if t >= 700 else late
+        tt = torch.full((B,), float(t), device=dev)
+        got = net(trace["x_in"][k].contiguous(), tt)
+        ref = trace["eps"][k]
+        assert rel_l2(got, ref) <= EPS_REL_L2, t
+        assert float((got - ref).abs().max() / ref.abs().max()) <= EPS_MAX_ABS, t
+    # (4) the hand-off happened at the right step: free-running eps at t=699 comes from the late model
+    assert rel_l2(eps_tr[999 - 699], trace["eps"][999 - 699]) <= 5e-2
+    # (5) epilogue layout (sampler.py:145-146)
+    assert torch.allclose(smp.finalize(x), O.to_samples_nhwc(x))
+
+
+def test_get_samples_api_and_intermediates(dev):
+    from duodiff_b200 import sampler as S
+    early, sde, se = _model("cifar10_3", 21, False, dev)
+    g = torch.Generator().manual_seed(4)
+    noise = torch.randn(1000, 2, 3, 32, 32, generator=g)
+    out, inter = S.get_samples(early, 2, S.predict_noise_postprocessing, seed=0, num_channels=3, sample_height=32,
+                               sample_width=32, use_ddim=False, ddim_steps=50, ddim_eta=0.0,
+                               timesteps_save=[1, 990], noise=noise)
+    assert out.shape == (2, 32, 32, 3) and out.dtype == np.float32 and len(inter) == 2
+    torch.manual_seed(0)
+    x_T = torch.randn(2, 3, 32, 32).to(dev)
+    f = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    x_a = O.sample_ddpm(f, None, np.inf, x_T.clone(), noise.to(dev), t_first=999, t_last=999)
+    assert rel_l2(torch.from_numpy(inter[0]).to(dev), O.to_samples_nhwc(x_a)) <= 1e-3
+    x_0 = O.sample_ddpm(f, None, np.inf, x_T.clone(), noise.to(dev))
+    assert rel_l2(torch.from_numpy(out).to(dev), O.to_samples_nhwc(x_0)) <= IMG_REL_L2
+    with pytest.raises(NotImplementedError):
+        S.get_samples(early, 2, S.predict_noise_postprocessing, 0, 3, 32, 32, use_ddim=True)
+
+
+def test_ee_sampler_logs(dev):
+    """eesampler.get_samples: indices log and batch-mean probe log, indexed by t (eesampler.py:54-55,71-72)."""
+    import duodiff_b200 as ddb
+    from duodiff_b200 import eesampler as ES
+    torch.manual_seed(8)
+    net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["cifar10"]), "mlp_probe_per_layer")
+    heat_(net, 9)
+    _spread_probes(net, 13)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(CONFIGS["cifar10"])
+    B, thr = 3, 0.4
+    g = torch.Generator().manual_seed(6)
+    noise = torch.randn(1000, B, 3, 32, 32, generator=g)
+    samples, err_log, idx_log = ES.get_samples(net, B, seed=1, num_channels=3, sample_height=32, sample_width=32,
+                                               threshold=thr, depth=13, noise=noise)
+    assert samples.shape == (B, 32, 32, 3) and err_log.shape == (1000, 13) and idx_log.shape == (1000, B)
+    torch.manual_seed(1)
+    x_T = torch.randn(B, 3, 32, 32).to(dev)
+    model = lambda x, t, y: O.ee_forward(sd, spec, x, t, y)  # noqa: E731
+    nz = noise.to(dev)
+    # teacher-free comparison over the first 40 steps (before one flipped exit can cascade)
+    x0, r_err, r_idx = O.ee_sample(model, thr, 13, x_T, nz, t_first=999, t_last=960)
+    sl = slice(960, 1000)
+    assert (idx_log[sl] != r_idx[sl]).float().mean().item() <= 0.05
+    assert (err_log[sl] - r_err[sl]).abs().max().item() <= PROBE_MARGIN
+    assert np.isfinite(samples).all()

@@ -1,0 +1,101 @@
+"""Pins oracle/ (the CPU restatement) to the reference: fixtures in tests/golden/*.npz were produced by the
+unmodified reference modules (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import torch
+
+from oracle import uvit_oracle as O
+from tests.helpers import load_fixture, split_fixture
+
+torch.set_num_threads(4)
+ATOL = 2e-5  # fp32, different but equivalent op order (explicit softmax vs SDPA, reshape vs einops/conv)
+
+
+def test_schedule_bit_exact():
+    fx = load_fixture("schedule")
+    sch = O.ddpm_schedule()
+    for k in ("betas", "alphas", "alphas_bar", "alphas_bar_previous", "betas_tilde"):
+        assert np.array_equal(sch[k].numpy(), fx[k]), k
+
+
+def _check_forward(name, with_y):
+    fx = load_fixture(name)
+    sd, params = split_fixture(fx)
+    spec = O.UViTSpec.from_params(params)
+    y = torch.from_numpy(fx["y"]) if with_y else None
+    cap = []
+    out = O.uvit_forward(sd, spec, torch.from_numpy(fx["x"]), torch.from_numpy(fx["t"]), y, capture=cap)
+    for i in range(spec.depth):
+        np.testing.assert_allclose(cap[i + 1].numpy(), fx[f"hidden_{i}"], atol=ATOL * 10, rtol=1e-5)
+    np.testing.assert_allclose(out.numpy(), fx["out"], atol=ATOL, rtol=1e-5)
+
+
+def test_uvit_forward_unconditional():
+    _check_forward("uvit_forward_tiny", False)
+
+
+def test_uvit_forward_class_conditional_raw_timesteps():
+    _check_forward("uvit_forward_tiny_cls", True)
+
+
+def test_ee_forward_probes_and_heads():
+    fx = load_fixture("ee_forward_tiny")
+    sd, params = split_fixture(fx)
+    spec = O.UViTSpec.from_params(params)
+    eps, cls, outs = O.ee_forward(sd, spec, torch.from_numpy(fx["x"]), torch.from_numpy(fx["t"]))
+    assert len(cls) == len(outs) == spec.depth  # tests/models/test_early_exit.py:98-115 of the reference
+    np.testing.assert_allclose(eps.numpy(), fx["eps"], atol=ATOL, rtol=1e-5)
+    np.testing.assert_allclose(torch.stack(cls).numpy(), fx["cls"], atol=1e-6)
+    np.testing.assert_allclose(torch.stack(outs).numpy(), fx["outs"], atol=ATOL, rtol=1e-5)
+
+
+def _replay_reference_rng(seed, shape):
+    """seed_everything + x_T draw of sampler.py:99-100; z_t drawn lazily from the same global CPU stream."""
+    torch.manual_seed(seed)
+    x_T = torch.randn(*shape)
+    return x_T, (lambda t: torch.randn(*shape))
+
+
+def test_duodiff_sampler_all_rules():
+    fx = load_fixture("duodiff_sampler_tiny")
+    sde, pe = split_fixture(fx, "we::", "p::")
+    sdl, pl = split_fixture(fx, "wl::", "q::")
+    se, sl = O.UViTSpec.from_params(pe), O.UViTSpec.from_params(pl)
+    assert (fx["early_calls"], fx["early_t_min"], fx["late_calls"], fx["late_t_max"]) == (300, 700, 700, 699)  # Q1
+    early = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    late = lambda x, t, y: O.uvit_forward(sdl, sl, x, t, y)  # noqa: E731
+    for rule in ("predict_noise", "predict_original", "predict_previous"):
+        x_T, noise = _replay_reference_rng(5, (2, 3, 8, 8))
+        x0 = O.sample_ddpm(early, late, 300, x_T, noise, rule=rule)
+        got = O.to_samples_nhwc(x0).numpy()
+        ref = fx[f"samples_{rule}"]
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() <= 2e-4 * scale, rule  # 1000 chained fp32 steps
+
+
+def test_duodiff_sampler_intermediates():
+    fx = load_fixture("duodiff_sampler_tiny")
+    sde, pe = split_fixture(fx, "we::", "p::")
+    sdl, pl = split_fixture(fx, "wl::", "q::")
+    se, sl = O.UViTSpec.from_params(pe), O.UViTSpec.from_params(pl)
+    early = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    late = lambda x, t, y: O.uvit_forward(sdl, sl, x, t, y)  # noqa: E731
+    # timesteps_save=[1,300,990] -> saved after the steps t = 999, 700, 10, appended in loop order
+    x_T, noise = _replay_reference_rng(5, (2, 3, 8, 8))
+    x = O.sample_ddpm(early, late, 300, x_T, noise, t_first=999, t_last=999)
+    ref = fx["inter_predict_noise_0"]
+    assert np.abs(O.to_samples_nhwc(x).numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_ee_sampler_logs_and_samples():
+    fx = load_fixture("ee_sampler_tiny")
+    sd, params = split_fixture(fx)
+    spec = O.UViTSpec.from_params(params)
+    model = lambda x, t, y: O.ee_forward(sd, spec, x, t, y)  # noqa: E731
+    x_T, noise = _replay_reference_rng(9, (3, 3, 8, 8))
+    x0, err_log, idx_log = O.ee_sample(model, float(fx["threshold"]), spec.depth, x_T, noise)
+    # exit indices must be identical except where a probe sits within 1e-5 of the threshold
+    mism = (idx_log.numpy() != fx["idx_log"]).mean()
+    assert mism <= 0.002, mism
+    np.testing.assert_allclose(err_log.numpy(), fx["err_log"], atol=5e-4)
+    ref = fx["samples"]
+    assert np.abs(O.to_samples_nhwc(x0).numpy() - ref).max() <= 5e-3 * np.abs(ref).max()
