@@ -187,4 +187,302 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_mma_kernel(const __n
     }
 }
 
+
+// =====================================================================================================
+// v2: tcgen05 / TMEM attention for the 256-patch-token layout of every reference config (L = 256 + extras).
+//
+// One CTA per (sample, head, 128-query tile); 2 CTAs co-reside per SM (80 KB smem, 256 TMEM columns each) so the
+// softmax of one overlaps the MMAs / TMA loads of the other.
+//   keys   [extras, L)  (the 256 patch tokens): S = Q K^T on the tensor core, M=128 x N=256 x K=64, fp32 in TMEM
+//   keys   [0, extras)  (time / label tokens):  1-2 dot products per query row on the CUDA cores
+//   softmax: one thread per query row reads its S row from TMEM (no shuffles), writes P (bf16, packed) back over
+//            the first 128 columns of S; O = P V accumulates in columns [128,192) of the same allocation with
+//            A = P from TMEM and B = V (MN-major, 128B swizzle) from shared memory.
+// The query rows [0, extras) are handled by attention_extras_kernel below.
+// =====================================================================================================
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct AttnArgs {
+    CUtensorMap tmQKV;  // [B, L, 3D] bf16, box {64, 128, 1}
+    CUtensorMap tmKV;   // [B, L, 3D] bf16, box {64, 256, 1}
+    CUtensorMap tmOut;  // [B, L, D]  bf16, box {64, 128, 1}
+    const __nv_bfloat16* qkv;
+    int L, H, extras;
+    float scale_log2e;
+    const int* b_dev;  // optional live batch size (early-exit compaction)
+};
+
+constexpr int ATT2_THREADS = 192;
+constexpr int ATT2_SMEM = 16384 + 32768 + 32768 + 1024 + 128;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 2) attention_tcgen05_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ uint8_t att2_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att2_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;           // 128 x 128 B (later reused as the output staging tile)
+    uint8_t* sK = smem + 16384;   // 256 x 128 B
+    uint8_t* sV = smem + 49152;   // 256 x 128 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
+    uint64_t* qk_full = bars + 0;
+    uint64_t* v_full = bars + 1;
+    uint64_t* s_full = bars + 2;
+    uint64_t* p_full = bars + 3;
+    uint64_t* o_full = bars + 4;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x & 1;
+    const int bh = blockIdx.x >> 1;
+    const int b = bh / a.H, h = bh % a.H;
+    if (a.b_dev && b >= *a.b_dev) return;
+    const int D = a.H * 64;
+    const int q0 = a.extras + tile * 128;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.tmQKV);
+        tma_prefetch_desc(&a.tmKV);
+        tma_prefetch_desc(&a.tmOut);
+        mbar_init(qk_full, 1);
+        mbar_init(v_full, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_holder);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(qk_full, 16384 + 32768);
+            tma_load_3d(sQ, &a.tmQKV, qk_full, h * 64, q0, b);
+            tma_load_3d(sK, &a.tmKV, qk_full, D + h * 64, a.extras, b);
+            mbar_expect_tx(v_full, 32768);
+            tma_load_3d(sV, &a.tmKV, v_full, 2 * D + h * 64, a.extras, b);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(qk_full, 0);
+            tc_fence_after();
+            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
+            const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK));
+            constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+            umma_commit(s_full);
+            mbar_wait(p_full, 0);
+            mbar_wait(v_full, 0);
+            tc_fence_after();
+            const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV));
+            constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+#pragma unroll
+            for (int k = 0; k < 16; ++k)  // 16 keys per step: P columns +8, V rows +16 (2048 B)
+                umma_f16_ts(tmem + 128, tmem + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
+            umma_commit(o_full);
+        }
+    } else {
+        // ================================================================= softmax + epilogue: one thread per query row
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
+        const float c = a.scale_log2e;
+        const __nv_bfloat16* xrow = a.qkv + (size_t)b * a.L * 3 * D;  // extras tokens of this sample
+
+        // scores against the extras keys on the CUDA cores (overlaps the Q K^T MMA)
+        mbar_wait(qk_full, 0);
+        float se[2] = {-INFINITY, -INFINITY};
+        {
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((j ^ (r & 7)) << 4));
+                const float qf[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                                     bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+                const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(xrow + D + h * 64) + j);
+                const float kf[8] = {bf16_lo(k0.x), bf16_hi(k0.x), bf16_lo(k0.y), bf16_hi(k0.y),
+                                     bf16_lo(k0.z), bf16_hi(k0.z), bf16_lo(k0.w), bf16_hi(k0.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc0 = fmaf(qf[e], kf[e], acc0);
+                if (a.extras == 2) {
+                    const uint4 k1 = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * D + D + h * 64) + j);
+                    const float kg[8] = {bf16_lo(k1.x), bf16_hi(k1.x), bf16_lo(k1.y), bf16_hi(k1.y),
+                                         bf16_lo(k1.z), bf16_hi(k1.z), bf16_lo(k1.w), bf16_hi(k1.w)};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc1 = fmaf(qf[e], kg[e], acc1);
+                }
+            }
+            se[0] = acc0;
+            if (a.extras == 2) se[1] = acc1;
+        }
+
+        mbar_wait(s_full, 0);
+        tc_fence_after();
+        // pass 1: row max
+        float m = fmaxf(se[0], se[1]);
+#pragma unroll 1
+        for (int j = 0; j < 8; j += 2) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(t_row + j * 32, v0);
+            tmem_ld_32x32b_x32(t_row + j * 32 + 32, v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
+        }
+        const float mc = m * c;
+        float sum = ex2_approx(fmaf(se[0], c, -mc));
+        float pe[2] = {sum, 0.f};
+        if (a.extras == 2) {
+            pe[1] = ex2_approx(fmaf(se[1], c, -mc));
+            sum += pe[1];
+        }
+        // pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_row + j * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
+                sum += p0 + p1;
+                pk[e] = pack_bf16(p0, p1);
+            }
+            tmem_st_32x32b_x16(t_row + j * 16, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+
+        // epilogue: O row (fp32) + extras-key contributions, normalise, bf16 -> smem (Q tile is dead) -> TMA store
+        const float inv = 1.f / sum;
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(t_row + 128, o0);
+        tmem_ld_32x32b_x32(t_row + 160, o1);
+        tmem_ld_wait();
+        uint8_t* srow = sQ + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(j < 4 ? o0[j * 8 + e] : o1[(j - 4) * 8 + e]);
+            const uint4 va = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * D + h * 64) + j);
+            const float vf[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
+                                 bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(pe[0], vf[e], o[e]);
+            if (a.extras == 2) {
+                const uint4 vb = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * D + 2 * D + h * 64) + j);
+                const float vg[8] = {bf16_lo(vb.x), bf16_hi(vb.x), bf16_lo(vb.y), bf16_hi(vb.y),
+                                     bf16_lo(vb.z), bf16_hi(vb.z), bf16_lo(vb.w), bf16_hi(vb.w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fmaf(pe[1], vg[e], o[e]);
+            }
+            uint4 w;
+            w.x = pack_bf16(o[0] * inv, o[1] * inv);
+            w.y = pack_bf16(o[2] * inv, o[3] * inv);
+            w.z = pack_bf16(o[4] * inv, o[5] * inv);
+            w.w = pack_bf16(o[6] * inv, o[7] * inv);
+            *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (warp == 2 && lane == 0) {
+            tma_store_3d(&a.tmOut, sQ, h * 64, q0, b);
+            tma_store_commit();
+            tma_store_wait_all<0>();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem);
+    }
+}
+
+// Query rows [0, extras) (time / label tokens) of every (sample, head): 1-2 rows x L keys on the CUDA cores.
+// grid = B*H, 128 threads.
+__global__ void __launch_bounds__(128) attention_extras_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                               __nv_bfloat16* __restrict__ out, int L, int H,
+                                                               int extras, float scale_log2e,
+                                                               const int* __restrict__ b_dev) {
+    __shared__ float sq[2][64];
+    __shared__ float sp[2][264];
+    __shared__ float red[2][4];
+    __shared__ float so[2][2][64];
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    if (b_dev && b >= *b_dev) return;
+    const int D = H * 64, tid = threadIdx.x;
+    const size_t rs = (size_t)3 * D;
+    const __nv_bfloat16* base = qkv + (size_t)b * L * rs + h * 64;
+    if (tid < 64 * extras) sq[tid >> 6][tid & 63] = __bfloat162float(base[(size_t)(tid >> 6) * rs + (tid & 63)]);
+    __syncthreads();
+    // scores
+    float mx[2] = {-INFINITY, -INFINITY};
+    for (int k = tid; k < L; k += 128) {
+        const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)k * rs + D);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 u = __ldg(kr + j);
+            const float kf[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s0 = fmaf(sq[0][j * 8 + e], kf[e], s0);
+                if (extras == 2) s1 = fmaf(sq[1][j * 8 + e], kf[e], s1);
+            }
+        }
+        sp[0][k] = s0, mx[0] = fmaxf(mx[0], s0);
+        if (extras == 2) sp[1][k] = s1, mx[1] = fmaxf(mx[1], s1);
+    }
+    for (int e = 0; e < extras; ++e) {
+        float v = mx[e];
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((tid & 31) == 0) red[e][tid >> 5] = v;
+    }
+    __syncthreads();
+    float sm[2] = {0.f, 0.f}, gm[2];
+    for (int e = 0; e < extras; ++e) gm[e] = fmaxf(fmaxf(red[e][0], red[e][1]), fmaxf(red[e][2], red[e][3]));
+    __syncthreads();
+    for (int k = tid; k < L; k += 128)
+        for (int e = 0; e < extras; ++e) {
+            const float p = exp2f((sp[e][k] - gm[e]) * scale_log2e);
+            sp[e][k] = p;
+            sm[e] += p;
+        }
+    for (int e = 0; e < extras; ++e) {
+        float v = sm[e];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[e][tid >> 5] = v;
+    }
+    __syncthreads();
+    // O[e][d] = sum_k p[e][k] V[k][d]; thread = (half of the keys, d)
+    const int d = tid & 63, half = tid >> 6;
+    float o0 = 0.f, o1 = 0.f;
+    for (int k = half; k < L; k += 2) {
+        const float v = __bfloat162float(base[(size_t)k * rs + 2 * D + d]);
+        o0 = fmaf(sp[0][k], v, o0);
+        if (extras == 2) o1 = fmaf(sp[1][k], v, o1);
+    }
+    so[0][half][d] = o0, so[1][half][d] = o1;
+    __syncthreads();
+    if (tid < 64 * extras) {
+        const int e = tid >> 6;
+        const float tot = red[e][0] + red[e][1] + red[e][2] + red[e][3];
+        out[((size_t)b * L + e) * D + h * 64 + d] = __float2bfloat16_rn((so[e][0][d] + so[e][1][d]) / tot);
+    }
+}
+
 }  // namespace ddb

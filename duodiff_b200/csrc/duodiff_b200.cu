@@ -138,6 +138,21 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
     return DDB_OK;
 }
 
+// bf16 [d2, d1, d0] (d0 contiguous) with byte strides; box {64, box1, 1}, SWIZZLE_128B
+static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                             uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
+    DDB_TRY(load_encode());
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstr[2] = {stride1_bytes, stride2_bytes};
+    cuuint32_t box[3] = {64, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DDB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+    return DDB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI>
 static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
@@ -178,6 +193,32 @@ static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_de
         case 2048: ln_stats_kernel<2048><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
         default: return fail(DDB_ERR_INVALID, "embed_dim %d unsupported (need 256/512/768/1024/2048)", D);
     }
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
+// tcgen05 attention: needs exactly 256 patch tokens (L = 256 + extras)
+static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* out, int Bcap, int L, int H) {
+    memset(&a, 0, sizeof(a));
+    const uint64_t D = (uint64_t)H * 64;
+    a.qkv = qkv, a.L = L, a.H = H, a.extras = L - 256;
+    a.scale_log2e = 0.125f * 1.4426950408889634f;
+    DDB_TRY(make_tmap_bf16_3d(&a.tmQKV, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 128));
+    DDB_TRY(make_tmap_bf16_3d(&a.tmKV, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 256));
+    DDB_TRY(make_tmap_bf16_3d(&a.tmOut, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 128));
+    return DDB_OK;
+}
+static int launch_attention_tc(const AttnArgs& a, __nv_bfloat16* out, int B, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ATT2_SMEM));
+        configured = true;
+    }
+    if (B <= 0) return DDB_OK;
+    attention_tcgen05_kernel<<<B * a.H * 2, ATT2_THREADS, ATT2_SMEM, st>>>(a);
+    LAUNCH_CHECK();
+    attention_extras_kernel<<<B * a.H, 128, 0, st>>>(a.qkv, out, a.L, a.H, a.extras, a.scale_log2e, a.b_dev);
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -248,6 +289,7 @@ struct ddb_model {
     std::vector<BlockOps> ops;
     GemmArgs final_dec;
     std::vector<GemmArgs> head_dec;
+    AttnArgs attn;
     std::vector<Buf> keep;  // misc allocations
 };
 
@@ -471,6 +513,8 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
         cur = m->xo[i]->p;
         if (i < half) skips.push_back(cur);
     }
+    DDB_TRY(plan_attention(m->attn, m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), cfg->max_batch, m->L,
+                           m->Hh));
     DDB_TRY(plan_gemm(m->final_dec, m, cur, D, nullptr, 0, m->final_head.dec, 64, nullptr, nullptr, st));
     plan_decode_geometry(m->final_dec, m, m->img_pre->as<float>());
     if (cfg->early_exit) {
@@ -557,7 +601,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         }
         {
             ProfScope ps(PC_ATTENTION);
-            DDB_TRY(launch_attention(m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), B, m->L, m->Hh, st));
+            DDB_TRY(launch_attention_tc(m->attn, m->ao->as<__nv_bfloat16>(), B, st));
         }
         op.proj.M = M;
         {
@@ -862,10 +906,19 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
     return launch_gemm(g, epi, di.num_sms, (cudaStream_t)stream);
 }
 
-int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, void* stream) {
+int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, int32_t variant,
+                     void* stream) {
     if (!qkv_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
     DeviceInfo di;
     DDB_TRY(device_info(di));
+    const bool tc_ok = (L == 257 || L == 258);
+    if (variant == 2 && !tc_ok) return fail(DDB_ERR_INVALID, "tcgen05 attention needs L = 256 + {1,2}");
+    if (variant == 2 || (variant == 0 && tc_ok)) {
+        AttnArgs a;
+        DDB_TRY(plan_attention(a, reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
+                               reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H));
+        return launch_attention_tc(a, reinterpret_cast<__nv_bfloat16*>(out_dev), B, (cudaStream_t)stream);
+    }
     return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
                             reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H, (cudaStream_t)stream);
 }

@@ -121,8 +121,11 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
                 const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
                 const void* residual_dev, void* out_dev, int32_t M, int32_t N, int32_t K0, int32_t K1, int32_t epi,
                 void* stream);
-/* softmax(q k^T / 8) v over qkv [B*L, 3*H*64] bf16 -> out [B*L, H*64] bf16 (models/uvit.py:159-164) */
-int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, void* stream);
+/* softmax(q k^T / 8) v over qkv [B*L, 3*H*64] bf16 -> out [B*L, H*64] bf16 (models/uvit.py:159-164).
+ * variant 0: the model path's choice (tcgen05/TMEM kernel when L = 256 + {1,2}, else the mma.sync kernel);
+ * 1: force the generic mma.sync kernel; 2: force the tcgen05 kernel. */
+int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, int32_t variant,
+                     void* stream);
 /* per-row (mean, M2) of x [M, D] bf16 -> stats [M,2] f32 */
 int ddb_op_ln_stats(const void* x_dev, int32_t M, int32_t D, float* stats_dev, void* stream);
 /* W' = bf16(W*gamma), colsum, bias' (LayerNorm folding) for W [N,K] f32 */

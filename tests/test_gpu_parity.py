@@ -86,14 +86,16 @@ def test_op_gemm(dev, M, N, K0, K1, epi):
     assert rel_l2(out.float(), ref) <= 5e-3
 
 
-@pytest.mark.parametrize("B,L,H", [(1, 257, 1), (2, 257, 8), (3, 258, 12), (2, 258, 16), (1, 17, 2)])
-def test_op_attention(dev, B, L, H):
+@pytest.mark.parametrize("B,L,H,variant", [(1, 257, 1, 2), (2, 257, 8, 2), (3, 258, 12, 2), (2, 258, 16, 0),
+                                              (2, 257, 8, 1), (3, 258, 12, 1), (1, 17, 2, 0), (2, 100, 2, 1)])
+def test_op_attention(dev, B, L, H, variant):
+    """variant 2 = tcgen05/TMEM kernel (the model path), 1 = generic mma.sync kernel, 0 = dispatcher."""
     lib, Lb = _lib()
     g = torch.Generator().manual_seed(B * 31 + H)
     D = H * 64
     qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.5).to(dev).bfloat16()
     out = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
-    lib.check(Lb.ddb_op_attention(lib.ptr(qkv), lib.ptr(out), B, L, H, lib.current_stream_ptr()))
+    lib.check(Lb.ddb_op_attention(lib.ptr(qkv), lib.ptr(out), B, L, H, variant, lib.current_stream_ptr()))
     torch.cuda.synchronize()
     x = qkv.float().view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = (torch.softmax(x[0] @ x[1].transpose(-1, -2) * 0.125, -1) @ x[2]).permute(0, 2, 1, 3).reshape(B * L, D)
@@ -193,9 +195,10 @@ def test_batch_invariance(dev):
 
 # ------------------------------------------------------------------------------------------------ early exit
 def _spread_probes(net, depth):
+    """Random-init probes all sit near 0.5; spread them so that every exit layer occurs.  After
+    heat_() the probe weights have std 0.08, i.e. per-token logits of a few units like a trained probe."""
     with torch.no_grad():
         for i in range(depth):
-            net.matrix[f"{i}"].classifier[0].weight.mul_(40.0)
             net.matrix[f"{i}"].classifier[0].bias.fill_(1.5 - 3.0 * i / depth)
 
 
@@ -218,6 +221,8 @@ def test_ee_forward_matches_oracle(dev):
         r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t)
     assert rel_l2(eps, r_eps) <= EPS_REL_L2
     cls_t, r_cls_t = torch.stack(cls), torch.stack(r_cls)
+    print(f"probe max deviation {(cls_t - r_cls_t).abs().max().item():.2e}; range "
+          f"{r_cls_t.min().item():.3f}..{r_cls_t.max().item():.3f}")
     assert (cls_t - r_cls_t).abs().max().item() <= PROBE_MARGIN
     for i in range(13):
         assert rel_l2(outs[i], r_outs[i]) <= EPS_REL_L2, i
