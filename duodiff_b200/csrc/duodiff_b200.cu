@@ -16,6 +16,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 using namespace ddb;
 
@@ -169,6 +170,39 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     LAUNCH_CHECK();
     return DDB_OK;
 }
+// runtime options (ddb_set_option): gemm_variant 2 = CTA-pair kernel (default), 1 = single-CTA kernel
+static int g_gemm_variant = 2;
+
+template <int EPI, bool STATS>
+static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    auto kfn = gemm2_tcgen05_kernel<EPI, STATS>;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = ((a.M + 255) / 256) * (a.N / 256);
+    int clusters = num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (clusters <= 0) return DDB_OK;
+    kfn<<<2 * clusters, 384, Gemm2Cfg::SMEM_BYTES, st>>>(a);
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+// CTA-pair GEMM: a.tmB must have been encoded with a 128-row box
+static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
+    const bool stats = a.stats_out != nullptr;
+    switch (epi) {
+        case EPI_BIAS:
+            return stats ? launch_gemm2_t<EPI_BIAS, true>(a, num_sms, st) : launch_gemm2_t<EPI_BIAS, false>(a, num_sms, st);
+        case EPI_LN: return launch_gemm2_t<EPI_LN, false>(a, num_sms, st);
+        case EPI_LN_GELU: return launch_gemm2_t<EPI_LN_GELU, false>(a, num_sms, st);
+        case EPI_RES:
+            return stats ? launch_gemm2_t<EPI_RES, true>(a, num_sms, st) : launch_gemm2_t<EPI_RES, false>(a, num_sms, st);
+    }
+    return fail(DDB_ERR_INVALID, "unknown CTA-pair GEMM epilogue %d", epi);
+}
+
 static int launch_gemm(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     switch (epi) {
         case EPI_BIAS: return launch_gemm_t<256, EPI_BIAS>(a, num_sms, st);
@@ -283,7 +317,7 @@ struct ddb_model {
     std::vector<HeadW> ee_heads;
     std::vector<Buf> probe_w, probe_b;
     // workspace
-    Buf x0, xs, xm, qkv, ao, hbuf, stats, img_pre, probe_sig, scores, outputs, exit_idx;
+    Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_sig, scores, outputs, exit_idx;
     std::vector<Buf> xo;
     // plan
     std::vector<BlockOps> ops;
@@ -388,6 +422,7 @@ static int plan_gemm(GemmArgs& g, const ddb_model* m, const void* A0, int K0, co
     DDB_TRY(make_tmap_bf16(&g.tmA0, A0, m->Mpad, K0, K0, 128));
     if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, A1, m->Mpad, K1, K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmB, W.w->p, W.N, K0 + K1, K0 + K1, BN));
+    if (BN == 256) DDB_TRY(make_tmap_bf16(&g.tmB2, W.w->p, W.N, K0 + K1, K0 + K1, 128));
     if (out) DDB_TRY(make_tmap_bf16(&g.tmOut, out, m->Mpad, W.N, W.N, 128));
     if (res) DDB_TRY(make_tmap_bf16(&g.tmRes, res, m->Mpad, W.N, W.N, 128));
     return DDB_OK;
@@ -482,6 +517,7 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     DDB_TRY(new_buf(m->qkv, act * 3));
     DDB_TRY(new_buf(m->hbuf, (size_t)m->Mpad * cfg->mlp_hidden * 2));
     DDB_TRY(new_buf(m->stats, (size_t)m->Mpad * sizeof(float2)));
+    DDB_TRY(new_buf(m->stats_p, (size_t)m->Mpad * (D / 64) * sizeof(float2)));
     DDB_TRY(new_buf(m->img_pre, (size_t)cfg->max_batch * m->chw * 4));
     m->xo.resize(cfg->depth);
     for (int i = 0; i < cfg->depth; ++i) DDB_TRY(new_buf(m->xo[i], act));
@@ -559,76 +595,73 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         LAUNCH_CHECK();
     }
 
+    // LayerNorm statistics travel either as one (mean, M2) per row from ln_stats_kernel (kind 1) or as D/64
+    // partials per row written by the producing CTA-pair GEMM's epilogue (kind 2).
+    float2* stp = m->stats_p->as<float2>();
+    const bool pair = (g_gemm_variant == 2);
+    const int np_p = D / 64;
+    int kind = 0;
+    auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
+        g.M = M;
+        if (ln_in) {
+            g.stats = kind == 2 ? stp : st2;
+            g.nparts = kind == 2 ? np_p : 1;
+        }
+        g.stats_out = (pair && stats_out) ? stp : nullptr;
+        ProfScope ps(cat);
+        return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
+    };
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     for (int i = 0; i < c.depth; ++i) {
-        BlockOps op = m->ops[i];
+        const BlockOps& op = m->ops[i];
         const BlockW& bw = m->blocks[i];
-        bool have_stats = false;
         if (ee) {
             // probe i + head i look at the block input (models/early_exit.py:294-296)
             DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
                                     m->probe_sig->as<float>(), st));
+            kind = 1;
             {
                 ProfScope ps(PC_EE_OTHER);
                 probe_mean_kernel<<<B, 128, 0, st>>>(m->probe_sig->as<float>(), m->L,
                                                      m->scores->as<float>() + (size_t)i * B);
                 LAUNCH_CHECK();
             }
-            GemmArgs hd = m->head_dec[i];
-            hd.M = M;
-            {
-                ProfScope ps(PC_GEMM_DECODE);
-                DDB_TRY(launch_gemm(hd, EPI_DECODE, nsm, st));
-            }
+            DDB_TRY(run_gemm(m->head_dec[i], EPI_DECODE, PC_GEMM_DECODE, true, false));
             DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(),
                              m->outputs->as<float>() + (size_t)i * B * m->chw, B, st));
-            have_stats = true;
         }
         if (bw.has_skip) {
-            op.skip.M = M;
-            {
-                ProfScope ps(PC_GEMM_SKIP);
-                DDB_TRY(launch_gemm(op.skip, EPI_BIAS, nsm, st));
-            }
+            DDB_TRY(run_gemm(op.skip, EPI_BIAS, PC_GEMM_SKIP, false, true));
             cur = m->xs->as<__nv_bfloat16>();
-            have_stats = false;
+            kind = pair ? 2 : 0;
         }
-        if (!have_stats) DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
-        op.qkv.M = M;
-        {
-            ProfScope ps(PC_GEMM_QKV);
-            DDB_TRY(launch_gemm(op.qkv, EPI_LN, nsm, st));
+        if (kind == 0) {
+            DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+            kind = 1;
         }
+        DDB_TRY(run_gemm(op.qkv, EPI_LN, PC_GEMM_QKV, true, false));
         {
             ProfScope ps(PC_ATTENTION);
             DDB_TRY(launch_attention_tc(m->attn, m->ao->as<__nv_bfloat16>(), B, st));
         }
-        op.proj.M = M;
-        {
-            ProfScope ps(PC_GEMM_PROJ);
-            DDB_TRY(launch_gemm(op.proj, EPI_RES, nsm, st));
+        DDB_TRY(run_gemm(op.proj, EPI_RES, PC_GEMM_PROJ, false, true));
+        if (pair) {
+            kind = 2;
+        } else {
+            DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+            kind = 1;
         }
-        DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
-        op.fc1.M = M;
-        {
-            ProfScope ps(PC_GEMM_FC1);
-            DDB_TRY(launch_gemm(op.fc1, EPI_LN_GELU, nsm, st));
-        }
-        op.fc2.M = M;
-        {
-            ProfScope ps(PC_GEMM_FC2);
-            DDB_TRY(launch_gemm(op.fc2, EPI_RES, nsm, st));
-        }
+        DDB_TRY(run_gemm(op.fc1, EPI_LN_GELU, PC_GEMM_FC1, true, false));
+        DDB_TRY(run_gemm(op.fc2, EPI_RES, PC_GEMM_FC2, false, true));
+        kind = pair ? 2 : 0;
         cur = m->xo[i]->as<__nv_bfloat16>();
     }
     (void)half;
-    DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
-    GemmArgs fd = m->final_dec;
-    fd.M = M;
-    {
-        ProfScope ps(PC_GEMM_DECODE);
-        DDB_TRY(launch_gemm(fd, EPI_DECODE, nsm, st));
+    if (kind == 0) {
+        DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+        kind = 1;
     }
+    DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
     DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
     return DDB_OK;
 }
@@ -714,6 +747,15 @@ extern "C" {
 const char* ddb_version(void) { return "duodiff_b200 0.1.0 (sm_100a)"; }
 const char* ddb_last_error(void) { return g_err; }
 int64_t ddb_launch_count(void) { return g_launches.load(); }
+int ddb_set_option(const char* name, int32_t value) {
+    if (!name) return fail(DDB_ERR_INVALID, "null option name");
+    if (!strcmp(name, "gemm_variant")) {
+        if (value != 1 && value != 2) return fail(DDB_ERR_INVALID, "gemm_variant must be 1 or 2");
+        g_gemm_variant = value;
+        return DDB_OK;
+    }
+    return fail(DDB_ERR_INVALID, "unknown option '%s'", name);
+}
 
 int ddb_model_create(const ddb_uvit_config* cfg, const ddb_tensor* tensors, int32_t n_tensors, ddb_model** out) {
     if (!cfg || !tensors || !out) return fail(DDB_ERR_INVALID, "null argument");
@@ -883,9 +925,13 @@ int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, 
 // ---- single-operator entry points
 int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const float* bias_dev,
                 const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
-                const void* residual_dev, void* out_dev, int32_t M, int32_t N, int32_t K0, int32_t K1, int32_t epi,
-                void* stream) {
+                const void* residual_dev, void* out_dev, float* stats_out_dev, int32_t M, int32_t N, int32_t K0,
+                int32_t K1, int32_t epi, int32_t variant, void* stream) {
     if (!a0_dev || !w_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
+    if (variant == 0) variant = g_gemm_variant;
+    if (variant != 1 && variant != 2) return fail(DDB_ERR_INVALID, "variant must be 0, 1 or 2");
+    if (stats_out_dev && (variant != 2 || (epi != EPI_BIAS && epi != EPI_RES)))
+        return fail(DDB_ERR_INVALID, "stats_out needs the CTA-pair kernel with a bias or residual epilogue");
     if (epi < 0 || epi > EPI_RES) return fail(DDB_ERR_INVALID, "epi must be 0..3");
     if (N % 256 || K0 % 64 || K1 % 64 || M < 1) return fail(DDB_ERR_INVALID, "need N%%256==0, K%%64==0, M>=1");
     if ((epi == EPI_LN || epi == EPI_LN_GELU) && (!colsum_dev || !stats_dev))
@@ -901,9 +947,12 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
     DDB_TRY(make_tmap_bf16(&g.tmA0, a0_dev, M, K0, K0, 128));
     if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, a1_dev, M, K1, K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmB, w_dev, N, K0 + K1, K0 + K1, 256));
+    DDB_TRY(make_tmap_bf16(&g.tmB2, w_dev, N, K0 + K1, K0 + K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmOut, out_dev, M, N, N, 128));
     if (residual_dev) DDB_TRY(make_tmap_bf16(&g.tmRes, residual_dev, M, N, N, 128));
-    return launch_gemm(g, epi, di.num_sms, (cudaStream_t)stream);
+    g.stats_out = reinterpret_cast<float2*>(stats_out_dev);
+    return variant == 2 ? launch_gemm2(g, epi, di.num_sms, (cudaStream_t)stream)
+                        : launch_gemm(g, epi, di.num_sms, (cudaStream_t)stream);
 }
 
 int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, int32_t variant,

@@ -34,6 +34,7 @@ struct GemmArgs {
     CUtensorMap tmA0;   // [M, K0] bf16, box {64, 128}
     CUtensorMap tmA1;   // [M, K1] bf16 (second K source; unused when K1 == 0)
     CUtensorMap tmB;    // [N, K0+K1] bf16, box {64, BN}
+    CUtensorMap tmB2;   // same tensor, box {64, 128}: one CTA's half of the W tile in the CTA-pair kernel
     CUtensorMap tmOut;  // [M, N] bf16, box {64, 128}
     CUtensorMap tmRes;  // [M, N] bf16 residual, box {64, 128}
     int M, N, K0, K1;
@@ -44,6 +45,7 @@ struct GemmArgs {
     int ln_dim;
     float ln_eps;
     const int* m_dev;  // optional: live row count read from device memory (early-exit compaction)
+    float2* stats_out;  // optional [M, N/64]: per-row (mean, M2) of every 64-column output chunk (gemm2 only)
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;

@@ -112,15 +112,19 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
                     int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream);
 /* samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146). */
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* Runtime switches for A/B measurements: "gemm_variant" = 2 (CTA-pair kernel, default) or 1 (single-CTA kernel). */
+int ddb_set_option(const char* name, int32_t value);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t ddb_launch_count(void);
 
 /* ---- single-operator entry points (used by the parity tests; same kernels as the model path) ---- */
-/* out[M,N] = epi([A0|A1] W^T); bf16 row-major operands.  epi: 0 bias, 1 LN-fold, 2 LN-fold+GELU, 3 bias+residual */
+/* out[M,N] = epi([A0|A1] W^T); bf16 row-major operands.  epi: 0 bias, 1 LN-fold, 2 LN-fold+GELU, 3 bias+residual.
+ * stats_out_dev (optional, [M, N/64, 2] f32): per-row (mean, M2) of every 64-column output chunk.
+ * variant 0: the model path's kernel; 1: single-CTA 128x256 tiles; 2: CTA-pair (cta_group::2) 256x256 tiles. */
 int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const float* bias_dev,
                 const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
-                const void* residual_dev, void* out_dev, int32_t M, int32_t N, int32_t K0, int32_t K1, int32_t epi,
-                void* stream);
+                const void* residual_dev, void* out_dev, float* stats_out_dev, int32_t M, int32_t N, int32_t K0,
+                int32_t K1, int32_t epi, int32_t variant, void* stream);
 /* softmax(q k^T / 8) v over qkv [B*L, 3*H*64] bf16 -> out [B*L, H*64] bf16 (models/uvit.py:159-164).
  * variant 0: the model path's choice (tcgen05/TMEM kernel when L = 256 + {1,2}, else the mma.sync kernel);
  * 1: force the generic mma.sync kernel; 2: force the tcgen05 kernel. */

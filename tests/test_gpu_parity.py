@@ -50,11 +50,14 @@ def _model(name, seed, hot, dev, ee=False):
 
 
 # ------------------------------------------------------------------------------------------------ operators
+@pytest.mark.parametrize("variant", [2, 1])
 @pytest.mark.parametrize("M,N,K0,K1,epi", [
     (128, 256, 64, 0, 0), (300, 512, 512, 0, 0), (1000, 512, 512, 512, 0), (1000, 1536, 512, 0, 1),
     (1000, 2048, 512, 0, 2), (1000, 512, 2048, 0, 3), (257 * 8, 768, 768, 0, 3), (1, 256, 64, 0, 0),
+    (257 * 128, 512, 512, 0, 3),
 ])
-def test_op_gemm(dev, M, N, K0, K1, epi):
+def test_op_gemm(dev, M, N, K0, K1, epi, variant):
+    """variant 2 = CTA-pair (cta_group::2) kernel of the model path, 1 = single-CTA kernel."""
     lib, L = _lib()
     g = torch.Generator().manual_seed(M + N + epi)
     a0 = (torch.randn(M, K0, generator=g) + 0.3).to(dev).bfloat16()
@@ -71,8 +74,11 @@ def test_op_gemm(dev, M, N, K0, K1, epi):
         mean = A.mean(1)
         m2 = ((A - mean[:, None]) ** 2).sum(1)
         stats = torch.stack([mean, m2], 1).contiguous()
+    want_stats = variant == 2 and epi in (0, 3)
+    sout = torch.zeros(M, N // 64, 2, device=dev) if want_stats else None
     lib.check(L.ddb_op_gemm(lib.ptr(a0), lib.ptr(a1), lib.ptr(w), lib.ptr(bias), lib.ptr(colsum), lib.ptr(stats), 1, K,
-                            lib.ptr(res), lib.ptr(out), M, N, K0, K1, epi, lib.current_stream_ptr()))
+                            lib.ptr(res), lib.ptr(out), lib.ptr(sout), M, N, K0, K1, epi, variant,
+                            lib.current_stream_ptr()))
     torch.cuda.synchronize()
     acc = A @ w.float().t()
     if epi == 0:
@@ -84,6 +90,11 @@ def test_op_gemm(dev, M, N, K0, K1, epi):
         ref = acc + bias + res.float()
     assert torch.isfinite(out.float()).all()
     assert rel_l2(out.float(), ref) <= 5e-3
+    if want_stats:  # fused LayerNorm partial statistics (fp32, before the bf16 rounding of the output)
+        chunks = ref.view(M, N // 64, 64)
+        mean = chunks.mean(-1)
+        assert rel_l2(sout[..., 0], mean) <= 1e-4
+        assert rel_l2(sout[..., 1], ((chunks - mean[..., None]) ** 2).sum(-1)) <= 1e-3
 
 
 @pytest.mark.parametrize("B,L,H,variant", [(1, 257, 1, 2), (2, 257, 8, 2), (3, 258, 12, 2), (2, 258, 16, 0),
@@ -180,6 +191,26 @@ def test_uvit_forward_golden_dims_rejected(dev):
                    qkv_bias=False, num_classes=-1, normalize_timesteps=True).to(dev)
     with pytest.raises(DuoDiffError):
         net(torch.zeros(1, 3, 8, 8, device=dev), torch.zeros(1, device=dev))
+
+
+def test_gemm_variants_agree_on_the_forward(dev):
+    """The single-CTA kernel + standalone LN statistics and the CTA-pair kernel + fused statistics are two
+    implementations of the same forward."""
+    lib, L = _lib()
+    net, sd, spec = _model("celeba", 5, True, dev)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 64, 64, generator=g).to(dev)
+    t = torch.full((3,), 77.0, device=dev)
+    a = net(x, t)
+    try:
+        lib.check(L.ddb_set_option(b"gemm_variant", 1))
+        b = net(x, t)
+    finally:
+        lib.check(L.ddb_set_option(b"gemm_variant", 2))
+    with torch.no_grad():
+        ref = O.uvit_forward(sd, spec, x, t, None)
+    assert rel_l2(a, ref) <= EPS_REL_L2 and rel_l2(b, ref) <= EPS_REL_L2
+    assert rel_l2(a, b) <= EPS_REL_L2
 
 
 def test_batch_invariance(dev):

@@ -35,7 +35,7 @@ def report(name, got, ref, tol):
     return ok
 
 
-def gemm_case(M, N, K0, K1, epi, seed=0):
+def gemm_case(M, N, K0, K1, epi, seed=0, variant=2):
     g = torch.Generator(device="cpu").manual_seed(seed)
     a0 = (torch.randn(M, K0, generator=g) * 1.0 + 0.3).to(dev).bfloat16()
     a1 = torch.randn(M, K1, generator=g).to(dev).bfloat16() if K1 else None
@@ -51,9 +51,11 @@ def gemm_case(M, N, K0, K1, epi, seed=0):
         mean = A.mean(1)
         m2 = ((A - mean[:, None]) ** 2).sum(1)
         stats = torch.stack([mean, m2], 1).contiguous()
+    want_stats = variant == 2 and epi in (0, 3)
+    sout = torch.zeros(M, N // 64, 2, device=dev) if want_stats else None
     _lib.check(L.ddb_op_gemm(_lib.ptr(a0), _lib.ptr(a1), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(colsum),
-                             _lib.ptr(stats), 1, K, _lib.ptr(res), _lib.ptr(out), M, N, K0, K1, epi,
-                             _lib.current_stream_ptr()))
+                             _lib.ptr(stats), 1, K, _lib.ptr(res), _lib.ptr(out), _lib.ptr(sout), M, N, K0, K1, epi,
+                             variant, _lib.current_stream_ptr()))
     torch.cuda.synchronize()
     acc = A @ w.float().t()
     if epi == 0:
@@ -65,12 +67,22 @@ def gemm_case(M, N, K0, K1, epi, seed=0):
             ref = torch.nn.functional.gelu(ref)
     else:
         ref = acc + bias + res.float()
-    return report(f"gemm M={M} N={N} K0={K0} K1={K1} epi={epi}", out, ref, 1e-2)
+    ok = report(f"gemm v{variant} M={M} N={N} K0={K0} K1={K1} epi={epi}", out, ref, 1e-2)
+    if want_stats:
+        chunks = ref.view(M, N // 64, 64)
+        mean = chunks.mean(-1)
+        m2 = ((chunks - mean[..., None]) ** 2).sum(-1)
+        ok &= report("   chunk mean", sout[..., 0], mean, 1e-4)
+        ok &= report("   chunk M2", sout[..., 1], m2, 1e-3)
+    return ok
 
 
 def group_gemm():
     ok = True
+    ok &= gemm_case(128, 256, 64, 0, 0, variant=1)
+    ok &= gemm_case(1000, 512, 512, 0, 3, variant=1)
     ok &= gemm_case(128, 256, 64, 0, 0)
+    ok &= gemm_case(256, 256, 64, 0, 0)
     ok &= gemm_case(128, 256, 512, 0, 0)
     ok &= gemm_case(300, 512, 512, 0, 0)
     ok &= gemm_case(1000, 512, 512, 512, 0)
