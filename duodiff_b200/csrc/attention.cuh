@@ -411,78 +411,82 @@ __global__ void __launch_bounds__(ATT2_THREADS, 2) attention_tcgen05_kernel(cons
     }
 }
 
-// Query rows [0, extras) (time / label tokens) of every (sample, head): 1-2 rows x L keys on the CUDA cores.
-// grid = B*H, 128 threads.
+// Query rows [0, extras) (time / label tokens) of every (sample, head): one warp per (sample, head, row).
+// Lane l scores keys l, l+32, ... (16-byte loads of the key rows), warp-shuffle softmax, then each lane owns two
+// output dims and streams V with coalesced 128-byte warp loads.  grid = ceil(B*H*extras / 4), 128 threads.
 __global__ void __launch_bounds__(128) attention_extras_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                __nv_bfloat16* __restrict__ out, int L, int H,
-                                                               int extras, float scale_log2e,
+                                                               int extras, float scale_log2e, int B,
                                                                const int* __restrict__ b_dev) {
-    __shared__ float sq[2][64];
-    __shared__ float sp[2][264];
-    __shared__ float red[2][4];
-    __shared__ float so[2][2][64];
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
-    if (b_dev && b >= *b_dev) return;
-    const int D = H * 64, tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int Bl = b_dev ? *b_dev : B;
+    if (wid >= Bl * H * extras) return;
+    const int e = wid % extras, bh = wid / extras;
+    const int b = bh / H, h = bh % H;
+    const int D = H * 64;
     const size_t rs = (size_t)3 * D;
     const __nv_bfloat16* base = qkv + (size_t)b * L * rs + h * 64;
-    if (tid < 64 * extras) sq[tid >> 6][tid & 63] = __bfloat162float(base[(size_t)(tid >> 6) * rs + (tid & 63)]);
-    __syncthreads();
-    // scores
-    float mx[2] = {-INFINITY, -INFINITY};
-    for (int k = tid; k < L; k += 128) {
-        const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)k * rs + D);
-        float s0 = 0.f, s1 = 0.f;
+    // q row (64 dims) in registers, identical in every lane
+    float q[64];
+    {
+        const uint4* qr = reinterpret_cast<const uint4*>(base + (size_t)e * rs);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint4 u = __ldg(kr + j);
-            const float kf[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                                 bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+            const uint4 u = __ldg(qr + j);
+            q[j * 8 + 0] = bf16_lo(u.x), q[j * 8 + 1] = bf16_hi(u.x), q[j * 8 + 2] = bf16_lo(u.y);
+            q[j * 8 + 3] = bf16_hi(u.y), q[j * 8 + 4] = bf16_lo(u.z), q[j * 8 + 5] = bf16_hi(u.z);
+            q[j * 8 + 6] = bf16_lo(u.w), q[j * 8 + 7] = bf16_hi(u.w);
+        }
+    }
+    constexpr int KPL = 9;  // keys per lane: covers L <= 288
+    float sc[KPL];
+    float mx = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                s0 = fmaf(sq[0][j * 8 + e], kf[e], s0);
-                if (extras == 2) s1 = fmaf(sq[1][j * 8 + e], kf[e], s1);
+    for (int i = 0; i < KPL; ++i) {
+        const int k = i * 32 + lane;
+        float s = -INFINITY;
+        if (k < L) {
+            const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)k * rs + D);
+            s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 u = __ldg(kr + j);
+                s = fmaf(q[j * 8 + 0], bf16_lo(u.x), s), s = fmaf(q[j * 8 + 1], bf16_hi(u.x), s);
+                s = fmaf(q[j * 8 + 2], bf16_lo(u.y), s), s = fmaf(q[j * 8 + 3], bf16_hi(u.y), s);
+                s = fmaf(q[j * 8 + 4], bf16_lo(u.z), s), s = fmaf(q[j * 8 + 5], bf16_hi(u.z), s);
+                s = fmaf(q[j * 8 + 6], bf16_lo(u.w), s), s = fmaf(q[j * 8 + 7], bf16_hi(u.w), s);
             }
         }
-        sp[0][k] = s0, mx[0] = fmaxf(mx[0], s0);
-        if (extras == 2) sp[1][k] = s1, mx[1] = fmaxf(mx[1], s1);
+        sc[i] = s;
+        mx = fmaxf(mx, s);
     }
-    for (int e = 0; e < extras; ++e) {
-        float v = mx[e];
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if ((tid & 31) == 0) red[e][tid >> 5] = v;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        sc[i] = exp2f((sc[i] - mx) * scale_log2e);  // exp2(-inf) = 0 for k >= L
+        sum += sc[i];
     }
-    __syncthreads();
-    float sm[2] = {0.f, 0.f}, gm[2];
-    for (int e = 0; e < extras; ++e) gm[e] = fmaxf(fmaxf(red[e][0], red[e][1]), fmaxf(red[e][2], red[e][3]));
-    __syncthreads();
-    for (int k = tid; k < L; k += 128)
-        for (int e = 0; e < extras; ++e) {
-            const float p = exp2f((sp[e][k] - gm[e]) * scale_log2e);
-            sp[e][k] = p;
-            sm[e] += p;
-        }
-    for (int e = 0; e < extras; ++e) {
-        float v = sm[e];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((tid & 31) == 0) red[e][tid >> 5] = v;
-    }
-    __syncthreads();
-    // O[e][d] = sum_k p[e][k] V[k][d]; thread = (half of the keys, d)
-    const int d = tid & 63, half = tid >> 6;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    // O[2*lane, 2*lane+1] = sum_k p_k V[k][.]
     float o0 = 0.f, o1 = 0.f;
-    for (int k = half; k < L; k += 2) {
-        const float v = __bfloat162float(base[(size_t)k * rs + 2 * D + d]);
-        o0 = fmaf(sp[0][k], v, o0);
-        if (extras == 2) o1 = fmaf(sp[1][k], v, o1);
+    const __nv_bfloat16* vbase = base + 2 * D + 2 * lane;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+        const int kmax = min(32, L - i * 32);
+#pragma unroll 8
+        for (int src = 0; src < 32; ++src) {
+            const float p = __shfl_sync(0xffffffffu, sc[i], src);
+            if (src < kmax) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(vbase + (size_t)(i * 32 + src) * rs));
+                o0 = fmaf(p, bf16_lo(v), o0);
+                o1 = fmaf(p, bf16_hi(v), o1);
+            }
+        }
     }
-    so[0][half][d] = o0, so[1][half][d] = o1;
-    __syncthreads();
-    if (tid < 64 * extras) {
-        const int e = tid >> 6;
-        const float tot = red[e][0] + red[e][1] + red[e][2] + red[e][3];
-        out[((size_t)b * L + e) * D + h * 64 + d] = __float2bfloat16_rn((so[e][0][d] + so[e][1][d]) / tot);
-    }
+    const float inv = 1.f / sum;
+    *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + e) * D + h * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
 }
 
 }  // namespace ddb

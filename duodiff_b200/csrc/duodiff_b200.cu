@@ -172,33 +172,46 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 }
 // runtime options (ddb_set_option): gemm_variant 2 = CTA-pair kernel (default), 1 = single-CTA kernel
 static int g_gemm_variant = 2;
+static int g_gemm_debug = 0;
 
-template <int EPI, bool STATS>
+template <int EPI, bool STATS, int STAGES, int NBUF>
 static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = gemm2_tcgen05_kernel<EPI, STATS>;
+    constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
+    constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN>::SMEM_BYTES;
+    auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF>;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         configured = true;
     }
     const int tiles = ((a.M + 255) / 256) * (a.N / 256);
+    if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
     int clusters = num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return DDB_OK;
-    kfn<<<2 * clusters, 384, Gemm2Cfg::SMEM_BYTES, st>>>(a);
+    kfn<<<2 * clusters, 384, kSmem, st>>>(a);
     LAUNCH_CHECK();
     return DDB_OK;
 }
-// CTA-pair GEMM: a.tmB must have been encoded with a 128-row box
+// CTA-pair GEMM: a.tmB2 must have been encoded with a 128-row box.  Pipeline shape per epilogue:
+//   LN / LN+GELU (K = embed_dim, epilogue-heavy): 4 operand stages, aux-staged row statistics + bias + colsum
+//   residual, K <= 512 (proj: epilogue-latency-bound): 4 stages, 3 staging buffers (residual prefetched 2 chunks ahead)
+//   residual / bias, K > 512 (fc2, skip: mainloop-bound): 5 stages, 2 staging buffers
 static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     const bool stats = a.stats_out != nullptr;
+    const bool short_k = (a.K0 + a.K1) <= 512;
     switch (epi) {
         case EPI_BIAS:
-            return stats ? launch_gemm2_t<EPI_BIAS, true>(a, num_sms, st) : launch_gemm2_t<EPI_BIAS, false>(a, num_sms, st);
-        case EPI_LN: return launch_gemm2_t<EPI_LN, false>(a, num_sms, st);
-        case EPI_LN_GELU: return launch_gemm2_t<EPI_LN_GELU, false>(a, num_sms, st);
+            return stats ? launch_gemm2_t<EPI_BIAS, true, 5, 2>(a, num_sms, st)
+                         : launch_gemm2_t<EPI_BIAS, false, 5, 2>(a, num_sms, st);
+        case EPI_LN: return launch_gemm2_t<EPI_LN, false, 4, 2>(a, num_sms, st);
+        case EPI_LN_GELU: return launch_gemm2_t<EPI_LN_GELU, false, 4, 2>(a, num_sms, st);
         case EPI_RES:
-            return stats ? launch_gemm2_t<EPI_RES, true>(a, num_sms, st) : launch_gemm2_t<EPI_RES, false>(a, num_sms, st);
+            if (short_k)
+                return stats ? launch_gemm2_t<EPI_RES, true, 4, 3>(a, num_sms, st)
+                             : launch_gemm2_t<EPI_RES, false, 4, 3>(a, num_sms, st);
+            return stats ? launch_gemm2_t<EPI_RES, true, 5, 2>(a, num_sms, st)
+                         : launch_gemm2_t<EPI_RES, false, 5, 2>(a, num_sms, st);
     }
     return fail(DDB_ERR_INVALID, "unknown CTA-pair GEMM epilogue %d", epi);
 }
@@ -252,7 +265,8 @@ static int launch_attention_tc(const AttnArgs& a, __nv_bfloat16* out, int B, cud
     if (B <= 0) return DDB_OK;
     attention_tcgen05_kernel<<<B * a.H * 2, ATT2_THREADS, ATT2_SMEM, st>>>(a);
     LAUNCH_CHECK();
-    attention_extras_kernel<<<B * a.H, 128, 0, st>>>(a.qkv, out, a.L, a.H, a.extras, a.scale_log2e, a.b_dev);
+    attention_extras_kernel<<<(B * a.H * a.extras + 3) / 4, 128, 0, st>>>(a.qkv, out, a.L, a.H, a.extras,
+                                                                       a.scale_log2e, B, a.b_dev);
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -752,6 +766,10 @@ int ddb_set_option(const char* name, int32_t value) {
     if (!strcmp(name, "gemm_variant")) {
         if (value != 1 && value != 2) return fail(DDB_ERR_INVALID, "gemm_variant must be 1 or 2");
         g_gemm_variant = value;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "gemm_debug")) {
+        g_gemm_debug = value;
         return DDB_OK;
     }
     return fail(DDB_ERR_INVALID, "unknown option '%s'", name);

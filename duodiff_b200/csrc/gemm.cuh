@@ -45,6 +45,8 @@ struct GemmArgs {
     int ln_dim;
     float ln_eps;
     const int* m_dev;  // optional: live row count read from device memory (early-exit compaction)
+    int debug;          // bench-only knobs (ddb_set_option "gemm_debug"): 1 = epilogue drains TMEM but skips math/stores,
+                        // 2 = MMA issue skipped (barrier traffic only), 4 = no TMA operand loads
     float2* stats_out;  // optional [M, N/64]: per-row (mean, M2) of every 64-column output chunk (gemm2 only)
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32

@@ -261,6 +261,45 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+// ----------------------------------------------------------------------------- packed fp32x2 math (FFMA2 on sm_100)
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t f2_to_bf16x2(f32x2 v) {
+    float lo, hi;
+    f2_unpack(v, lo, hi);
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // ----------------------------------------------------------------------------- misc
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
@@ -270,6 +309,16 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // GELU (exact-erf form, nn.GELU default) as 0.5 x (1 + tanh(x q(x^2))) with q fitted to the erf form on [-8, 8]
 // (max abs deviation 2.5e-5 before the tanh.approx error of ~2^-11 relative; well inside bf16 output rounding).
 // x^2 is clamped so the cubic-in-x^2 inner polynomial stays monotone for any input.
+__device__ __forceinline__ f32x2 gelu_fast2(f32x2 x) {
+    float a, b;
+    f2_unpack(f2_mul(x, x), a, b);
+    const f32x2 x2 = f2_pack(fminf(a, 64.f), fminf(b, 64.f));
+    const f32x2 q = f2_fma(f2_fma(f2_splat(-0.00035151747709065645f), x2, f2_splat(0.0370056505644417f)), x2,
+                           f2_splat(0.7975078789081762f));
+    const f32x2 hx = f2_mul(x, f2_splat(0.5f));
+    f2_unpack(f2_mul(x, q), a, b);
+    return f2_fma(hx, f2_pack(tanh_approx(a), tanh_approx(b)), hx);
+}
 __device__ __forceinline__ float gelu_fast(float x) {
     const float x2 = fminf(x * x, 64.f);
     const float q = fmaf(fmaf(-0.00035151747709065645f, x2, 0.0370056505644417f), x2, 0.7975078789081762f);
