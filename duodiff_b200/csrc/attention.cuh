@@ -1,12 +1,13 @@
 // Fused non-causal attention for U-ViT (models/uvit.py:155-166): softmax(q k^T / sqrt(64)) v per (sample, head).
 // Sequence length is 257/258 in every config and head_dim is 64, so K and V of one (sample, head) live in
-// shared memory for the whole CTA and the score matrix never touches HBM.
+// shared memory for the whole work item and the score matrix never touches HBM.
 //
 // Input  qkv [B*L, 3*D] bf16, feature index = k*(H*64) + h*64 + d  (k in {q,k,v}; models/uvit.py:159-161)
 // Output o   [B*L, D]   bf16, feature index = h*64 + d             (models/uvit.py:164)
 //
-// v1: mma.sync.m16n8k16 (bf16 -> fp32) with online softmax; one CTA per (sample, head), 8 warps, each warp
-// owns 16-query-row blocks.
+// Two kernels:
+//   attention_mma_kernel      generic L (any length that fits shared memory): mma.sync.m16n8k16 + online softmax
+//   attention_tcgen05_kernel  the model path for L = 256 + extras: persistent, warp-specialised, tcgen05 / TMEM
 #pragma once
 #include "ptx.cuh"
 
@@ -37,9 +38,108 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 constexpr int ATT_THREADS = 256;
 
-// smem row = one key (64 bf16 = 128 B), 16-byte chunks XOR-swizzled by (row & 7)
+// smem row = one key (64 bf16 = 128 B), 16-byte chunks XOR-swizzled by (row & 7): the TMA SWIZZLE_128B pattern
 __device__ __forceinline__ uint32_t att_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// Online-softmax state of one warp's 16-query-row block (mma.sync fragment layout: lane = 4*g + t owns rows g, g+8).
+struct AttRowState {
+    float o[8][4];
+    float m0, m1, l0, l1;
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        m0 = m1 = -INFINITY;
+        l0 = l1 = 0.f;
+    }
+};
+
+// One block of up to 64 keys: S = Q K^T, online softmax, O += P V.  sK/sV: swizzled [key][64] bf16 tiles (shared
+// addresses) indexed by absolute key; keys >= kend are masked.  nt = number of 8-key n-tiles in the block (V must be
+// readable for an even number of them).
+__device__ __forceinline__ void att_mma_block(uint32_t sK_u, uint32_t sV_u, int kb0, int nt, int kend,
+                                              const uint32_t (&qf)[4][4], AttRowState& st, float scale_log2e,
+                                              int lane) {
+    const int t = lane & 3;
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        if (j < nt) {
+            const int key = kb0 + j * 8 + (lane & 7);
+            const int cs = lane >> 3;  // which 8x8 matrix this lane addresses (dim chunk)
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(sK_u + att_swz(key, cs), b0, b1, b2, b3);  // dims 0..31
+            mma_bf16_16816(s[j], qf[0], b0, b1);
+            mma_bf16_16816(s[j], qf[1], b2, b3);
+            ldmatrix_x4(sK_u + att_swz(key, cs + 4), b0, b1, b2, b3);  // dims 32..63
+            mma_bf16_16816(s[j], qf[2], b0, b1);
+            mma_bf16_16816(s[j], qf[3], b2, b3);
+        }
+    }
+    // mask padded keys, block row max
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nt) {
+            const int key = kb0 + j * 8 + 2 * t;
+            if (key >= kend) s[j][0] = s[j][2] = -INFINITY;
+            if (key + 1 >= kend) s[j][1] = s[j][3] = -INFINITY;
+            bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
+            bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
+        }
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(st.m0, bm0), nm1 = fmaxf(st.m1, bm1);  // finite: every block has a valid key
+    const float corr0 = exp2f((st.m0 - nm0) * scale_log2e), corr1 = exp2f((st.m1 - nm1) * scale_log2e);
+    st.m0 = nm0, st.m1 = nm1;
+    const float ms0 = nm0 * scale_log2e, ms1 = nm1 * scale_log2e;
+    float ps0 = 0.f, ps1 = 0.f;
+    uint32_t pf[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nt) {
+            const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -ms0));
+            const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -ms0));
+            const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -ms1));
+            const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -ms1));
+            ps0 += p0 + p1;
+            ps1 += p2 + p3;
+            pf[j][0] = pack_bf16(p0, p1);
+            pf[j][1] = pack_bf16(p2, p3);
+        } else {
+            pf[j][0] = pf[j][1] = 0u;
+        }
+    }
+    st.l0 = st.l0 * corr0 + ps0;
+    st.l1 = st.l1 * corr1 + ps1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        st.o[i][0] *= corr0, st.o[i][1] *= corr0;
+        st.o[i][2] *= corr1, st.o[i][3] *= corr1;
+    }
+    // O += P V  (k-steps of 16 keys)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (2 * kk < nt) {
+            const uint32_t pa[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
+            // ldmatrix.trans: matrices (keys 0-7, dims d..d+7), (keys 8-15, same dims), then dims +8
+            const int key = kb0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int dsel = lane >> 4;  // 0/1 -> dim chunk offset
+#pragma unroll
+            for (int dn = 0; dn < 4; ++dn) {
+                uint32_t v0, v1, v2, v3;
+                ldmatrix_x4_trans(sV_u + att_swz(key, dn * 2 + dsel), v0, v1, v2, v3);
+                mma_bf16_16816(st.o[dn * 2], pa, v0, v1);
+                mma_bf16_16816(st.o[dn * 2 + 1], pa, v2, v3);
+            }
+        }
+    }
+}
+
+// Generic-L kernel: one CTA per (sample, head), 8 warps, each warp owns 16-query-row blocks.
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                    __nv_bfloat16* __restrict__ out, int L, int H,
                                                                    float scale_log2e) {
@@ -86,91 +186,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_mma_kernel(const __n
                 qf[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(q1 + ks * 16 + 8 + 2 * t));
             }
         }
-        float o[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-
-        for (int kb0 = 0; kb0 < Lp; kb0 += 64) {
-            const int nt = min(8, (Lp - kb0) >> 3);  // 8-key n-tiles in this block (even)
-            float s[8][4];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                if (j < nt) {
-                    const int key = kb0 + j * 8 + (lane & 7);
-                    const int cs = lane >> 3;  // which 8x8 matrix this lane addresses (dim chunk)
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(sK_u + att_swz(key, cs), b0, b1, b2, b3);  // dims 0..31
-                    mma_bf16_16816(s[j], qf[0], b0, b1);
-                    mma_bf16_16816(s[j], qf[1], b2, b3);
-                    ldmatrix_x4(sK_u + att_swz(key, cs + 4), b0, b1, b2, b3);  // dims 32..63
-                    mma_bf16_16816(s[j], qf[2], b0, b1);
-                    mma_bf16_16816(s[j], qf[3], b2, b3);
-                }
-            }
-            // mask padded keys, block row max
-            float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < nt) {
-                    const int key = kb0 + j * 8 + 2 * t;
-                    if (key >= L) s[j][0] = s[j][2] = -INFINITY;
-                    if (key + 1 >= L) s[j][1] = s[j][3] = -INFINITY;
-                    bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
-                    bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
-                }
-            }
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-            const float nm0 = fmaxf(m0, bm0), nm1 = fmaxf(m1, bm1);  // finite: every block has a valid key
-            const float corr0 = exp2f((m0 - nm0) * scale_log2e), corr1 = exp2f((m1 - nm1) * scale_log2e);
-            m0 = nm0, m1 = nm1;
-            const float ms0 = nm0 * scale_log2e, ms1 = nm1 * scale_log2e;
-            float ps0 = 0.f, ps1 = 0.f;
-            uint32_t pf[8][2];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < nt) {
-                    const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -ms0));
-                    const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -ms0));
-                    const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -ms1));
-                    const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -ms1));
-                    ps0 += p0 + p1;
-                    ps1 += p2 + p3;
-                    pf[j][0] = pack_bf16(p0, p1);
-                    pf[j][1] = pack_bf16(p2, p3);
-                } else {
-                    pf[j][0] = pf[j][1] = 0u;
-                }
-            }
-            l0 = l0 * corr0 + ps0;
-            l1 = l1 * corr1 + ps1;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                o[i][0] *= corr0, o[i][1] *= corr0;
-                o[i][2] *= corr1, o[i][3] *= corr1;
-            }
-            // O += P V  (k-steps of 16 keys)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                if (2 * kk < nt) {
-                    const uint32_t pa[4] = {pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1]};
-                    // ldmatrix.trans: matrices (keys 0-7, dims d..d+7), (keys 8-15, same dims), then dims +8
-                    const int key = kb0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                    const int dsel = lane >> 4;  // 0/1 -> dim chunk offset
-#pragma unroll
-                    for (int dn = 0; dn < 4; ++dn) {
-                        uint32_t v0, v1, v2, v3;
-                        ldmatrix_x4_trans(sV_u + att_swz(key, dn * 2 + dsel), v0, v1, v2, v3);
-                        mma_bf16_16816(o[dn * 2], pa, v0, v1);
-                        mma_bf16_16816(o[dn * 2 + 1], pa, v2, v3);
-                    }
-                }
-            }
-        }
+        AttRowState st;
+        st.init();
+        for (int kb0 = 0; kb0 < Lp; kb0 += 64)
+            att_mma_block(sK_u, sV_u, kb0, min(8, (Lp - kb0) >> 3), L, qf, st, scale_log2e, lane);
+        float l0 = st.l0, l1 = st.l1;
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
         l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -181,312 +201,357 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_mma_kernel(const __n
         __nv_bfloat16* o1 = out + ((size_t)b * L + row1) * D + h * 64 + 2 * t;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (row0 < L) *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(o[i][0] * inv0, o[i][1] * inv0);
-            if (row1 < L) *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_bf16(o[i][2] * inv1, o[i][3] * inv1);
+            if (row0 < L) *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(st.o[i][0] * inv0, st.o[i][1] * inv0);
+            if (row1 < L) *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_bf16(st.o[i][2] * inv1, st.o[i][3] * inv1);
         }
     }
 }
 
-
 // =====================================================================================================
-// v2: tcgen05 / TMEM attention for the 256-patch-token layout of every reference config (L = 256 + extras).
+// Persistent, warp-specialised tcgen05 / TMEM attention for the 256-patch-token layout of every reference
+// config (L = 256 + extras, extras = 1 time token (+ 1 label token)).
 //
-// One CTA per (sample, head, 128-query tile); 2 CTAs co-reside per SM (80 KB smem, 256 TMEM columns each) so the
-// softmax of one overlaps the MMAs / TMA loads of the other.
-//   keys   [extras, L)  (the 256 patch tokens): S = Q K^T on the tensor core, M=128 x N=256 x K=64, fp32 in TMEM
-//   keys   [0, extras)  (time / label tokens):  1-2 dot products per query row on the CUDA cores
-//   softmax: one thread per query row reads its S row from TMEM (no shuffles), writes P (bf16, packed) back over
-//            the first 128 columns of S; O = P V accumulates in columns [128,192) of the same allocation with
-//            A = P from TMEM and B = V (MN-major, 128B swizzle) from shared memory.
-// The query rows [0, extras) are handled by attention_extras_kernel below.
+// One CTA per SM; a work item is one (sample, head): K and V are TMA-loaded ONCE per item and shared by the two
+// 128-query tiles and the extras query rows; operands are double-buffered across items, and the tensor-core work
+// of one tile overlaps the softmax of the other:
+//   warps 0-3  softmax warpgroup of query tile 0 (one thread per query row, no shuffles)
+//   warps 4-7  softmax warpgroup of query tile 1
+//   warp  8    TMA producer: {Q0, Q1, K, V, X} of item i+1 while item i is being processed (2 x 102 KB stages);
+//              X = tokens 0..15 of the sample (q, k and v slices): the extras tokens plus don't-care patch tokens
+//   warp  9    MMA issuer + TMEM owner (512 columns = 2 tiles x 256); event-driven over both tiles' barriers
+//   warp  10   extras QUERY rows (tokens [0, extras)) on mma.sync from the same shared-memory K / V tiles
+// Per tile t (TMEM columns relative to 256 t):
+//   S_t = Q_t K^T          M=128, N=256 (patch keys), K=64; fp32 in [0, 256)
+//   extras KEY scores      1-2 dot products per query row on the CUDA cores (k rows read from the X tile)
+//   softmax                pass 1 row max (FMNMX3), pass 2 P = exp2(s*c - m*c) -> bf16 written back over [0, 128)
+//                          (each TMEM load is issued one chunk ahead of the math on the previous chunk); the extras
+//                          keys' probabilities go to [128, 136) as a 17th k-step of 16 keys (14-15 of them zero)
+//   O_t = P_t [V; V_x]     A = P from TMEM, B = V (MN-major) from smem, 17 k-steps, fp32 in [192, 256)
+//   epilogue               O row / sum -> bf16 -> the tile's own (dead) Q buffer -> TMA store
 // =====================================================================================================
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 struct AttnArgs {
     CUtensorMap tmQKV;  // [B, L, 3D] bf16, box {64, 128, 1}
     CUtensorMap tmKV;   // [B, L, 3D] bf16, box {64, 256, 1}
+    CUtensorMap tmX;    // [B, L, 3D] bf16, box {64, 16, 1}
     CUtensorMap tmOut;  // [B, L, D]  bf16, box {64, 128, 1}
     const __nv_bfloat16* qkv;
-    int L, H, extras;
+    __nv_bfloat16* out;
+    int L, H, extras, B;
     float scale_log2e;
     const int* b_dev;  // optional live batch size (early-exit compaction)
 };
 
-constexpr int ATT2_THREADS = 192;
-constexpr int ATT2_SMEM = 16384 + 32768 + 32768 + 1024 + 128;
+constexpr int ATT3_THREADS = 352;
+// stage: Q0 16K | Q1 16K | K 32K | V 32K | Vx 2K (must follow V: 17th k-step of the PV MMA) | Kx 2K | Qx 2K
+constexpr int ATT3_OFF_K = 32768, ATT3_OFF_V = 65536, ATT3_OFF_VX = 98304, ATT3_OFF_KX = 100352, ATT3_OFF_QX = 102400;
+constexpr int ATT3_STAGE = 104448;
+constexpr int ATT3_OFF_BAR = 2 * ATT3_STAGE;
+constexpr int ATT3_SMEM = ATT3_OFF_BAR + 256;
+constexpr uint32_t ATT3_QK_BYTES = 16384 + 16384 + 32768 + 2048 + 2048, ATT3_V_BYTES = 32768 + 2048;
 
-__global__ void __launch_bounds__(ATT2_THREADS, 2) attention_tcgen05_kernel(const __grid_constant__ AttnArgs a) {
-    extern __shared__ uint8_t att2_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(att2_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;           // 128 x 128 B (later reused as the output staging tile)
-    uint8_t* sK = smem + 16384;   // 256 x 128 B
-    uint8_t* sV = smem + 49152;   // 256 x 128 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 81920);
-    uint64_t* qk_full = bars + 0;
-    uint64_t* v_full = bars + 1;
-    uint64_t* s_full = bars + 2;
-    uint64_t* p_full = bars + 3;
-    uint64_t* o_full = bars + 4;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+__global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(const __grid_constant__ AttnArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT3_OFF_BAR);
+    uint64_t* qk_full = bars + 0;      // [2] per operand stage
+    uint64_t* v_full = bars + 2;       // [2]
+    uint64_t* stage_empty = bars + 4;  // [2] 4 arrivals: PV MMAs retired, both tiles' TMA stores read, extras warp
+    uint64_t* s_full = bars + 6;       // [2] per query tile
+    uint64_t* p_full = bars + 8;       // [2]
+    uint64_t* o_full = bars + 10;      // [2]
+    uint64_t* tmem_free = bars + 12;   // [2]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x & 1;
-    const int bh = blockIdx.x >> 1;
-    const int b = bh / a.H, h = bh % a.H;
-    if (a.b_dev && b >= *a.b_dev) return;
     const int D = a.H * 64;
-    const int q0 = a.extras + tile * 128;
+    const int n_items = (a.b_dev ? *a.b_dev : a.B) * a.H;
+    const int my_items =
+        (n_items > (int)blockIdx.x) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (warp == 0 && lane == 0) {
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // swizzled tiles need 1024-byte alignment
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&a.tmQKV);
         tma_prefetch_desc(&a.tmKV);
+        tma_prefetch_desc(&a.tmX);
         tma_prefetch_desc(&a.tmOut);
-        mbar_init(qk_full, 1);
-        mbar_init(v_full, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_full, 4);
-        mbar_init(o_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&stage_empty[i], 4);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 4);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&tmem_free[i], 4);
+        }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<256>(tmem_holder);
+    if (warp == 9) tmem_alloc<512>(tmem_holder);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
 
-    if (warp == 0) {
+    if (warp == 8) {
+        // ================================================================= TMA producer
         if (lane == 0) {
-            mbar_expect_tx(qk_full, 16384 + 32768);
-            tma_load_3d(sQ, &a.tmQKV, qk_full, h * 64, q0, b);
-            tma_load_3d(sK, &a.tmKV, qk_full, D + h * 64, a.extras, b);
-            mbar_expect_tx(v_full, 32768);
-            tma_load_3d(sV, &a.tmKV, v_full, 2 * D + h * 64, a.extras, b);
+            for (int it = 0; it < my_items; ++it) {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int b = item / a.H, h = item % a.H;
+                const int s = it & 1;
+                uint8_t* st = smem + s * ATT3_STAGE;
+                mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
+                mbar_expect_tx(&qk_full[s], ATT3_QK_BYTES);
+                tma_load_3d(st + ATT3_OFF_K, &a.tmKV, &qk_full[s], D + h * 64, a.extras, b);
+                tma_load_3d(st, &a.tmQKV, &qk_full[s], h * 64, a.extras, b);
+                tma_load_3d(st + 16384, &a.tmQKV, &qk_full[s], h * 64, a.extras + 128, b);
+                tma_load_3d(st + ATT3_OFF_KX, &a.tmX, &qk_full[s], D + h * 64, 0, b);
+                tma_load_3d(st + ATT3_OFF_QX, &a.tmX, &qk_full[s], h * 64, 0, b);
+                mbar_expect_tx(&v_full[s], ATT3_V_BYTES);
+                tma_load_3d(st + ATT3_OFF_V, &a.tmKV, &v_full[s], 2 * D + h * 64, a.extras, b);
+                tma_load_3d(st + ATT3_OFF_VX, &a.tmX, &v_full[s], 2 * D + h * 64, 0, b);
+            }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(qk_full, 0);
-            tc_fence_after();
-            const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(sQ));
-            const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(sK));
+    } else if (warp == 9) {
+        // ================================================================= MMA issuer (one thread, event-driven)
+        if (lane == 0 && my_items > 0) {
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ss(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-            umma_commit(s_full);
-            mbar_wait(p_full, 0);
-            mbar_wait(v_full, 0);
-            tc_fence_after();
-            const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(sV));
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+            int s_it[2] = {0, 0};   // next item whose S_t has not been issued
+            int pv_it[2] = {0, 0};  // next item whose O_t = P_t V has not been issued
+            while (pv_it[0] < my_items || pv_it[1] < my_items) {
+                bool progressed = false;
 #pragma unroll
-            for (int k = 0; k < 16; ++k)  // 16 keys per step: P columns +8, V rows +16 (2048 B)
-                umma_f16_ts(tmem + 128, tmem + 8 * k, dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
-            umma_commit(o_full);
+                for (int t = 0; t < 2; ++t) {
+                    // S_t(i): needs the operands of item i and the tile's TMEM columns (O_t(i-1) drained)
+                    int i = s_it[t];
+                    if (i < my_items && i == pv_it[t] && mbar_test(&tmem_free[t], (i & 1) ^ 1) &&
+                        mbar_test(&qk_full[i & 1], (i >> 1) & 1)) {
+                        tc_fence_after();
+                        const uint8_t* st = smem + (i & 1) * ATT3_STAGE;
+                        const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(st + t * 16384));
+                        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(st + ATT3_OFF_K));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ss(tmem + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                        umma_commit(&s_full[t]);
+                        s_it[t] = i + 1;
+                        progressed = true;
+                    }
+                    // O_t(i) = P_t [V; V_x]: needs P_t(i) and V of item i
+                    i = pv_it[t];
+                    if (i < my_items && s_it[t] > i && mbar_test(&p_full[t], i & 1) &&
+                        mbar_test(&v_full[i & 1], (i >> 1) & 1)) {
+                        tc_fence_after();
+                        const uint8_t* st = smem + (i & 1) * ATT3_STAGE;
+                        const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(st + ATT3_OFF_V));
+#pragma unroll
+                        for (int k = 0; k < 17; ++k)  // 16 keys per step: P columns +8, V rows +16 (2048 B)
+                            umma_f16_ts(tmem + t * 256 + 192, tmem + t * 256 + 8 * k,
+                                        dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
+                        umma_commit(&o_full[t]);
+                        pv_it[t] = i + 1;
+                        // once both tiles' PV MMAs of item i are issued, their retirement frees the operand stage
+                        if (pv_it[t ^ 1] > i) umma_commit(&stage_empty[i & 1]);
+                        progressed = true;
+                    }
+                }
+                if (!progressed) __nanosleep(32);
+            }
+        }
+    } else if (warp == 10) {
+        // ================================================================= extras query rows on mma.sync
+        const int g = lane >> 2, t = lane & 3;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / a.H, h = item % a.H;
+            const int s = it & 1;
+            const uint8_t* st = smem + s * ATT3_STAGE;
+            mbar_wait(&qk_full[s], (it >> 1) & 1);
+            // A fragments: rows g (token g of the sample; only g < extras is kept), rows g+8 are zero
+            uint32_t qf[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qf[ks][0] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2) + 4 * t);
+                qf[ks][2] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2 + 1) + 4 * t);
+                qf[ks][1] = qf[ks][3] = 0u;
+            }
+            AttRowState rs;
+            rs.init();
+            mbar_wait(&v_full[s], (it >> 1) & 1);
+            // extras keys: the first 8 tokens of the X tile, of which [0, extras) are valid
+            att_mma_block(smem_u32(st + ATT3_OFF_KX), smem_u32(st + ATT3_OFF_VX), 0, 1, a.extras, qf, rs, a.scale_log2e,
+                          lane);
+            const uint32_t sK_u = smem_u32(st + ATT3_OFF_K), sV_u = smem_u32(st + ATT3_OFF_V);
+#pragma unroll 1
+            for (int kb0 = 0; kb0 < 256; kb0 += 64) att_mma_block(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stage_empty[s]);  // this warp no longer reads the stage
+            float l0 = rs.l0;
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            if (g < a.extras) {
+                const float inv0 = 1.f / l0;
+                __nv_bfloat16* o0 = a.out + ((size_t)b * a.L + g) * D + h * 64 + 2 * t;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(rs.o[i][0] * inv0, rs.o[i][1] * inv0);
+            }
         }
     } else {
         // ================================================================= softmax + epilogue: one thread per query row
+        const int t = warp >> 2;  // query tile == warpgroup
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
-        const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16);
+        const int et = threadIdx.x & 127;
+        const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16) + t * 256;
         const float c = a.scale_log2e;
-        const __nv_bfloat16* xrow = a.qkv + (size_t)b * a.L * 3 * D;  // extras tokens of this sample
+        const int q0 = a.extras + t * 128;
 
-        // scores against the extras keys on the CUDA cores (overlaps the Q K^T MMA)
-        mbar_wait(qk_full, 0);
-        float se[2] = {-INFINITY, -INFINITY};
-        {
-            float acc0 = 0.f, acc1 = 0.f;
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / a.H, h = item % a.H;
+            const int s = it & 1;
+            const uint32_t ph = it & 1;
+            uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;  // this tile's Q; later its output staging buffer
+            const uint8_t* sKx = smem + s * ATT3_STAGE + ATT3_OFF_KX;
+
+            // scores against the extras keys on the CUDA cores (overlaps the Q K^T MMA)
+            mbar_wait(&qk_full[s], (it >> 1) & 1);
+            float se0 = 0.f, se1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((j ^ (r & 7)) << 4));
                 const float qf[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
                                      bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-                const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(xrow + D + h * 64) + j);
+                const uint4 k0 = *reinterpret_cast<const uint4*>(sKx + att_swz(0, j));
                 const float kf[8] = {bf16_lo(k0.x), bf16_hi(k0.x), bf16_lo(k0.y), bf16_hi(k0.y),
                                      bf16_lo(k0.z), bf16_hi(k0.z), bf16_lo(k0.w), bf16_hi(k0.w)};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc0 = fmaf(qf[e], kf[e], acc0);
+                for (int e = 0; e < 8; ++e) se0 = fmaf(qf[e], kf[e], se0);
                 if (a.extras == 2) {
-                    const uint4 k1 = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * D + D + h * 64) + j);
+                    const uint4 k1 = *reinterpret_cast<const uint4*>(sKx + att_swz(1, j));
                     const float kg[8] = {bf16_lo(k1.x), bf16_hi(k1.x), bf16_lo(k1.y), bf16_hi(k1.y),
                                          bf16_lo(k1.z), bf16_hi(k1.z), bf16_lo(k1.w), bf16_hi(k1.w)};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc1 = fmaf(qf[e], kg[e], acc1);
+                    for (int e = 0; e < 8; ++e) se1 = fmaf(qf[e], kg[e], se1);
                 }
             }
-            se[0] = acc0;
-            if (a.extras == 2) se[1] = acc1;
-        }
+            if (a.extras != 2) se1 = -INFINITY;
 
-        mbar_wait(s_full, 0);
-        tc_fence_after();
-        // pass 1: row max
-        float m = fmaxf(se[0], se[1]);
-#pragma unroll 1
-        for (int j = 0; j < 8; j += 2) {
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(t_row + j * 32, v0);
-            tmem_ld_32x32b_x32(t_row + j * 32 + 32, v1);
+            mbar_wait(&s_full[t], ph);
+            tc_fence_after();
+            uint32_t va[32], vb[32];
+            // ---- pass 1: row max; the load of chunk j+1 is in flight while chunk j is reduced
+            float m0 = se0, m1 = se1, m2 = -INFINITY, m3 = -INFINITY;
+            tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) m = fmaxf(m, fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e])));
-        }
-        const float mc = m * c;
-        float sum = ex2_approx(fmaf(se[0], c, -mc));
-        float pe[2] = {sum, 0.f};
-        if (a.extras == 2) {
-            pe[1] = ex2_approx(fmaf(se[1], c, -mc));
-            sum += pe[1];
-        }
-        // pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
-#pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(t_row + j * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), c, -mc));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), c, -mc));
-                sum += p0 + p1;
-                pk[e] = pack_bf16(p0, p1);
-            }
-            tmem_st_32x32b_x16(t_row + j * 16, pk);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-
-        // epilogue: O row (fp32) + extras-key contributions, normalise, bf16 -> smem (Q tile is dead) -> TMA store
-        const float inv = 1.f / sum;
-        mbar_wait(o_full, 0);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(t_row + 128, o0);
-        tmem_ld_32x32b_x32(t_row + 160, o1);
-        tmem_ld_wait();
-        uint8_t* srow = sQ + r * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float o[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(j < 4 ? o0[j * 8 + e] : o1[(j - 4) * 8 + e]);
-            const uint4 va = __ldg(reinterpret_cast<const uint4*>(xrow + 2 * D + h * 64) + j);
-            const float vf[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
-                                 bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaf(pe[0], vf[e], o[e]);
-            if (a.extras == 2) {
-                const uint4 vb = __ldg(reinterpret_cast<const uint4*>(xrow + 3 * D + 2 * D + h * 64) + j);
-                const float vg[8] = {bf16_lo(vb.x), bf16_hi(vb.x), bf16_lo(vb.y), bf16_hi(vb.y),
-                                     bf16_lo(vb.z), bf16_hi(vb.z), bf16_lo(vb.w), bf16_hi(vb.w)};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = fmaf(pe[1], vg[e], o[e]);
-            }
-            uint4 w;
-            w.x = pack_bf16(o[0] * inv, o[1] * inv);
-            w.y = pack_bf16(o[2] * inv, o[3] * inv);
-            w.z = pack_bf16(o[4] * inv, o[5] * inv);
-            w.w = pack_bf16(o[6] * inv, o[7] * inv);
-            *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (warp == 2 && lane == 0) {
-            tma_store_3d(&a.tmOut, sQ, h * 64, q0, b);
-            tma_store_commit();
-            tma_store_wait_all<0>();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc<256>(tmem);
-    }
-}
-
-// Query rows [0, extras) (time / label tokens) of every (sample, head): one warp per (sample, head, row).
-// Lane l scores keys l, l+32, ... (16-byte loads of the key rows), warp-shuffle softmax, then each lane owns two
-// output dims and streams V with coalesced 128-byte warp loads.  grid = ceil(B*H*extras / 4), 128 threads.
-__global__ void __launch_bounds__(128) attention_extras_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                               __nv_bfloat16* __restrict__ out, int L, int H,
-                                                               int extras, float scale_log2e, int B,
-                                                               const int* __restrict__ b_dev) {
-    const int lane = threadIdx.x & 31;
-    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int Bl = b_dev ? *b_dev : B;
-    if (wid >= Bl * H * extras) return;
-    const int e = wid % extras, bh = wid / extras;
-    const int b = bh / H, h = bh % H;
-    const int D = H * 64;
-    const size_t rs = (size_t)3 * D;
-    const __nv_bfloat16* base = qkv + (size_t)b * L * rs + h * 64;
-    // q row (64 dims) in registers, identical in every lane
-    float q[64];
-    {
-        const uint4* qr = reinterpret_cast<const uint4*>(base + (size_t)e * rs);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 u = __ldg(qr + j);
-            q[j * 8 + 0] = bf16_lo(u.x), q[j * 8 + 1] = bf16_hi(u.x), q[j * 8 + 2] = bf16_lo(u.y);
-            q[j * 8 + 3] = bf16_hi(u.y), q[j * 8 + 4] = bf16_lo(u.z), q[j * 8 + 5] = bf16_hi(u.z);
-            q[j * 8 + 6] = bf16_lo(u.w), q[j * 8 + 7] = bf16_hi(u.w);
-        }
-    }
-    constexpr int KPL = 9;  // keys per lane: covers L <= 288
-    float sc[KPL];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-        const int k = i * 32 + lane;
-        float s = -INFINITY;
-        if (k < L) {
-            const uint4* kr = reinterpret_cast<const uint4*>(base + (size_t)k * rs + D);
-            s = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint4 u = __ldg(kr + j);
-                s = fmaf(q[j * 8 + 0], bf16_lo(u.x), s), s = fmaf(q[j * 8 + 1], bf16_hi(u.x), s);
-                s = fmaf(q[j * 8 + 2], bf16_lo(u.y), s), s = fmaf(q[j * 8 + 3], bf16_hi(u.y), s);
-                s = fmaf(q[j * 8 + 4], bf16_lo(u.z), s), s = fmaf(q[j * 8 + 5], bf16_hi(u.z), s);
-                s = fmaf(q[j * 8 + 6], bf16_lo(u.w), s), s = fmaf(q[j * 8 + 7], bf16_hi(u.w), s);
+                uint32_t(&cur)[32] = (j & 1) ? vb : va;
+                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    m0 = fmax3(m0, __uint_as_float(cur[e + 0]), __uint_as_float(cur[e + 1]));
+                    m1 = fmax3(m1, __uint_as_float(cur[e + 2]), __uint_as_float(cur[e + 3]));
+                    m2 = fmax3(m2, __uint_as_float(cur[e + 4]), __uint_as_float(cur[e + 5]));
+                    m3 = fmax3(m3, __uint_as_float(cur[e + 6]), __uint_as_float(cur[e + 7]));
+                }
+                if (j < 7) tmem_ld_wait();
+            }
+            const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+            const float pe0 = ex2_approx(fmaf(se0, c, -mc));
+            const float pe1 = (a.extras == 2) ? ex2_approx(fmaf(se1, c, -mc)) : 0.f;
+            // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
+            const f32x2 c2 = f2_splat(c), nmc2 = f2_splat(-mc);
+            f32x2 sum2 = f2_pack(pe0, pe1), sum2b = f2_splat(0.f);
+            tmem_ld_32x32b_x32(t_row, va);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t(&cur)[32] = (j & 1) ? vb : va;
+                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
+                if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+                uint32_t pk[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    float x0, x1;
+                    f2_unpack(f2_fma(f2_pack_u(cur[2 * e], cur[2 * e + 1]), c2, nmc2), x0, x1);
+                    const f32x2 p = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                    if (e & 1)
+                        sum2b = f2_add(sum2b, p);
+                    else
+                        sum2 = f2_add(sum2, p);
+                    pk[e] = f2_to_bf16x2(p);
+                }
+                if (j < 7) tmem_ld_wait();
+                // P chunk j lands in columns [16j, 16j+16): inside S chunk j/2, which is already in registers
+                tmem_st_32x32b_x16(t_row + j * 16, pk);
+            }
+            {
+                // 17th k-step: keys = tokens 0..15 of the sample, non-zero weight only for the extras tokens
+                const uint32_t px[8] = {pack_bf16(pe0, pe1), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st_32x32b_x8(t_row + 128, px);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[t]);
+            float sa, sb, sc, sd;
+            f2_unpack(sum2, sa, sb);
+            f2_unpack(sum2b, sc, sd);
+            const float inv = 1.f / ((sa + sb) + (sc + sd));
+
+            // ---- epilogue: O row (fp32) out of TMEM, then release the tile's columns for S_t of the next item
+            mbar_wait(&o_full[t], ph);
+            tc_fence_after();
+            tmem_ld_32x32b_x32(t_row + 192, va);
+            tmem_ld_32x32b_x32(t_row + 224, vb);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_free[t]);
+            // row r of the Q tile is only ever touched by this thread and by the (retired) S MMA: reuse it as staging
+            uint8_t* srow = sQ + r * 128;
+            const f32x2 inv2 = f2_splat(inv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t* o = (j < 4) ? &va[j * 8] : &vb[(j - 4) * 8];
+                uint4 w;
+                w.x = f2_to_bf16x2(f2_mul(f2_pack_u(o[0], o[1]), inv2));
+                w.y = f2_to_bf16x2(f2_mul(f2_pack_u(o[2], o[3]), inv2));
+                w.z = f2_to_bf16x2(f2_mul(f2_pack_u(o[4], o[5]), inv2));
+                w.w = f2_to_bf16x2(f2_mul(f2_pack_u(o[6], o[7]), inv2));
+                *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + t, 128);
+            if (et == 0) {
+                tma_store_3d(&a.tmOut, sQ, h * 64, q0, b);
+                tma_store_commit();
+                tma_store_wait_read<0>();       // the store has read the staging tile ...
+                mbar_arrive(&stage_empty[s]);   // ... so the producer may overwrite this stage's Q_t
             }
         }
-        sc[i] = s;
-        mx = fmaxf(mx, s);
+        if (et == 0) tma_store_wait_all<0>();
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-        sc[i] = exp2f((sc[i] - mx) * scale_log2e);  // exp2(-inf) = 0 for k >= L
-        sum += sc[i];
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
     }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    // O[2*lane, 2*lane+1] = sum_k p_k V[k][.]
-    float o0 = 0.f, o1 = 0.f;
-    const __nv_bfloat16* vbase = base + 2 * D + 2 * lane;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-        const int kmax = min(32, L - i * 32);
-#pragma unroll 8
-        for (int src = 0; src < 32; ++src) {
-            const float p = __shfl_sync(0xffffffffu, sc[i], src);
-            if (src < kmax) {
-                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(vbase + (size_t)(i * 32 + src) * rs));
-                o0 = fmaf(p, bf16_lo(v), o0);
-                o1 = fmaf(p, bf16_hi(v), o1);
-            }
-        }
-    }
-    const float inv = 1.f / sum;
-    *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + e) * D + h * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
 }
 
 }  // namespace ddb

@@ -248,25 +248,26 @@ static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_de
 static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* out, int Bcap, int L, int H) {
     memset(&a, 0, sizeof(a));
     const uint64_t D = (uint64_t)H * 64;
-    a.qkv = qkv, a.L = L, a.H = H, a.extras = L - 256;
+    a.qkv = qkv, a.out = out, a.L = L, a.H = H, a.extras = L - 256, a.B = Bcap;
     a.scale_log2e = 0.125f * 1.4426950408889634f;
     DDB_TRY(make_tmap_bf16_3d(&a.tmQKV, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 128));
     DDB_TRY(make_tmap_bf16_3d(&a.tmKV, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 256));
+    DDB_TRY(make_tmap_bf16_3d(&a.tmX, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 16));
     DDB_TRY(make_tmap_bf16_3d(&a.tmOut, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 128));
     return DDB_OK;
 }
-static int launch_attention_tc(const AttnArgs& a, __nv_bfloat16* out, int B, cudaStream_t st) {
+// persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
+static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      ATT2_SMEM));
+                                      ATT3_SMEM));
         configured = true;
     }
     if (B <= 0) return DDB_OK;
-    attention_tcgen05_kernel<<<B * a.H * 2, ATT2_THREADS, ATT2_SMEM, st>>>(a);
-    LAUNCH_CHECK();
-    attention_extras_kernel<<<(B * a.H * a.extras + 3) / 4, 128, 0, st>>>(a.qkv, out, a.L, a.H, a.extras,
-                                                                       a.scale_log2e, B, a.b_dev);
+    a.B = B;
+    const int items = B * a.H;
+    attention_tcgen05_kernel<<<items < num_sms ? items : num_sms, ATT3_THREADS, ATT3_SMEM, st>>>(a);
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -656,7 +657,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         DDB_TRY(run_gemm(op.qkv, EPI_LN, PC_GEMM_QKV, true, false));
         {
             ProfScope ps(PC_ATTENTION);
-            DDB_TRY(launch_attention_tc(m->attn, m->ao->as<__nv_bfloat16>(), B, st));
+            DDB_TRY(launch_attention_tc(m->attn, B, nsm, st));
         }
         DDB_TRY(run_gemm(op.proj, EPI_RES, PC_GEMM_PROJ, false, true));
         if (pair) {
@@ -984,7 +985,7 @@ int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, i
         AttnArgs a;
         DDB_TRY(plan_attention(a, reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
                                reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H));
-        return launch_attention_tc(a, reinterpret_cast<__nv_bfloat16*>(out_dev), B, (cudaStream_t)stream);
+        return launch_attention_tc(a, B, di.num_sms, (cudaStream_t)stream);
     }
     return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
                             reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H, (cudaStream_t)stream);

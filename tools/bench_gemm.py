@@ -14,6 +14,8 @@ ap.add_argument("--variants", default="2,1")
 ap.add_argument("--debug", default="0")
 ap.add_argument("--M", type=int, default=257 * 128)
 ap.add_argument("--D", type=int, default=512)
+ap.add_argument("--only", default="")
+ap.add_argument("--n", type=int, default=20)
 a = ap.parse_args()
 L = _lib.load()
 dev = torch.device("cuda:0")
@@ -22,6 +24,8 @@ shapes = [("qkv", 3 * D, D, 0, 1), ("proj", D, D, 0, 3), ("fc1", 4 * D, D, 0, 2)
           ("skip", D, D, D, 0)]
 NBUF = 3
 for name, N, K0, K1, epi in shapes:
+    if a.only and name not in a.only.split(","):
+        continue
     K = K0 + K1
     a0 = [torch.randn(M, K0, device=dev).bfloat16() for _ in range(NBUF)]
     a1 = [torch.randn(M, K1, device=dev).bfloat16() for _ in range(NBUF)] if K1 else [None] * NBUF
@@ -49,7 +53,7 @@ for name, N, K0, K1, epi in shapes:
                 run(i)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 20
+            n = a.n
             e0.record()
             for i in range(n):
                 run(i)
