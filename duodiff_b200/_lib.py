@@ -45,6 +45,7 @@ _SIGS = {
     "ddb_op_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32,
                               C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ddb_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "ddb_debug_set_ptr": (C.c_int, [C.c_char_p, _P]),
     "ddb_op_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ddb_op_ln_stats": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "ddb_op_pack_linear": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -218,15 +218,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_mma_kernel(const __n
 //   warps 4-7  softmax warpgroup of query tile 1
 //   warp  8    TMA producer: {Q0, Q1, K, V, X} of item i+1 while item i is being processed (2 x 102 KB stages);
 //              X = tokens 0..15 of the sample (q, k and v slices): the extras tokens plus don't-care patch tokens
-//   warp  9    MMA issuer + TMEM owner (512 columns = 2 tiles x 256); event-driven over both tiles' barriers
+//   warp  9    MMA issuer of tile 0 + TMEM owner (512 columns = 2 tiles x 256)
 //   warp  10   extras QUERY rows (tokens [0, extras)) on mma.sync from the same shared-memory K / V tiles
+//   warp  11   MMA issuer of tile 1 (starts half a period late: the two softmax warpgroups then run out of phase
+//              and keep the MUFU pipe -- the binding unit, 256 ex2 per query row -- busy)
 // Per tile t (TMEM columns relative to 256 t):
 //   S_t = Q_t K^T          M=128, N=256 (patch keys), K=64; fp32 in [0, 256)
 //   extras KEY scores      1-2 dot products per query row on the CUDA cores (k rows read from the X tile)
-//   softmax                pass 1 row max (FMNMX3), pass 2 P = exp2(s*c - m*c) -> bf16 written back over [0, 128)
-//                          (each TMEM load is issued one chunk ahead of the math on the previous chunk); the extras
-//                          keys' probabilities go to [128, 136) as a 17th k-step of 16 keys (14-15 of them zero)
-//   O_t = P_t [V; V_x]     A = P from TMEM, B = V (MN-major) from smem, 17 k-steps, fp32 in [192, 256)
+//   softmax                pass 1 row max (FMNMX3), pass 2 P = exp2(s*c - m*c) -> bf16 written back over consumed S
+//                          columns: keys [0,128) -> [0, 64), keys [128,256) -> [128, 192) (each TMEM load is issued
+//                          one chunk ahead of the math on the previous chunk); the extras keys' probabilities go to
+//                          [192, 200) as a 17th k-step of 16 keys (14-15 of them zero)
+//   O_t = P_t [V; V_x]     A = P from TMEM, B = V (MN-major) from smem, 17 k-steps, fp32 in [64, 128); the first 8
+//                          k-steps are issued as soon as keys [0,128) are done and run under the rest of pass 2
 //   epilogue               O row / sum -> bf16 -> the tile's own (dead) Q buffer -> TMA store
 // =====================================================================================================
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -250,9 +254,10 @@ struct AttnArgs {
     int L, H, extras, B;
     float scale_log2e;
     const int* b_dev;  // optional live batch size (early-exit compaction)
+    long long* trace;  // bench-only: CTA 0 records clock64() at the phase boundaries of every item ([it][tile][8])
 };
 
-constexpr int ATT3_THREADS = 352;
+constexpr int ATT3_THREADS = 384;
 // stage: Q0 16K | Q1 16K | K 32K | V 32K | Vx 2K (must follow V: 17th k-step of the PV MMA) | Kx 2K | Qx 2K
 constexpr int ATT3_OFF_K = 32768, ATT3_OFF_V = 65536, ATT3_OFF_VX = 98304, ATT3_OFF_KX = 100352, ATT3_OFF_QX = 102400;
 constexpr int ATT3_STAGE = 104448;
@@ -265,12 +270,13 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT3_OFF_BAR);
     uint64_t* qk_full = bars + 0;      // [2] per operand stage
     uint64_t* v_full = bars + 2;       // [2]
-    uint64_t* stage_empty = bars + 4;  // [2] 4 arrivals: PV MMAs retired, both tiles' TMA stores read, extras warp
+    uint64_t* stage_empty = bars + 4;  // [2] 5 arrivals: each tile's MMAs retired + its TMA store read, extras warp
     uint64_t* s_full = bars + 6;       // [2] per query tile
     uint64_t* p_full = bars + 8;       // [2]
     uint64_t* o_full = bars + 10;      // [2]
     uint64_t* tmem_free = bars + 12;   // [2]
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* p_half = bars + 14;      // [2] P of keys [0, 128) written
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.H * 64;
@@ -287,11 +293,12 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(&qk_full[i], 1);
             mbar_init(&v_full[i], 1);
-            mbar_init(&stage_empty[i], 4);
+            mbar_init(&stage_empty[i], 5);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
             mbar_init(&tmem_free[i], 4);
+            mbar_init(&p_half[i], 4);
         }
         fence_mbar_init();
     }
@@ -321,51 +328,55 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 tma_load_3d(st + ATT3_OFF_VX, &a.tmX, &v_full[s], 2 * D + h * 64, 0, b);
             }
         }
-    } else if (warp == 9) {
-        // ================================================================= MMA issuer (one thread, event-driven)
-        if (lane == 0 && my_items > 0) {
+    } else if (warp == 9 || warp == 11) {
+        // ================================================================= MMA issuers: one thread per query tile
+        // (two independent in-order streams, so neither tile ever waits behind the other tile's barrier)
+        if (lane == 0) {
+            const int t = (warp == 9) ? 0 : 1;
             constexpr uint32_t idesc_s = umma_idesc_bf16(128, 256);
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-            int s_it[2] = {0, 0};   // next item whose S_t has not been issued
-            int pv_it[2] = {0, 0};  // next item whose O_t = P_t V has not been issued
-            while (pv_it[0] < my_items || pv_it[1] < my_items) {
-                bool progressed = false;
+            for (int it = 0; it < my_items; ++it) {
+                const int s = it & 1;
+                const uint8_t* st = smem + s * ATT3_STAGE;
+                // S_t(it): needs the operands of the item and the tile's TMEM columns (O_t(it-1) drained)
+                mbar_wait(&qk_full[s], (it >> 1) & 1);
+                mbar_wait(&tmem_free[t], (it & 1) ^ 1);
+                // start tile 1 half a period late so the two softmax warpgroups do not fight over the MUFU pipe
+                if (t == 1 && it == 0) mbar_wait(&p_full[0], 0);
+                tc_fence_after();
+                const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(st + t * 16384));
+                const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(st + ATT3_OFF_K));
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    // S_t(i): needs the operands of item i and the tile's TMEM columns (O_t(i-1) drained)
-                    int i = s_it[t];
-                    if (i < my_items && i == pv_it[t] && mbar_test(&tmem_free[t], (i & 1) ^ 1) &&
-                        mbar_test(&qk_full[i & 1], (i >> 1) & 1)) {
-                        tc_fence_after();
-                        const uint8_t* st = smem + (i & 1) * ATT3_STAGE;
-                        const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(st + t * 16384));
-                        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(st + ATT3_OFF_K));
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[t]);
+                // O_t(it) = P_t [V; V_x]: 16 keys per k-step (P columns +8, V rows +16 = 2048 B); the first 8
+                // k-steps start as soon as the first half of P is written
+                long long* tr = (a.trace && blockIdx.x == 0) ? a.trace + (it * 2 + t) * 16 + 8 : nullptr;
+                if (tr) tr[0] = clock64();
+                mbar_wait(&v_full[s], (it >> 1) & 1);
+                const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(st + ATT3_OFF_V));
+                mbar_wait(&p_half[t], it & 1);
+                tc_fence_after();
+                if (tr) tr[1] = clock64();
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ss(tmem + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                        umma_commit(&s_full[t]);
-                        s_it[t] = i + 1;
-                        progressed = true;
-                    }
-                    // O_t(i) = P_t [V; V_x]: needs P_t(i) and V of item i
-                    i = pv_it[t];
-                    if (i < my_items && s_it[t] > i && mbar_test(&p_full[t], i & 1) &&
-                        mbar_test(&v_full[i & 1], (i >> 1) & 1)) {
-                        tc_fence_after();
-                        const uint8_t* st = smem + (i & 1) * ATT3_STAGE;
-                        const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(st + ATT3_OFF_V));
+                for (int k = 0; k < 8; ++k)
+                    umma_f16_ts(tmem + t * 256 + 64, tmem + t * 256 + 8 * k, dv + (uint64_t)(k * (2048 >> 4)),
+                                idesc_o, k != 0);
+                if (tr) tr[2] = clock64();
+                mbar_wait(&p_full[t], it & 1);
+                tc_fence_after();
+                if (tr) tr[3] = clock64();
 #pragma unroll
-                        for (int k = 0; k < 17; ++k)  // 16 keys per step: P columns +8, V rows +16 (2048 B)
-                            umma_f16_ts(tmem + t * 256 + 192, tmem + t * 256 + 8 * k,
-                                        dv + (uint64_t)(k * (2048 >> 4)), idesc_o, k != 0);
-                        umma_commit(&o_full[t]);
-                        pv_it[t] = i + 1;
-                        // once both tiles' PV MMAs of item i are issued, their retirement frees the operand stage
-                        if (pv_it[t ^ 1] > i) umma_commit(&stage_empty[i & 1]);
-                        progressed = true;
-                    }
+                for (int k = 8; k < 17; ++k)
+                    umma_f16_ts(tmem + t * 256 + 64, tmem + t * 256 + 64 + 8 * k, dv + (uint64_t)(k * (2048 >> 4)),
+                                idesc_o, 1u);
+                umma_commit(&o_full[t]);
+                umma_commit(&stage_empty[s]);  // this tile's MMAs no longer read the operand stage once retired
+                if (tr) {
+                    tr[4] = clock64();
+                    mbar_wait(&o_full[t], it & 1);
+                    tr[5] = clock64();
                 }
-                if (!progressed) __nanosleep(32);
             }
         }
     } else if (warp == 10) {
@@ -417,17 +428,13 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         const float c = a.scale_log2e;
         const int q0 = a.extras + t * 128;
 
-        for (int it = 0; it < my_items; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
-            const int b = item / a.H, h = item % a.H;
+        // scores of query row r against the extras keys (tokens [0, extras)) of item `it`, on the CUDA cores
+        auto extras_scores = [&](int it, float& se0, float& se1) {
             const int s = it & 1;
-            const uint32_t ph = it & 1;
-            uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;  // this tile's Q; later its output staging buffer
+            const uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;
             const uint8_t* sKx = smem + s * ATT3_STAGE + ATT3_OFF_KX;
-
-            // scores against the extras keys on the CUDA cores (overlaps the Q K^T MMA)
             mbar_wait(&qk_full[s], (it >> 1) & 1);
-            float se0 = 0.f, se1 = 0.f;
+            se0 = 0.f, se1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((j ^ (r & 7)) << 4));
@@ -447,29 +454,54 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 }
             }
             if (a.extras != 2) se1 = -INFINITY;
+        };
 
+        float se0 = 0.f, se1 = 0.f;
+        if (my_items > 0) extras_scores(0, se0, se1);
+        for (int it = 0; it < my_items; ++it) {
+            const int item = blockIdx.x + it * gridDim.x;
+            const int b = item / a.H, h = item % a.H;
+            const int s = it & 1;
+            const uint32_t ph = it & 1;
+            uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;  // this tile's Q; later its output staging buffer
+
+            long long* tr = (a.trace && blockIdx.x == 0 && r == 0) ? a.trace + (it * 2 + t) * 16 : nullptr;
+            if (tr) tr[0] = clock64();
             mbar_wait(&s_full[t], ph);
             tc_fence_after();
+            if (tr) tr[1] = clock64();
+            // the previous item's TMA store was issued ~1000 clk ago: once it has read its staging tile (the Q_t
+            // buffer of the other stage) that stage may be refilled
+            if (et == 0 && it > 0) {
+                tma_store_wait_read<0>();
+                mbar_arrive(&stage_empty[s ^ 1]);
+            }
+            if (tr) tr[2] = clock64();
             uint32_t va[32], vb[32];
             // ---- pass 1: row max; the load of chunk j+1 is in flight while chunk j is reduced
             float m0 = se0, m1 = se1, m2 = -INFINITY, m3 = -INFINITY;
             tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
+#pragma unroll 1
+            for (int jj = 0; jj < 8; jj += 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
-                if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+                for (int u = 0; u < 2; ++u) {
+                    uint32_t(&cur)[32] = u ? vb : va;
+                    uint32_t(&nxt)[32] = u ? va : vb;
+                    const int j = jj + u;
+                    if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
-                    m0 = fmax3(m0, __uint_as_float(cur[e + 0]), __uint_as_float(cur[e + 1]));
-                    m1 = fmax3(m1, __uint_as_float(cur[e + 2]), __uint_as_float(cur[e + 3]));
-                    m2 = fmax3(m2, __uint_as_float(cur[e + 4]), __uint_as_float(cur[e + 5]));
-                    m3 = fmax3(m3, __uint_as_float(cur[e + 6]), __uint_as_float(cur[e + 7]));
+                    for (int e = 0; e < 32; e += 8) {
+                        m0 = fmax3(m0, __uint_as_float(cur[e + 0]), __uint_as_float(cur[e + 1]));
+                        m1 = fmax3(m1, __uint_as_float(cur[e + 2]), __uint_as_float(cur[e + 3]));
+                        m2 = fmax3(m2, __uint_as_float(cur[e + 4]), __uint_as_float(cur[e + 5]));
+                        m3 = fmax3(m3, __uint_as_float(cur[e + 6]), __uint_as_float(cur[e + 7]));
+                    }
+                    if (j < 7) tmem_ld_wait();
                 }
-                if (j < 7) tmem_ld_wait();
             }
             const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
+            if (tr) tr[3] = clock64();
             const float pe0 = ex2_approx(fmaf(se0, c, -mc));
             const float pe1 = (a.extras == 2) ? ex2_approx(fmaf(se1, c, -mc)) : 0.f;
             // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
@@ -477,46 +509,63 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             f32x2 sum2 = f2_pack(pe0, pe1), sum2b = f2_splat(0.f);
             tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
+#pragma unroll 1
+            for (int jj = 0; jj < 8; jj += 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t(&cur)[32] = (j & 1) ? vb : va;
-                uint32_t(&nxt)[32] = (j & 1) ? va : vb;
-                if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
-                uint32_t pk[16];
+                for (int u = 0; u < 2; ++u) {
+                    uint32_t(&cur)[32] = u ? vb : va;
+                    uint32_t(&nxt)[32] = u ? va : vb;
+                    const int j = jj + u;
+                    if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+                    uint32_t pk[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    float x0, x1;
-                    f2_unpack(f2_fma(f2_pack_u(cur[2 * e], cur[2 * e + 1]), c2, nmc2), x0, x1);
-                    const f32x2 p = f2_pack(ex2_approx(x0), ex2_approx(x1));
-                    if (e & 1)
-                        sum2b = f2_add(sum2b, p);
-                    else
-                        sum2 = f2_add(sum2, p);
-                    pk[e] = f2_to_bf16x2(p);
+                    for (int e = 0; e < 16; ++e) {
+                        float x0, x1;
+                        f2_unpack(f2_fma(f2_pack_u(cur[2 * e], cur[2 * e + 1]), c2, nmc2), x0, x1);
+                        const f32x2 p = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                        if (e & 1)
+                            sum2b = f2_add(sum2b, p);
+                        else
+                            sum2 = f2_add(sum2, p);
+                        pk[e] = f2_to_bf16x2(p);
+                    }
+                    if (j < 7) tmem_ld_wait();
+                    // P chunk j < 4 -> columns [16j, 16j+16) (inside S chunk j/2), j >= 4 -> [128 + 16(j-4), ..)
+                    // (inside S chunks 4, 5): always columns whose scores are already in registers
+                    tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);
                 }
-                if (j < 7) tmem_ld_wait();
-                // P chunk j lands in columns [16j, 16j+16): inside S chunk j/2, which is already in registers
-                tmem_st_32x32b_x16(t_row + j * 16, pk);
+                if (jj == 2) {
+                    // keys [0, 128) are done: the first 8 k-steps of O = P V run under the rest of pass 2
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_half[t]);
+                }
             }
             {
                 // 17th k-step: keys = tokens 0..15 of the sample, non-zero weight only for the extras tokens
                 const uint32_t px[8] = {pack_bf16(pe0, pe1), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                tmem_st_32x32b_x8(t_row + 128, px);
+                tmem_st_32x32b_x8(t_row + 192, px);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[t]);
+            if (tr) tr[4] = clock64();
             float sa, sb, sc, sd;
             f2_unpack(sum2, sa, sb);
             f2_unpack(sum2b, sc, sd);
             const float inv = 1.f / ((sa + sb) + (sc + sd));
+            // while the tensor core finishes O: the next item's extras-key scores (its operands landed long ago)
+            if (it + 1 < my_items) extras_scores(it + 1, se0, se1);
+            if (tr) tr[5] = clock64();
 
             // ---- epilogue: O row (fp32) out of TMEM, then release the tile's columns for S_t of the next item
             mbar_wait(&o_full[t], ph);
             tc_fence_after();
-            tmem_ld_32x32b_x32(t_row + 192, va);
-            tmem_ld_32x32b_x32(t_row + 224, vb);
+            if (tr) tr[6] = clock64();
+            tmem_ld_32x32b_x32(t_row + 64, va);
+            tmem_ld_32x32b_x32(t_row + 96, vb);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -539,11 +588,14 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             if (et == 0) {
                 tma_store_3d(&a.tmOut, sQ, h * 64, q0, b);
                 tma_store_commit();
-                tma_store_wait_read<0>();       // the store has read the staging tile ...
-                mbar_arrive(&stage_empty[s]);   // ... so the producer may overwrite this stage's Q_t
             }
+            if (tr) tr[7] = clock64();
         }
-        if (et == 0) tma_store_wait_all<0>();
+        if (et == 0 && my_items > 0) {
+            tma_store_wait_read<0>();
+            mbar_arrive(&stage_empty[(my_items - 1) & 1]);
+            tma_store_wait_all<0>();
+        }
     }
     __syncwarp();
     tc_fence_before();

@@ -256,6 +256,7 @@ static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* 
     DDB_TRY(make_tmap_bf16_3d(&a.tmOut, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 128));
     return DDB_OK;
 }
+static long long* g_attn_trace = nullptr;  // bench-only (ddb_debug_set_ptr "attn_trace")
 // persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
 static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st) {
     static bool configured = false;
@@ -266,6 +267,7 @@ static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st) 
     }
     if (B <= 0) return DDB_OK;
     a.B = B;
+    a.trace = g_attn_trace;
     const int items = B * a.H;
     attention_tcgen05_kernel<<<items < num_sms ? items : num_sms, ATT3_THREADS, ATT3_SMEM, st>>>(a);
     LAUNCH_CHECK();
@@ -774,6 +776,14 @@ int ddb_set_option(const char* name, int32_t value) {
         return DDB_OK;
     }
     return fail(DDB_ERR_INVALID, "unknown option '%s'", name);
+}
+
+int ddb_debug_set_ptr(const char* name, void* p) {
+    if (name && !strcmp(name, "attn_trace")) {
+        g_attn_trace = reinterpret_cast<long long*>(p);
+        return DDB_OK;
+    }
+    return fail(DDB_ERR_INVALID, "unknown debug pointer '%s'", name ? name : "(null)");
 }
 
 int ddb_model_create(const ddb_uvit_config* cfg, const ddb_tensor* tensors, int32_t n_tensors, ddb_model** out) {

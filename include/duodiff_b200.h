@@ -114,6 +114,8 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 /* Runtime switches for A/B measurements: "gemm_variant" = 2 (CTA-pair kernel, default) or 1 (single-CTA kernel). */
 int ddb_set_option(const char* name, int32_t value);
+/* Bench-only instrumentation hooks (tools/): "attn_trace" = device buffer [items][2][8] of clock64() stamps. */
+int ddb_debug_set_ptr(const char* name, void* dev_ptr);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t ddb_launch_count(void);
 
