@@ -711,11 +711,12 @@ struct ddb_sampler {
     int switch_t = -1, B = 0, step_mode = 0, ee_mode = 0;
     float ee_threshold = -1.f;
     size_t n = 0;
-    Buf coef, t_dev, t_vec, eps, score_mean;
+    Buf coef, t_dev, t_vec, eps, score_mean, x_buf, seed_dev;
+    // One captured step per backbone.  The graph works on the sampler-owned x_buf and reads t and the Philox seed
+    // from device memory, so it is captured once and replayed for every call / seed / caller buffer.
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_nodes[2] = {0, 0};
-    const void* graph_key[2][5] = {{nullptr}};
-    unsigned long long graph_seed[2] = {0, 0};
+    const void* graph_key[2][4] = {{nullptr}};
 };
 
 __global__ void set_t_kernel(int* t_dev, int t) { *t_dev = t; }
@@ -731,8 +732,8 @@ __global__ void score_mean_kernel(const float* __restrict__ scores, int depth, i
 
 // one sampling step on the stream: forward + update (+ bookkeeping). t comes from s->t_dev (device).
 static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y, const float* z_all,
-                        unsigned long long seed, int t_host, float* eps_save, float* x_save, int32_t* exit_save,
-                        float* score_save, cudaStream_t st) {
+                        unsigned long long seed, const unsigned long long* seed_dev, int t_host, float* eps_save,
+                        float* x_save, int32_t* exit_save, float* score_save, cudaStream_t st) {
     const int B = s->B;
     fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->t_dev->as<int>(), s->t_vec->as<float>(), B);
     LAUNCH_CHECK();
@@ -751,7 +752,7 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y
     (void)t_host;
     ddpm_step_kernel<<<(unsigned)((s->n / 4 + 255) / 256), 256, 0, st>>>(x, eps, z_all, s->n, s->n,
                                                                          s->coef->as<float>(), s->t_dev->as<int>(), 0,
-                                                                         s->step_mode, seed, x_save);
+                                                                         s->step_mode, seed, seed_dev, x_save);
     LAUNCH_CHECK();
     dec_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>());
     LAUNCH_CHECK();
@@ -845,7 +846,7 @@ int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, 
     if (t < 0 || t > 999 || n <= 0 || n % 4) return fail(DDB_ERR_INVALID, "bad t=%d or n=%lld", t, (long long)n);
     // z_dev is this step's tensor: stride 0 makes z_all + t*stride land on it
     ddpm_step_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        x_dev, model_out_dev, z_dev, (size_t)n, (size_t)0, coef_dev, nullptr, t, mode, seed, nullptr);
+        x_dev, model_out_dev, z_dev, (size_t)n, (size_t)0, coef_dev, nullptr, t, mode, seed, nullptr, nullptr);
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -865,6 +866,8 @@ int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int3
     DDB_TRY(new_buf(s->t_dev, 4));
     DDB_TRY(new_buf(s->t_vec, (size_t)B * 4));
     DDB_TRY(new_buf(s->eps, s->n * 4));
+    DDB_TRY(new_buf(s->x_buf, s->n * 4));
+    DDB_TRY(new_buf(s->seed_dev, 8));
     *out = s.release();
     return DDB_OK;
 }
@@ -889,19 +892,24 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
     if (!use_graph) {
         for (int t = t_first, k = 0; t >= t_last; --t, ++k) {
             ddb_model* m = (s->late && t < s->switch_t) ? s->late : s->early;
-            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, t,
+            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, nullptr, t,
                                  eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
                                  x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr,
                                  exit_idx_trace_dev, score_mean_trace_dev, st));
         }
         return DDB_OK;
     }
-    // ---- graph replay: one captured step per backbone, t read from device memory
+    // ---- graph replay: one captured step per backbone; t, the seed and x live in sampler-owned device memory
+    float* xb = s->x_buf->as<float>();
+    unsigned long long* sd = s->seed_dev->as<unsigned long long>();
+    CUDA_TRY(cudaMemcpyAsync(xb, x_dev, s->n * 4, cudaMemcpyDeviceToDevice, st));
+    set_u64_kernel<<<1, 1, 0, st>>>(sd, seed);
+    LAUNCH_CHECK();
     for (int which = 0; which < 2; ++which) {
         ddb_model* m = which == 0 ? s->early : s->late;
         if (!m) continue;
-        const void* key[5] = {x_dev, y_dev, z_all_dev, exit_idx_trace_dev, score_mean_trace_dev};
-        if (s->graph[which] && (memcmp(key, s->graph_key[which], sizeof(key)) != 0 || s->graph_seed[which] != seed)) {
+        const void* key[4] = {y_dev, z_all_dev, exit_idx_trace_dev, score_mean_trace_dev};
+        if (s->graph[which] && memcmp(key, s->graph_key[which], sizeof(key)) != 0) {
             cudaGraphExecDestroy(s->graph[which]);
             s->graph[which] = nullptr;
         }
@@ -911,7 +919,7 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
             cudaGraph_t g = nullptr;
             CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
             const long long before = g_launches.load();
-            int r = sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, 0, nullptr, nullptr, exit_idx_trace_dev,
+            int r = sampler_step(s, m, xb, y_dev, z_all_dev, 0, sd, 0, nullptr, nullptr, exit_idx_trace_dev,
                                  score_mean_trace_dev, cs);
             g_launches.store(before);  // captured, not executed: replays are counted below
             cudaError_t e = cudaStreamEndCapture(cs, &g);
@@ -932,7 +940,6 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
             cudaStreamDestroy(cs);
             if (e != cudaSuccess) return fail(DDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
             memcpy(s->graph_key[which], key, sizeof(key));
-            s->graph_seed[which] = seed;
         }
     }
     for (int t = t_first; t >= t_last; --t) {
@@ -940,6 +947,7 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
         CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
         g_launches.fetch_add(s->graph_nodes[which], std::memory_order_relaxed);
     }
+    CUDA_TRY(cudaMemcpyAsync(x_dev, xb, s->n * 4, cudaMemcpyDeviceToDevice, st));
     return DDB_OK;
 }
 

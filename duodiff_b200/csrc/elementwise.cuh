@@ -244,8 +244,10 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
                                                         const float* __restrict__ z_all, size_t n, size_t z_stride,
                                                         const float* __restrict__ coef, const int* __restrict__ t_dev,
                                                         int t_host, int mode, unsigned long long seed,
+                                                        const unsigned long long* __restrict__ seed_dev,
                                                         float* __restrict__ x_save) {
     const int t = t_dev ? *t_dev : t_host;
+    if (seed_dev) seed = *seed_dev;  // graph replay: the Philox key lives in device memory
     const float c0 = coef[t * 4 + 0], c1 = coef[t * 4 + 1], sg = coef[t * 4 + 2];
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
@@ -286,6 +288,7 @@ __global__ void fill_t_kernel(const int* __restrict__ t_dev, float* __restrict__
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) t_vec[i] = (float)(*t_dev);
 }
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 __global__ void dec_t_kernel(int* t_dev) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev -= 1;
 }

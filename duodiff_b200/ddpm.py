@@ -63,6 +63,23 @@ def switch_step(t_switch) -> int:
     return 1000 - ts if 1 <= ts <= 1000 else -1
 
 
+_SAMPLER_CACHE: "dict[tuple, Sampler]" = {}
+
+
+def cached_sampler(early: Engine, late: "Engine | None", t_switch, batch: int, rule: str = "predict_noise",
+                   variance: str = "beta_tilde", ee_threshold: "float | None" = None, ee_mode: int = 0) -> "Sampler":
+    """Sampler for this (models, batch, rule): its buffers and captured CUDA graphs are reused across get_samples()
+    calls (the graphs read t, the seed and x from sampler-owned device memory, so they do not depend on the call)."""
+    key = (early.handle.value, late.handle.value if late is not None else None, switch_step(t_switch), batch, rule,
+           variance, ee_threshold, ee_mode)
+    smp = _SAMPLER_CACHE.get(key)
+    if smp is None:
+        while len(_SAMPLER_CACHE) >= 4:  # bounded: each entry owns a few x-sized device buffers and two graphs
+            _SAMPLER_CACHE.pop(next(iter(_SAMPLER_CACHE)))
+        smp = _SAMPLER_CACHE[key] = Sampler(early, late, t_switch, batch, rule, variance, ee_threshold, ee_mode)
+    return smp
+
+
 class Sampler:
     """get_samples()' inner loop (sampler.py:128-139 / eesampler.py:57-82) as one C call."""
 

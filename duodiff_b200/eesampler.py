@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _io
-from .ddpm import Sampler
+from .ddpm import cached_sampler
 from .early_exit import EarlyExitUViT
 from .uvit import UViT
 
@@ -31,7 +31,8 @@ def get_samples(model, batch_size: int, seed: int, num_channels: int, sample_hei
     x = torch.randn(batch_size, num_channels, sample_height, sample_width).pin_memory().to(dev, non_blocking=True)
     with torch.cuda.device(dev):
         eng = model.engine(batch_size)
-        sampler = Sampler(eng, None, np.inf, batch_size, rule="predict_noise", ee_threshold=threshold, ee_mode=mode)
+        sampler = cached_sampler(eng, None, np.inf, batch_size, rule="predict_noise", ee_threshold=threshold,
+                                 ee_mode=mode)
         exit_log = torch.zeros(1000, batch_size, device=dev, dtype=torch.int32)
         score_log = torch.zeros(1000, depth, device=dev, dtype=torch.float32)
         if noise is not None:

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _io
-from .ddpm import RULES, Sampler
+from .ddpm import RULES, cached_sampler
 from .uvit import UViT
 
 
@@ -71,7 +71,7 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
     with torch.cuda.device(dev):
         early = model.engine(batch_size)
         late = late_model.engine(batch_size) if late_model is not None else None
-        sampler = Sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
+        sampler = cached_sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
         if noise is not None:
             noise = noise.to(device=dev, dtype=torch.float32).contiguous()
         # reference: `if 1000 - t in timesteps_save` after the update at t -> save x after step t = 1000 - s
