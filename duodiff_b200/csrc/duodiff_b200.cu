@@ -603,12 +603,25 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
     float2* st2 = m->stats->as<float2>();
 
+    // token assembly; outside the early-exit path it also writes the LayerNorm statistics of the first block
+    // (the early-exit path runs ln_stats_kernel anyway: it carries the MLP probe)
     {
         ProfScope ps(PC_EMBED);
-        embed_tokens_kernel<<<B * (c.img_size / c.patch_size), 256, m->pd * EMB_TOK * 4, st>>>(
-            x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),
-            m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(),
-            c.in_chans, c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps);
+        const int grid = B * (c.img_size / c.patch_size);
+        float2* emb_stats = ee ? nullptr : st2;
+#define DDB_EMBED(PD)                                                                                              \
+    embed_tokens_kernel<PD><<<grid, 256, 0, st>>>(                                                                 \
+        x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),               \
+        m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(),       \
+        emb_stats, c.in_chans, c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps)
+        switch (m->pd) {
+            case 12: DDB_EMBED(12); break;
+            case 16: DDB_EMBED(16); break;
+            case 48: DDB_EMBED(48); break;
+            case 64: DDB_EMBED(64); break;
+            default: return fail(DDB_ERR_INVALID, "patch_dim %d unsupported (12, 16, 48 or 64)", m->pd);
+        }
+#undef DDB_EMBED
         LAUNCH_CHECK();
     }
 
@@ -628,6 +641,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         ProfScope ps(cat);
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
+    if (!ee) kind = 1;  // statistics of x0 were written by the token-assembly kernel
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     for (int i = 0; i < c.depth; ++i) {
         const BlockOps& op = m->ops[i];
