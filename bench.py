@@ -186,6 +186,8 @@ def run_reference(args, rank: int, world: int) -> None:
         return
     steps, warm = max(args.steps, 1), max(args.warmup, 0)
     batch = 8
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host thread
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     vals, info = [], None
     t_begin = time.perf_counter()
     for i in range(warm + steps):
@@ -194,13 +196,16 @@ def run_reference(args, rank: int, world: int) -> None:
             vals.append(info["value"])
     ms = (time.perf_counter() - t_begin) * 1e3 / (warm + steps)
     v = statistics.mean(vals)
-    shallow, full, _ = PAIRS[args.config]
+    shallow, full, default_b = PAIRS[args.config]
+    B = args.batch or default_b
     info["value"] = v
+    # same metric / unit / config as the GPU arm; what was actually timed is described in cpu_baseline.sample
     line = dict(impl="reference", metric=METRIC, value=v, unit="images/sec", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic (random-init weights, N(0,1) x_T)",
-                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}), t_switch={T_SWITCH}, CPU sample at "
-                                     f"batch {batch}", t_switch=T_SWITCH, batch_per_gpu=batch),
+                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}",
+                            batch_per_gpu=B, global_batch=B * args.gpus, t_switch=T_SWITCH,
+                            parallelism=f"dp{args.gpus}", l2="n/a (host cores)"),
                 cpu_baseline=info, e2e=dict(value=v, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
