@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -335,6 +336,11 @@ struct ddb_model {
     std::vector<Buf> probe_w, probe_b;
     // workspace
     Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_sig, scores, outputs, exit_idx;
+    // early-exit compaction (mode 1): device-side live counts, slot maps, gather lists, scratch batch of leavers
+    Buf ee_n, ee_slot, ee_keep_src, ee_exit_src, ee_exit_slot, xe, stats_e;
+    std::vector<GemmArgs> head_dec_x;       // head i on the scratch batch
+    std::vector<EeBufList> ee_live;         // buffers that must be compacted when samples leave before block i
+    std::vector<int> ee_live_n;
     std::vector<Buf> xo;
     // plan
     std::vector<BlockOps> ops;
@@ -543,6 +549,13 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
         DDB_TRY(new_buf(m->scores, (size_t)cfg->depth * cfg->max_batch * 4));
         DDB_TRY(new_buf(m->outputs, (size_t)(cfg->depth + 1) * cfg->max_batch * m->chw * 4));
         DDB_TRY(new_buf(m->exit_idx, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_n, 4 * 4));
+        DDB_TRY(new_buf(m->ee_slot, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_keep_src, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_exit_src, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_exit_slot, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->xe, act));
+        DDB_TRY(new_buf(m->stats_e, (size_t)m->Mpad * sizeof(float2)));
     }
     // ---- plan (buffer routing of models/uvit.py:367-375)
     m->ops.resize(cfg->depth);
@@ -578,29 +591,65 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
             DDB_TRY(plan_gemm(m->head_dec[i], m, in, D, nullptr, 0, m->ee_heads[i].dec, 64, nullptr, nullptr, st));
             plan_decode_geometry(m->head_dec[i], m, m->img_pre->as<float>());
         }
+        // compaction mode: head i on the scratch batch of leavers; list of live buffers per layer = the block input
+        // plus every long skip that is still pending (models/uvit.py:367-375)
+        m->head_dec_x.resize(cfg->depth);
+        m->ee_live.resize(cfg->depth);
+        m->ee_live_n.resize(cfg->depth);
+        for (int i = 0; i < cfg->depth; ++i) {
+            DDB_TRY(plan_gemm(m->head_dec_x[i], m, m->xe->p, D, nullptr, 0, m->ee_heads[i].dec, 64, nullptr, nullptr,
+                              m->stats_e->as<float2>()));
+            plan_decode_geometry(m->head_dec_x[i], m, m->img_pre->as<float>());
+            m->head_dec_x[i].m_dev = m->ee_n->as<int>() + 3;
+            const int last_skip = (i <= half) ? std::min(i, half) - 1 : half - 1 - (i - half - 1);
+            EeBufList& bl = m->ee_live[i];
+            memset(&bl, 0, sizeof(bl));
+            int n = 0;
+            void* cur_in = (i == 0) ? m->x0->p : m->xo[i - 1]->p;
+            bl.p[n++] = reinterpret_cast<__nv_bfloat16*>(cur_in);
+            for (int k = 0; k <= last_skip; ++k) {
+                if (m->xo[k]->p == cur_in) continue;
+                if (n >= 8) return fail(DDB_ERR_INVALID, "depth %d needs more than 8 live buffers", cfg->depth);
+                bl.p[n++] = m->xo[k]->as<__nv_bfloat16>();
+            }
+            m->ee_live_n[i] = n;
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
     return DDB_OK;
 }
 
-static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st) {
+static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st,
+                    const int* n_dev = nullptr, const int* slot_map = nullptr) {
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
     const int smem = (C * (CONV_BAND + 2) * (W + 2) + C * C * 9 + C) * 4;
     ProfScope ps(PC_CONV);
     conv3x3_kernel<<<B * (H / CONV_BAND), 256, smem, st>>>(in, hw.conv_w->as<float>(), hw.conv_b->as<float>(), out,
-                                                            C, H, W);
+                                                            C, H, W, n_dev, slot_map);
     LAUNCH_CHECK();
     return DDB_OK;
 }
 
 // The launch sequence of one forward.  ee: evaluate probes + heads (simulate mode) into m->scores / m->outputs.
+// Compaction-mode parameters of a forward (ddb_ee_forward mode 1)
+struct EeCompact {
+    float threshold;
+    int32_t* exit_idx;     // [B]
+    const int* t_dev;      // device timestep for the logs (or null)
+    int32_t* exit_log;     // [1000,B] by t (or null)
+    float* score_mean_log; // [1000,depth] by t (or null)
+};
+
 static int forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float* eps, bool ee,
-                        cudaStream_t st) {
+                        cudaStream_t st, const EeCompact* cp = nullptr) {
     const ddb_uvit_config& c = m->cfg;
     if (B < 1 || B > c.max_batch) return fail(DDB_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, c.max_batch);
     if (m->extras == 2 && !y) return fail(DDB_ERR_INVALID, "class-conditional model needs y (models/uvit.py:361)");
     if (ee && !c.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
+    if (cp && (!ee || B > 1024)) return fail(DDB_ERR_INVALID, "compaction needs an early-exit model and batch <= 1024");
     const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
+    // compaction: live sample / row counts are read from device memory by every kernel after the token assembly
+    int* een = cp ? m->ee_n->as<int>() : nullptr;
     float2* st2 = m->stats->as<float2>();
 
     // token assembly; outside the early-exit path it also writes the LayerNorm statistics of the first block
@@ -633,6 +682,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     int kind = 0;
     auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
         g.M = M;
+        if (cp && !g.m_dev) g.m_dev = een + 1;
         if (ln_in) {
             g.stats = kind == 2 ? stp : st2;
             g.nparts = kind == 2 ? np_p : 1;
@@ -642,11 +692,50 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
     if (!ee) kind = 1;  // statistics of x0 were written by the token-assembly kernel
+    if (cp) {
+        ProfScope ps(PC_EE_OTHER);
+        const int n = std::max(B, c.depth * B);
+        ee_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(een, m->ee_slot->as<int>(), B, m->L, m->scores->as<float>(),
+                                                        c.depth, cp->exit_idx, cp->t_dev, cp->exit_log);
+        LAUNCH_CHECK();
+    }
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     for (int i = 0; i < c.depth; ++i) {
         const BlockOps& op = m->ops[i];
         const BlockW& bw = m->blocks[i];
-        if (ee) {
+        if (cp) {
+            // probe i on the live rows; leavers take head i's output and are squeezed out of every live buffer
+            DDB_TRY(launch_ln_stats(cur, M, D, een + 1, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
+                                    m->probe_sig->as<float>(), st));
+            kind = 1;
+            {
+                ProfScope ps(PC_EE_OTHER);
+                ee_decide_kernel<<<1, 1024, 0, st>>>(m->probe_sig->as<float>(), m->L, cp->threshold, i, B, c.depth, een,
+                                                     m->ee_slot->as<int>(), m->ee_keep_src->as<int>(),
+                                                     m->ee_exit_src->as<int>(), m->ee_exit_slot->as<int>(),
+                                                     m->scores->as<float>(), cp->exit_idx, cp->t_dev, cp->exit_log,
+                                                     cp->score_mean_log);
+                LAUNCH_CHECK();
+                ee_gather_exit_kernel<<<m->L, 128, 0, st>>>(cur, st2, een, m->ee_exit_src->as<int>(),
+                                                            m->xe->as<__nv_bfloat16>(), m->stats_e->as<float2>(), m->L,
+                                                            D);
+                LAUNCH_CHECK();
+            }
+            {
+                GemmArgs g = m->head_dec_x[i];
+                g.M = M;
+                ProfScope ps(PC_GEMM_DECODE);
+                DDB_TRY(launch_gemm(g, EPI_DECODE, nsm, st));
+            }
+            DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(), eps, B, st, een + 2,
+                             m->ee_exit_slot->as<int>()));
+            {
+                ProfScope ps(PC_EE_OTHER);
+                ee_compact_kernel<<<dim3(m->L, m->ee_live_n[i] + 1), 128, 0, st>>>(
+                    m->ee_live[i], m->ee_live_n[i], st2, een, m->ee_keep_src->as<int>(), m->L, D);
+                LAUNCH_CHECK();
+            }
+        } else if (ee) {
             // probe i + head i look at the block input (models/early_exit.py:294-296)
             DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
                                     m->probe_sig->as<float>(), st));
@@ -673,7 +762,9 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         DDB_TRY(run_gemm(op.qkv, EPI_LN, PC_GEMM_QKV, true, false));
         {
             ProfScope ps(PC_ATTENTION);
-            DDB_TRY(launch_attention_tc(m->attn, B, nsm, st));
+            AttnArgs aa = m->attn;
+            aa.b_dev = een;  // live sample count (compaction) or null
+            DDB_TRY(launch_attention_tc(aa, B, nsm, st));
         }
         DDB_TRY(run_gemm(op.proj, EPI_RES, PC_GEMM_PROJ, false, true));
         if (pair) {
@@ -693,16 +784,27 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         kind = 1;
     }
     DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
-    DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
+    if (cp)  // the samples that never left: full-model output, written to their original slots
+        DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st, een, m->ee_slot->as<int>()));
+    else
+        DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
     return DDB_OK;
 }
 
 static int ee_forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float threshold,
                            int mode, float* eps, int32_t* exit_idx, float* scores_out, float* outputs_out,
-                           const int* t_dev, int32_t* exit_log, cudaStream_t st) {
+                           const int* t_dev, int32_t* exit_log, float* score_log, cudaStream_t st) {
     if (!m->cfg.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
-    if (mode != 0) return fail(DDB_ERR_INVALID, "ee mode %d not implemented yet (0 = simulate)", mode);
+    if (mode != 0 && mode != 1) return fail(DDB_ERR_INVALID, "ee mode must be 0 (simulate) or 1 (compact)");
     const int depth = m->cfg.depth;
+    if (mode == 1) {
+        if (outputs_out) return fail(DDB_ERR_INVALID, "compact mode does not produce the per-layer head outputs");
+        EeCompact cp{threshold, exit_idx ? exit_idx : m->exit_idx->as<int32_t>(), t_dev, exit_log, score_log};
+        DDB_TRY(forward_impl(m, x, t, y, B, eps, true, st, &cp));
+        if (scores_out)
+            CUDA_TRY(cudaMemcpyAsync(scores_out, m->scores->p, (size_t)depth * B * 4, cudaMemcpyDeviceToDevice, st));
+        return DDB_OK;
+    }
     float* full = m->outputs->as<float>() + (size_t)depth * B * m->chw;
     DDB_TRY(forward_impl(m, x, t, y, B, full, true, st));
     int32_t* idx = exit_idx ? exit_idx : m->exit_idx->as<int32_t>();
@@ -754,8 +856,8 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y
     float* eps = eps_save ? eps_save : s->eps->as<float>();
     if (s->ee_threshold >= 0.f && m->cfg.early_exit) {
         DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, nullptr,
-                                nullptr, nullptr, s->t_dev->as<int>(), exit_save, st));
-        if (score_save) {
+                                nullptr, nullptr, s->t_dev->as<int>(), exit_save, score_save, st));
+        if (score_save && s->ee_mode == 0) {
             score_mean_kernel<<<m->cfg.depth, 32, 0, st>>>(m->scores->as<float>(), m->cfg.depth, B,
                                                            s->t_dev->as<int>(), score_save);
             LAUNCH_CHECK();
@@ -851,7 +953,7 @@ int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const i
                    float* outputs_dev, void* stream) {
     if (!m || !x_dev || !t_dev || !eps_dev) return fail(DDB_ERR_INVALID, "null argument");
     return ee_forward_impl(m, x_dev, t_dev, y_dev, B, threshold, mode, eps_dev, exit_idx_dev, scores_dev, outputs_dev,
-                           nullptr, nullptr, (cudaStream_t)stream);
+                           nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, const float* coef_dev, int32_t t,

@@ -301,12 +301,17 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
 // (sample, 16-row band).  Optional fused DDPM update (see ddpm_step_kernel) when x_io != null.
 // =====================================================================================================
 constexpr int CONV_BAND = 16;
+// n_dev / slot_map (early-exit compaction): only the first *n_dev input images are live and image b is written to
+// output slot slot_map[b].
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
                                                       const float* __restrict__ bias, float* __restrict__ out, int C,
-                                                      int H, int W) {
+                                                      int H, int W, const int* __restrict__ n_dev,
+                                                      const int* __restrict__ slot_map) {
     extern __shared__ float conv_smem[];  // [C][CONV_BAND+2][W+2] then weights [C*C*9] + bias[C]
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
+    if (n_dev && b >= *n_dev) return;
+    const int ob = slot_map ? slot_map[b] : b;
     const int SW = W + 2, SH = CONV_BAND + 2;
     float* sw = conv_smem + C * SH * SW;
     for (int i = threadIdx.x; i < C * SH * SW; i += blockDim.x) {
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) acc = fmaf(wp[dy * 3 + dx], sp[dy * SW + dx], acc);
         }
-        out[(((size_t)b * C + co) * H + y0 + yy) * W + xx] = acc;
+        out[(((size_t)ob * C + co) * H + y0 + yy) * W + xx] = acc;
     }
 }
 
@@ -466,6 +471,173 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
     float4* dst = reinterpret_cast<float4*>(eps + (size_t)b * chw);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw / 4; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = src[i];
+}
+
+// =====================================================================================================
+// Early-exit COMPACTION (ddb_ee_forward mode 1): samples whose probe score drops below the threshold at layer i take
+// head_i's output and leave the batch, so every later kernel works on M = n_active * L rows.
+// Device-side state ee_n[4] = {n_active, n_active*L, n_exit, n_exit*L}; slot[b] = original index of compact sample b.
+// =====================================================================================================
+__global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, int B, int L,
+                                float* __restrict__ scores, int depth, int* __restrict__ exit_idx,
+                                const int* __restrict__ t_dev, int* __restrict__ exit_log) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) ee_n[0] = B, ee_n[1] = B * L, ee_n[2] = 0, ee_n[3] = 0;
+    if (i < B) {
+        slot[i] = i;
+        exit_idx[i] = depth;
+        if (exit_log) exit_log[(size_t)(t_dev ? *t_dev : 0) * B + i] = depth;
+    }
+    if (i < depth * B) scores[i] = __int_as_float(0x7fc00000);  // NaN: "not produced" (sample had already left)
+}
+
+// One CTA of 1024 threads.  Scores the live samples (warp per sample), decides who leaves at `layer`, builds the
+// gather lists with a block-wide scan and updates the state.
+__global__ void __launch_bounds__(1024) ee_decide_kernel(
+    const float* __restrict__ sig, int L, float thr, int layer, int B, int depth, int* __restrict__ ee_n,
+    int* __restrict__ slot, int* __restrict__ keep_src, int* __restrict__ exit_src, int* __restrict__ exit_slot,
+    float* __restrict__ scores, int* __restrict__ exit_idx, const int* __restrict__ t_dev,
+    int* __restrict__ exit_log, float* __restrict__ score_mean_log) {
+    __shared__ float sc[1024];
+    __shared__ int new_slot[1024];
+    __shared__ int wtot[2][32];
+    __shared__ float wsum[32];
+    __shared__ float part[8][4];
+    const int n = ee_n[0];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // score = mean over tokens, with exactly the summation order of probe_mean_kernel (128 threads per sample), so the
+    // exit decisions of the two modes can never differ by rounding
+    const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127;
+    for (int b0 = 0; b0 < n; b0 += 8) {
+        const int b = b0 + grp;
+        float s = 0.f;
+        if (b < n)
+            for (int l = gt; l < L; l += 128) s += sig[(size_t)b * L + l];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) part[grp][(gt >> 5)] = s;
+        __syncthreads();
+        if (gt == 0 && b < n) sc[b] = (part[grp][0] + part[grp][1] + part[grp][2] + part[grp][3]) / (float)L;
+        __syncthreads();
+    }
+    const int b = threadIdx.x;
+    const bool live = b < n;
+    const float myscore = live ? sc[b] : 0.f;
+    const int myslot = live ? slot[b] : 0;
+    const int ex = (live && myscore <= thr) ? 1 : 0;
+    const int kp = (live && !ex) ? 1 : 0;
+    // block-wide exclusive scans of ex / kp and the sum of the live scores
+    int ie = ex, ik = kp;
+    float fs = myscore;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int te = __shfl_up_sync(0xffffffffu, ie, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
+        if (lane >= o) ie += te, ik += tk;
+    }
+    for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
+    if (lane == 31) wtot[0][warp] = ie, wtot[1][warp] = ik;
+    if (lane == 0) wsum[warp] = fs;
+    __syncthreads();
+    if (warp == 0) {
+        int ve = wtot[0][lane], vk = wtot[1][lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const int te = __shfl_up_sync(0xffffffffu, ve, o), tk = __shfl_up_sync(0xffffffffu, vk, o);
+            if (lane >= o) ve += te, vk += tk;
+        }
+        wtot[0][lane] = ve, wtot[1][lane] = vk;  // inclusive over warps
+        float t = wsum[lane];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) wsum[0] = t;
+    }
+    __syncthreads();
+    const int base_e = warp ? wtot[0][warp - 1] : 0, base_k = warp ? wtot[1][warp - 1] : 0;
+    const int n_exit = wtot[0][31], n_keep = wtot[1][31];
+    const int t_now = t_dev ? *t_dev : 0;
+    if (live) {
+        scores[(size_t)layer * B + myslot] = myscore;
+        if (ex) {
+            const int j = base_e + ie - 1;
+            exit_src[j] = b;
+            exit_slot[j] = myslot;
+            exit_idx[myslot] = layer;
+            if (exit_log) exit_log[(size_t)t_now * B + myslot] = layer;
+        } else {
+            const int j = base_k + ik - 1;
+            keep_src[j] = b;
+            new_slot[j] = myslot;
+        }
+    }
+    __syncthreads();
+    if (b < n_keep) slot[b] = new_slot[b];
+    if (b == 0) {
+        ee_n[0] = n_keep, ee_n[1] = n_keep * L, ee_n[2] = n_exit, ee_n[3] = n_exit * L;
+        // eesampler.py:71 logs the batch mean of every probe; here: the mean over the samples still in the batch
+        if (score_mean_log)
+            score_mean_log[(size_t)t_now * depth + layer] = n > 0 ? wsum[0] / (float)n : __int_as_float(0x7fc00000);
+    }
+}
+
+// rows of the leaving samples -> scratch batch [n_exit*L, D] (+ their LayerNorm statistics); grid = L CTAs
+__global__ void __launch_bounds__(128) ee_gather_exit_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const float2* __restrict__ stats,
+                                                             const int* __restrict__ ee_n,
+                                                             const int* __restrict__ exit_src,
+                                                             __nv_bfloat16* __restrict__ xe,
+                                                             float2* __restrict__ stats_e, int L, int D) {
+    const int n_exit = ee_n[2];
+    const int l = blockIdx.x;
+    const int chunks = D / 8;  // 16-byte chunks per row
+    for (int j = 0; j < n_exit; ++j) {
+        const size_t src = (size_t)exit_src[j] * L + l, dst = (size_t)j * L + l;
+        const uint4* sp = reinterpret_cast<const uint4*>(x + src * D);
+        uint4* dp = reinterpret_cast<uint4*>(xe + dst * D);
+        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dp[c] = sp[c];
+        if (threadIdx.x == 0) stats_e[dst] = stats[src];
+    }
+}
+
+// In-place compaction of the kept samples of up to 8 activation buffers (+ the row statistics, blockIdx.y == nbuf).
+// grid = (L, nbuf + 1).  A thread owns one 16-byte column chunk of token l and walks the kept samples in increasing
+// order: keep_src[j] >= j and is increasing, so a row is always read before it can be overwritten, and the loads of
+// the next samples never alias earlier stores (dst_j <= src_j < src_{j+1}).
+struct EeBufList {
+    __nv_bfloat16* p[8];
+};
+__global__ void __launch_bounds__(128) ee_compact_kernel(EeBufList bufs, int nbuf, float2* __restrict__ stats,
+                                                         const int* __restrict__ ee_n,
+                                                         const int* __restrict__ keep_src, int L, int D) {
+    if (ee_n[2] == 0) return;  // nobody left at this layer
+    const int n_keep = ee_n[0];
+    const int l = blockIdx.x;
+    if ((int)blockIdx.y == nbuf) {
+        if (threadIdx.x == 0)
+            for (int j = 0; j < n_keep; ++j) {
+                const int s = keep_src[j];
+                if (s != j) stats[(size_t)j * L + l] = stats[(size_t)s * L + l];
+            }
+        return;
+    }
+    __nv_bfloat16* buf = bufs.p[blockIdx.y];
+    const int chunks = D / 8;
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+        int j = 0;
+        for (; j + 4 <= n_keep; j += 4) {
+            uint4 v[4];
+            int s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s[u] = keep_src[j + u];
+                v[u] = reinterpret_cast<const uint4*>(buf + ((size_t)s[u] * L + l) * D)[c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (s[u] != j + u) reinterpret_cast<uint4*>(buf + ((size_t)(j + u) * L + l) * D)[c] = v[u];
+        }
+        for (; j < n_keep; ++j) {
+            const int s = keep_src[j];
+            if (s != j)
+                reinterpret_cast<uint4*>(buf + ((size_t)j * L + l) * D)[c] =
+                    reinterpret_cast<const uint4*>(buf + ((size_t)s * L + l) * D)[c];
+        }
+    }
 }
 
 }  // namespace ddb

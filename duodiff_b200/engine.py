@@ -73,7 +73,8 @@ class Engine:
         eps = torch.empty_like(x)
         idx = torch.empty(B, device=x.device, dtype=torch.int32)
         scores = torch.empty(self.depth, B, device=x.device) if want_all else None
-        outputs = torch.empty(self.depth + 1, *x.shape, device=x.device) if want_all else None
+        # per-layer head outputs only exist in simulate mode (compaction skips every head but the exit layer's)
+        outputs = torch.empty(self.depth + 1, *x.shape, device=x.device) if (want_all and mode == 0) else None
         _lib.check(self.lib.ddb_ee_forward(self.handle, x.data_ptr(), t.data_ptr(), _lib.ptr(y), B, float(threshold),
                                            mode, eps.data_ptr(), idx.data_ptr(), _lib.ptr(scores), _lib.ptr(outputs),
                                            _lib.current_stream_ptr()))

@@ -282,6 +282,75 @@ def test_ee_forward_matches_oracle(dev, hot):
     assert net.engine(B).ee_forward(x, t, None, threshold=0.0)[1].eq(13).all()
 
 
+@pytest.mark.parametrize("name,B", [("celeba", 9), ("imagenet64_3", 5)])
+def test_ee_compaction_equals_simulation(dev, name, B):
+    """mode 1 (leavers are squeezed out of the batch, later kernels run on fewer rows) must give every sample the
+    same eps and exit index as mode 0 (the reference's evaluate-everything semantics) -- bit for bit, because every
+    kernel is batch-invariant -- and both must agree with the oracle's selection."""
+    import duodiff_b200 as ddb
+    torch.manual_seed(15)
+    net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS[name]), "mlp_probe_per_layer")
+    heat_(net, 16)
+    depth = CONFIGS[name]["depth"]
+    _spread_probes(net, depth)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(CONFIGS[name])
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, spec.in_chans, spec.img_size, spec.img_size, generator=g).to(dev)
+    t = torch.full((B,), 321.0, device=dev)
+    y = torch.randint(0, spec.num_classes, (B,), generator=g).to(dev) if spec.num_classes > 0 else None
+    eng = net.engine(B)
+    with torch.no_grad():
+        r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t, y)
+    seen = set()
+    for thr in (0.0, 0.2, 0.35, 0.5, 0.65, 0.8, 1.0):
+        e0, i0, s0, _ = eng.ee_forward(x, t, y, threshold=thr, mode=0)
+        e1, i1, s1, o1 = eng.ee_forward(x, t, y, threshold=thr, mode=1)
+        torch.cuda.synchronize()
+        assert o1 is None
+        assert torch.equal(i0, i1), (thr, i0.tolist(), i1.tolist())
+        assert torch.equal(e0, e1), thr
+        # scores: identical up to each sample's exit layer, NaN ("not produced") after it
+        for b in range(B):
+            k = min(int(i1[b]), depth - 1)
+            assert torch.equal(s0[:k + 1, b], s1[:k + 1, b])
+            assert torch.isnan(s1[k + 1:, b]).all()
+        r_sel, r_idx, scores = O.ee_select(r_eps, r_cls, r_outs, thr)
+        near = ((scores[:-1] - thr).abs() < PROBE_MARGIN_HOT).any(0)
+        same = i1.long() == r_idx
+        assert bool((same | near).all())
+        ok = same.nonzero().flatten()
+        assert rel_l2(e1[ok], r_sel[ok]) <= EPS_REL_L2
+        seen.update(i1.tolist())
+    assert len(seen) >= 4, f"exit layers exercised: {sorted(seen)}"  # compaction happened at several depths
+
+
+def test_ee_sampler_compact_mode_matches_simulate(dev):
+    """eesampler.get_samples(mode=1): same samples and the same indices log as mode 0 (bit-exact), over a window that
+    contains many exits; the batch-mean probe log is taken over the samples still in the batch (documented)."""
+    import duodiff_b200 as ddb
+    from duodiff_b200 import eesampler as ES
+    torch.manual_seed(8)
+    net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["cifar10"]), "mlp_probe_per_layer")
+    heat_(net, 9)
+    _spread_probes(net, 13)
+    net = net.eval().to(dev)
+    B, thr = 5, 0.4
+    g = torch.Generator().manual_seed(6)
+    noise = torch.randn(1000, B, 3, 32, 32, generator=g)
+    kw = dict(seed=1, num_channels=3, sample_height=32, sample_width=32, threshold=thr, depth=13, noise=noise)
+    s0, err0, idx0 = ES.get_samples(net, B, mode=0, **kw)
+    s1, err1, idx1 = ES.get_samples(net, B, mode=1, **kw)
+    assert np.array_equal(s0, s1)
+    assert torch.equal(idx0, idx1)
+    assert idx1.min() < 13, "no early exits happened: the test would not exercise compaction"
+    assert err1.shape == (1000, 13)
+    full = (idx0 >= 12).all(dim=1)  # steps where nobody left before the last probe: the two logs coincide
+    if full.any():
+        assert torch.allclose(err0[full], err1[full], atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
     from duodiff_b200.ddpm import Sampler
