@@ -280,6 +280,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.H * 64;
+    pdl_launch_dependents();   // PDL: the set-up below overlaps the predecessor's tail
+    if (a.b_dev) pdl_wait();   // the live batch size is written by an earlier kernel of the step
     const int n_items = (a.b_dev ? *a.b_dev : a.B) * a.H;
     const int my_items =
         (n_items > (int)blockIdx.x) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
+    pdl_wait();  // qkv is the predecessor's output
 
     if (warp == 8) {
         // ================================================================= TMA producer

@@ -11,6 +11,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/duodiff_b200.h"
@@ -140,6 +141,21 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint
     return DDB_OK;
 }
 
+// bf16 row-major [rows, cols]; box = 32 columns (64 B, SWIZZLE_64B) x box_rows: the CTA-pair GEMM's output sub-chunks
+static int make_tmap_bf16_sw64(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                               uint32_t box_rows) {
+    DDB_TRY(load_encode());
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DDB_ERR_CUDA, "cuTensorMapEncodeTiled(sw64) failed (%d)", (int)r);
+    return DDB_OK;
+}
+
 // bf16 [d2, d1, d0] (d0 contiguous) with byte strides; box {64, box1, 1}, SWIZZLE_128B
 static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                              uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box1) {
@@ -155,6 +171,26 @@ static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uin
     return DDB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ launches
+static int g_use_pdl = 1;  // ddb_set_option "pdl": programmatic dependent launch between the kernels of a step
+// Launch with programmaticStreamSerialization: the kernel may become resident while its predecessor drains; every
+// kernel launched this way calls pdl_wait() before it touches global memory (csrc/ptx.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    if (!g_use_pdl) {
+        kfn<<<grid, block, smem, st>>>(std::forward<Args>(args)...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kfn, std::forward<Args>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI>
 static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
@@ -167,13 +203,14 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     const int tiles = ((a.M + 127) / 128) * (a.N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     if (grid <= 0) return DDB_OK;
-    kfn<<<grid, 384, GemmCfg<BN>::SMEM_BYTES, st>>>(a);
+    CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(384), GemmCfg<BN>::SMEM_BYTES, st, a));
     LAUNCH_CHECK();
     return DDB_OK;
 }
 // runtime options (ddb_set_option): gemm_variant 2 = CTA-pair kernel (default), 1 = single-CTA kernel
 static int g_gemm_variant = 2;
 static int g_gemm_debug = 0;
+static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
 template <int EPI, bool STATS, int STAGES, int NBUF>
 static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
@@ -190,7 +227,7 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     int clusters = num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return DDB_OK;
-    kfn<<<2 * clusters, 384, kSmem, st>>>(a);
+    CUDA_TRY(launch_pdl(kfn, dim3(2 * clusters), dim3(384), kSmem, st, a));
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -234,11 +271,11 @@ static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_de
     if (grid <= 0) return DDB_OK;
     ProfScope ps(PC_LN_STATS);
     switch (D) {
-        case 256: ln_stats_kernel<256><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
-        case 512: ln_stats_kernel<512><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
-        case 768: ln_stats_kernel<768><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
-        case 1024: ln_stats_kernel<1024><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
-        case 2048: ln_stats_kernel<2048><<<grid, 256, 0, st>>>(x, M, m_dev, stats, pw, pb, psig); break;
+        case 256: CUDA_TRY(launch_pdl(ln_stats_kernel<256>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
+        case 512: CUDA_TRY(launch_pdl(ln_stats_kernel<512>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
+        case 768: CUDA_TRY(launch_pdl(ln_stats_kernel<768>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
+        case 1024: CUDA_TRY(launch_pdl(ln_stats_kernel<1024>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
+        case 2048: CUDA_TRY(launch_pdl(ln_stats_kernel<2048>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
         default: return fail(DDB_ERR_INVALID, "embed_dim %d unsupported (need 256/512/768/1024/2048)", D);
     }
     LAUNCH_CHECK();
@@ -270,7 +307,8 @@ static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st) 
     a.B = B;
     a.trace = g_attn_trace;
     const int items = B * a.H;
-    attention_tcgen05_kernel<<<items < num_sms ? items : num_sms, ATT3_THREADS, ATT3_SMEM, st>>>(a);
+    CUDA_TRY(launch_pdl(attention_tcgen05_kernel, dim3(items < num_sms ? items : num_sms), dim3(ATT3_THREADS),
+                        ATT3_SMEM, st, a));
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -448,6 +486,8 @@ static int plan_gemm(GemmArgs& g, const ddb_model* m, const void* A0, int K0, co
     if (BN == 256) DDB_TRY(make_tmap_bf16(&g.tmB2, W.w->p, W.N, K0 + K1, K0 + K1, 128));
     if (out) DDB_TRY(make_tmap_bf16(&g.tmOut, out, m->Mpad, W.N, W.N, 128));
     if (res) DDB_TRY(make_tmap_bf16(&g.tmRes, res, m->Mpad, W.N, W.N, 128));
+    if (out && BN == 256) DDB_TRY(make_tmap_bf16_sw64(&g.tmOut2, out, m->Mpad, W.N, W.N, 128));
+    if (res && BN == 256) DDB_TRY(make_tmap_bf16_sw64(&g.tmRes2, res, m->Mpad, W.N, W.N, 128));
     return DDB_OK;
 }
 static void plan_decode_geometry(GemmArgs& g, const ddb_model* m, float* img) {
@@ -624,8 +664,9 @@ static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float*
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
     const int smem = (C * (CONV_BAND + 2) * (W + 2) + C * C * 9 + C) * 4;
     ProfScope ps(PC_CONV);
-    conv3x3_kernel<<<B * (H / CONV_BAND), 256, smem, st>>>(in, hw.conv_w->as<float>(), hw.conv_b->as<float>(), out,
-                                                            C, H, W, n_dev, slot_map);
+    CUDA_TRY(launch_pdl(conv3x3_kernel, dim3(B * (H / CONV_BAND)), dim3(256), (size_t)smem, st, in,
+                        (const float*)hw.conv_w->as<float>(), (const float*)hw.conv_b->as<float>(), out, C, H, W, n_dev,
+                        slot_map));
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -659,10 +700,12 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         const int grid = B * (c.img_size / c.patch_size);
         float2* emb_stats = ee ? nullptr : st2;
 #define DDB_EMBED(PD)                                                                                              \
-    embed_tokens_kernel<PD><<<grid, 256, 0, st>>>(                                                                 \
-        x, t, reinterpret_cast<const long long*>(y), m->pe_wt->as<float>(), m->pe_bias->as<float>(),               \
-        m->pos->as<float>(), m->label_emb ? m->label_emb->as<float>() : nullptr, m->x0->as<__nv_bfloat16>(),       \
-        emb_stats, c.in_chans, c.img_size, c.img_size, c.patch_size, D, m->L, m->extras, c.normalize_timesteps)
+    CUDA_TRY(launch_pdl(embed_tokens_kernel<PD>, dim3(grid), dim3(256), 0, st, x, t,                               \
+                        reinterpret_cast<const long long*>(y), (const float*)m->pe_wt->as<float>(),                \
+                        (const float*)m->pe_bias->as<float>(), (const float*)m->pos->as<float>(),                  \
+                        (const float*)(m->label_emb ? m->label_emb->as<float>() : nullptr),                        \
+                        m->x0->as<__nv_bfloat16>(), emb_stats, c.in_chans, c.img_size, c.img_size, c.patch_size, D, \
+                        m->L, m->extras, (int)c.normalize_timesteps))
         switch (m->pd) {
             case 12: DDB_EMBED(12); break;
             case 16: DDB_EMBED(16); break;
@@ -866,9 +909,9 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y
         DDB_TRY(forward_impl(m, x, s->t_vec->as<float>(), y, B, eps, false, st));
     }
     (void)t_host;
-    ddpm_step_kernel<<<(unsigned)((s->n / 4 + 255) / 256), 256, 0, st>>>(x, eps, z_all, s->n, s->n,
-                                                                         s->coef->as<float>(), s->t_dev->as<int>(), 0,
-                                                                         s->step_mode, seed, seed_dev, x_save);
+    CUDA_TRY(launch_pdl(ddpm_step_kernel, dim3((unsigned)((s->n / 4 + 255) / 256)), dim3(256), 0, st, x,
+                        (const float*)eps, z_all, s->n, s->n, (const float*)s->coef->as<float>(),
+                        (const int*)s->t_dev->as<int>(), 0, s->step_mode, seed, seed_dev, x_save));
     LAUNCH_CHECK();
     dec_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>());
     LAUNCH_CHECK();
@@ -892,10 +935,18 @@ int ddb_set_option(const char* name, int32_t value) {
         g_gemm_debug = value;
         return DDB_OK;
     }
+    if (!strcmp(name, "pdl")) {
+        g_use_pdl = value != 0;
+        return DDB_OK;
+    }
     return fail(DDB_ERR_INVALID, "unknown option '%s'", name);
 }
 
 int ddb_debug_set_ptr(const char* name, void* p) {
+    if (name && !strcmp(name, "gemm_trace")) {
+        g_gemm_trace = reinterpret_cast<long long*>(p);
+        return DDB_OK;
+    }
     if (name && !strcmp(name, "attn_trace")) {
         g_attn_trace = reinterpret_cast<long long*>(p);
         return DDB_OK;
@@ -1103,6 +1154,8 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
     DDB_TRY(make_tmap_bf16(&g.tmB2, w_dev, N, K0 + K1, K0 + K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmOut, out_dev, M, N, N, 128));
     if (residual_dev) DDB_TRY(make_tmap_bf16(&g.tmRes, residual_dev, M, N, N, 128));
+    DDB_TRY(make_tmap_bf16_sw64(&g.tmOut2, out_dev, M, N, N, 128));
+    if (residual_dev) DDB_TRY(make_tmap_bf16_sw64(&g.tmRes2, residual_dev, M, N, N, 128));
     g.stats_out = reinterpret_cast<float2*>(stats_out_dev);
     return variant == 2 ? launch_gemm2(g, epi, di.num_sms, (cudaStream_t)stream)
                         : launch_gemm(g, epi, di.num_sms, (cudaStream_t)stream);

@@ -71,6 +71,8 @@ __global__ void __launch_bounds__(256, 2) embed_tokens_kernel(
     const int Hp = H / P;
     const int b = blockIdx.x / Hp, hh = blockIdx.x % Hp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();  // x_img / tsteps come from the previous step's kernels
     // gather: k = (c*P + p1)*P + p2 ; token ww ; pixel (c, hh*P+p1, ww*P+p2)
     {
         // C*P*W = PD*16 elements: all global loads are issued before the first shared-memory store
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
     constexpr int CH = D / 256;  // 16-byte chunks per lane
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const int Mr = m_dev ? *m_dev : M;
     if (row >= Mr) return;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
@@ -310,6 +314,8 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
     extern __shared__ float conv_smem[];  // [C][CONV_BAND+2][W+2] then weights [C*C*9] + bias[C]
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
+    pdl_launch_dependents();
+    pdl_wait();
     if (n_dev && b >= *n_dev) return;
     const int ob = slot_map ? slot_map[b] : b;
     const int SW = W + 2, SH = CONV_BAND + 2;
@@ -371,6 +377,8 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
                                                         int t_host, int mode, unsigned long long seed,
                                                         const unsigned long long* __restrict__ seed_dev,
                                                         float* __restrict__ x_save) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = t_dev ? *t_dev : t_host;
     if (seed_dev) seed = *seed_dev;  // graph replay: the Philox key lives in device memory
     const float c0 = coef[t * 4 + 0], c1 = coef[t * 4 + 1], sg = coef[t * 4 + 2];

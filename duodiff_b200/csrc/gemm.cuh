@@ -37,6 +37,8 @@ struct GemmArgs {
     CUtensorMap tmB2;   // same tensor, box {64, 128}: one CTA's half of the W tile in the CTA-pair kernel
     CUtensorMap tmOut;  // [M, N] bf16, box {64, 128}
     CUtensorMap tmRes;  // [M, N] bf16 residual, box {64, 128}
+    CUtensorMap tmOut2; // [M, N] bf16, box {32, 128}, SWIZZLE_64B (CTA-pair kernel: 32-column sub-chunks)
+    CUtensorMap tmRes2; // [M, N] bf16 residual, box {32, 128}, SWIZZLE_64B
     int M, N, K0, K1;
     const float* bias;    // [N] or nullptr
     const float* colsum;  // [N]           (LN epilogues)
@@ -48,6 +50,7 @@ struct GemmArgs {
     int debug;          // bench-only knobs (ddb_set_option "gemm_debug"): 1 = epilogue drains TMEM but skips math/stores,
                         // 2 = MMA issue skipped (barrier traffic only), 4 = no TMA operand loads
     float2* stats_out;  // optional [M, N/64]: per-row (mean, M2) of every 64-column output chunk (gemm2 only)
+    long long* trace;   // bench-only: cluster 0 / leader records clock64() per tile ([tile][16])
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;
@@ -111,6 +114,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    pdl_launch_dependents();
+    if (a.m_dev) pdl_wait();
     const int M = a.m_dev ? *a.m_dev : a.M;
     const int nblk_n = a.N / BN;
     const int nblk_m = (M + Cfg::BM - 1) / Cfg::BM;
@@ -142,6 +147,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();
 
     if (warp == 0) {
         // ===================================================================== TMA producer

@@ -75,6 +75,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
 
+    // PDL: the set-up below (barriers, TMEM, descriptor prefetch, cluster sync) overlaps the predecessor's tail
+    pdl_launch_dependents();
+    if (a.m_dev) pdl_wait();  // the live row count is written by an earlier kernel of the step
     const int M = a.m_dev ? *a.m_dev : a.M;
     const int nblk_n = a.N / BN;
     const int nblk_m = (M + 255) / 256;
@@ -110,6 +113,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    pdl_wait();  // everything below reads or overwrites buffers of earlier kernels
 
     if (warp == kProducerWarp) {
         // ===================================================================== TMA producer (both CTAs)

@@ -107,6 +107,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the sampling step is launched with programmaticStreamSerialization: it may become resident while its
+// predecessor is still draining.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as this
+// grid's CTAs free their SMs; pdl_wait() blocks until the predecessor grid has completed and its writes are visible.
+// It must precede the first access to anything a previous kernel wrote (and any write a previous kernel may still
+// read).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- named barriers
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
