@@ -212,17 +212,19 @@ static int g_gemm_variant = 2;
 static int g_gemm_debug = 0;
 static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
-template <int EPI, bool STATS, int STAGES, int NBUF>
+static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
+                              // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
+template <int EPI, bool STATS, int STAGES, int NBUF, int BN = 256>
 static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
-    constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN>::SMEM_BYTES;
-    auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF>;
+    constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN, BN>::SMEM_BYTES;
+    auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF, BN>;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         configured = true;
     }
-    const int tiles = ((a.M + 255) / 256) * (a.N / 256);
+    const int tiles = ((a.M + 255) / 256) * (a.N / BN);
     if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
     int clusters = num_sms / 2;
     if (tiles < clusters) clusters = tiles;
@@ -238,6 +240,21 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     const bool stats = a.stats_out != nullptr;
     const bool short_k = (a.K0 + a.K1) <= 512;
+    // Wave quantisation: with 256x256 tiles an N = 512 GEMM at M = 32 896 has 258 tiles for 74 CTA pairs (3.49 -> 4
+    // rounds); 256x128 tiles give 516 (6.97 -> 7 half-size rounds).  Used whenever it removes at least 5 % of the
+    // rounds' work.
+    {
+        const int clusters = num_sms / 2, mb = (a.M + 255) / 256;
+        const int t256 = mb * (a.N / 256), t128 = mb * (a.N / 128);
+        const double r256 = (double)((t256 + clusters - 1) / clusters), r128 = 0.5 * ((t128 + clusters - 1) / clusters);
+        if (g_gemm_bn128 && a.N % 128 == 0 && r128 < 0.95 * r256 && (epi == EPI_BIAS || epi == EPI_RES)) {
+            if (epi == EPI_BIAS)
+                return stats ? launch_gemm2_t<EPI_BIAS, true, 6, 2, 128>(a, num_sms, st)
+                             : launch_gemm2_t<EPI_BIAS, false, 6, 2, 128>(a, num_sms, st);
+            return stats ? launch_gemm2_t<EPI_RES, true, 6, 2, 128>(a, num_sms, st)
+                         : launch_gemm2_t<EPI_RES, false, 6, 2, 128>(a, num_sms, st);
+        }
+    }
     switch (epi) {
         case EPI_BIAS:
             return stats ? launch_gemm2_t<EPI_BIAS, true, 5, 2>(a, num_sms, st)
@@ -484,6 +501,7 @@ static int plan_gemm(GemmArgs& g, const ddb_model* m, const void* A0, int K0, co
     if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, A1, m->Mpad, K1, K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmB, W.w->p, W.N, K0 + K1, K0 + K1, BN));
     if (BN == 256) DDB_TRY(make_tmap_bf16(&g.tmB2, W.w->p, W.N, K0 + K1, K0 + K1, 128));
+    if (BN == 256) DDB_TRY(make_tmap_bf16(&g.tmB3, W.w->p, W.N, K0 + K1, K0 + K1, 64));
     if (out) DDB_TRY(make_tmap_bf16(&g.tmOut, out, m->Mpad, W.N, W.N, 128));
     if (res) DDB_TRY(make_tmap_bf16(&g.tmRes, res, m->Mpad, W.N, W.N, 128));
     if (out && BN == 256) DDB_TRY(make_tmap_bf16_sw64(&g.tmOut2, out, m->Mpad, W.N, W.N, 128));
@@ -935,6 +953,10 @@ int ddb_set_option(const char* name, int32_t value) {
         g_gemm_debug = value;
         return DDB_OK;
     }
+    if (!strcmp(name, "gemm_bn128")) {
+        g_gemm_bn128 = value != 0;
+        return DDB_OK;
+    }
     if (!strcmp(name, "pdl")) {
         g_use_pdl = value != 0;
         return DDB_OK;
@@ -1152,6 +1174,7 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
     if (K1 > 0) DDB_TRY(make_tmap_bf16(&g.tmA1, a1_dev, M, K1, K1, 128));
     DDB_TRY(make_tmap_bf16(&g.tmB, w_dev, N, K0 + K1, K0 + K1, 256));
     DDB_TRY(make_tmap_bf16(&g.tmB2, w_dev, N, K0 + K1, K0 + K1, 128));
+    DDB_TRY(make_tmap_bf16(&g.tmB3, w_dev, N, K0 + K1, K0 + K1, 64));
     DDB_TRY(make_tmap_bf16(&g.tmOut, out_dev, M, N, N, 128));
     if (residual_dev) DDB_TRY(make_tmap_bf16(&g.tmRes, residual_dev, M, N, N, 128));
     DDB_TRY(make_tmap_bf16_sw64(&g.tmOut2, out_dev, M, N, N, 128));

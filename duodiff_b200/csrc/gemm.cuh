@@ -35,6 +35,7 @@ struct GemmArgs {
     CUtensorMap tmA1;   // [M, K1] bf16 (second K source; unused when K1 == 0)
     CUtensorMap tmB;    // [N, K0+K1] bf16, box {64, BN}
     CUtensorMap tmB2;   // same tensor, box {64, 128}: one CTA's half of the W tile in the CTA-pair kernel
+    CUtensorMap tmB3;   // same tensor, box {64, 64}: half of a 128-wide W tile (CTA-pair kernel, N = 512 GEMMs)
     CUtensorMap tmOut;  // [M, N] bf16, box {64, 128}
     CUtensorMap tmRes;  // [M, N] bf16 residual, box {64, 128}
     CUtensorMap tmOut2; // [M, N] bf16, box {32, 128}, SWIZZLE_64B (CTA-pair kernel: 32-column sub-chunks)

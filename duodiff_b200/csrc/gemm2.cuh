@@ -24,15 +24,15 @@
 
 namespace ddb {
 
-template <int STAGES_, int NBUF_, bool LN_>
+template <int STAGES_, int NBUF_, bool LN_, int BN_ = 256>
 struct Gemm2Cfg {
     static constexpr int BM = 128;  // rows per CTA (256 per pair)
-    static constexpr int BN = 256;
+    static constexpr int BN = BN_;  // 256, or 128 for the N = 512 GEMMs (wave quantisation: 258 -> 516 tiles on 74 pairs)
     static constexpr int BK = 64;
     static constexpr int STAGES = STAGES_;
     static constexpr int NBUF = NBUF_;                 // staging buffers per epilogue warpgroup
     static constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-    static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB: this CTA's half of W
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 / 8 KB: this CTA's half of W
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BUF_BYTES = 128 * 128;
     static constexpr int AUX_BYTES = LN_ ? 3072 : 1024;  // per buffer: [rowstats 1 KB][bias 1 KB][colsum 1 KB]
@@ -46,12 +46,13 @@ struct Gemm2Cfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int EPI, bool STATS, int STAGES, int NBUF>
+template <int EPI, bool STATS, int STAGES, int NBUF, int BN_ = 256>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_tcgen05_kernel(const __grid_constant__ GemmArgs a) {
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
-    using Cfg = Gemm2Cfg<STAGES, NBUF, kLN>;
+    using Cfg = Gemm2Cfg<STAGES, NBUF, kLN, BN_>;
     constexpr int BN = Cfg::BN;
+    static_assert(BN == 256 || BN == 128, "tile width");
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem + Cfg::OFF_A;
@@ -89,7 +90,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // swizzled tiles need 1024-byte alignment
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&a.tmA0);
-        tma_prefetch_desc(&a.tmB2);
+        tma_prefetch_desc(BN == 256 ? &a.tmB2 : &a.tmB3);
         if (a.K1 > 0) tma_prefetch_desc(&a.tmA1);
         tma_prefetch_desc(&a.tmOut);
         if (EPI == EPI_RES) tma_prefetch_desc(&a.tmRes);
@@ -123,7 +124,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
                 const int row0 = m_blk * 256 + (int)rank * 128;
-                const int wrow0 = n_blk * BN + (int)rank * 128;
+                const int wrow0 = n_blk * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     const uint32_t fb = leader_smem_addr(&full_bar[stage]);
@@ -135,7 +136,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                             tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &a.tmA0, fb, kb * Cfg::BK, row0);
                         else
                             tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &a.tmA1, fb, (kb - nkb0) * Cfg::BK, row0);
-                        tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, &a.tmB2, fb, kb * Cfg::BK, wrow0);
+                        tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, BN == 256 ? &a.tmB2 : &a.tmB3, fb, kb * Cfg::BK,
+                                         wrow0);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -186,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             const uint32_t ph = (it >> 1) & 1;
             uint8_t* ab = sAux + buf * Cfg::AUX_BYTES;
             mbar_wait(&aux_empty[buf], ph ^ 1);
-            const int col = n_blk * BN + t * 4;
+            const int col = n_blk * BN + (t * 4) % BN;  // BN = 128: threads 32-63 duplicate (harmless)
             if constexpr (kLN) {
                 float2* srow = reinterpret_cast<float2*>(ab);
 #pragma unroll
@@ -197,11 +199,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     if (row < M) ln_row_stats(a.stats, row, a.nparts, a.ln_dim, a.ln_eps, rstd, mr);
                     srow[r] = make_float2(rstd, mr);
                 }
-                *reinterpret_cast<float4*>(ab + 1024 + t * 16) =
+                *reinterpret_cast<float4*>(ab + 1024 + ((t * 16) % (BN * 4))) =
                     a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(ab + 2048 + t * 16) = __ldg(reinterpret_cast<const float4*>(a.colsum + col));
+                *reinterpret_cast<float4*>(ab + 2048 + ((t * 16) % (BN * 4))) =
+                    __ldg(reinterpret_cast<const float4*>(a.colsum + col));
             } else {
-                *reinterpret_cast<float4*>(ab + t * 16) =
+                *reinterpret_cast<float4*>(ab + ((t * 16) % (BN * 4))) =
                     a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             mbar_arrive(&aux_full[buf]);  // release: the st.shared above are visible to the waiting epilogue warps
@@ -215,16 +218,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const uint32_t bar_id = 1 + g;
         uint8_t* my_bufs = sOut + g * NBUF * Cfg::OUT_BUF_BYTES;
         uint64_t* my_res = res_bar + g * NBUF;
-        constexpr int CHUNKS_PER_WG = 2;
+        constexpr int CHUNKS_PER_WG = BN / 128;  // 64-column chunks per warpgroup and tile
         const bool traffic = !(a.debug & 8);
         uint32_t q = 0;
 
         // chunk sequence number s (0,1,2,...) of this warpgroup -> (tile, chunk-in-tile); residual prefetch
         auto prefetch_res = [&](uint32_t s) {
-            const int tile = cluster_id + (int)(s >> 1) * num_clusters;
+            const int tile = cluster_id + (int)(s / CHUNKS_PER_WG) * num_clusters;
             if (tile >= num_tiles) return;
             const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
-            const int c = g + 2 * (int)(s & 1);
+            const int c = g + 2 * (int)(s % CHUNKS_PER_WG);
             uint64_t* rb = &my_res[s % NBUF];
             mbar_expect_tx(rb, Cfg::OUT_BUF_BYTES);
             tma_load_2d(my_bufs + (s % NBUF) * Cfg::OUT_BUF_BYTES, &a.tmRes, rb, n_blk * BN + c * 64,
