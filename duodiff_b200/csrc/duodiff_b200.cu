@@ -680,16 +680,20 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
 static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st,
                     const int* n_dev = nullptr, const int* slot_map = nullptr) {
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
-    const int smem = (C * (CONV_BAND + 2) * (W + 2) + C * C * 9 + C) * 4;
+    const size_t smem = (size_t)C * (CONV_BAND + 2) * (W + 8) * 4;
+    const dim3 grid(B * (H / CONV_BAND));
+    const float* w = hw.conv_w->as<float>();
+    const float* bs = hw.conv_b->as<float>();
     ProfScope ps(PC_CONV);
-    CUDA_TRY(launch_pdl(conv3x3_kernel, dim3(B * (H / CONV_BAND)), dim3(256), (size_t)smem, st, in,
-                        (const float*)hw.conv_w->as<float>(), (const float*)hw.conv_b->as<float>(), out, C, H, W, n_dev,
-                        slot_map));
+    switch (C) {
+        case 3: CUDA_TRY(launch_pdl(conv3x3_kernel<3>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map)); break;
+        case 4: CUDA_TRY(launch_pdl(conv3x3_kernel<4>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map)); break;
+        default: return fail(DDB_ERR_INVALID, "in_chans %d unsupported by the final 3x3 conv (3 or 4)", C);
+    }
     LAUNCH_CHECK();
     return DDB_OK;
 }
 
-// The launch sequence of one forward.  ee: evaluate probes + heads (simulate mode) into m->scores / m->outputs.
 // Compaction-mode parameters of a forward (ddb_ee_forward mode 1)
 struct EeCompact {
     float threshold;

@@ -305,39 +305,65 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
 // (sample, 16-row band).  Optional fused DDPM update (see ddpm_step_kernel) when x_io != null.
 // =====================================================================================================
 constexpr int CONV_BAND = 16;
+// One CTA per (sample, 16-row band): the band (+1 halo row each side) of all C channels is staged in shared memory
+// with 128-bit loads, then every thread produces 4 horizontally adjacent pixels of every output channel from
+// registers (a 3 x 6 window per input channel) and stores them as one float4 per channel.  Requires W % 4 == 0.
 // n_dev / slot_map (early-exit compaction): only the first *n_dev input images are live and image b is written to
 // output slot slot_map[b].
+template <int C>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
-                                                      const float* __restrict__ bias, float* __restrict__ out, int C,
-                                                      int H, int W, const int* __restrict__ n_dev,
+                                                      const float* __restrict__ bias, float* __restrict__ out, int H,
+                                                      int W, const int* __restrict__ n_dev,
                                                       const int* __restrict__ slot_map) {
-    extern __shared__ float conv_smem[];  // [C][CONV_BAND+2][W+2] then weights [C*C*9] + bias[C]
+    extern __shared__ __align__(16) float conv_smem[];  // [C][CONV_BAND+2][W+8] (4 pad floats left and right)
+    __shared__ float sw[C * C * 9 + C];
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
     pdl_launch_dependents();
+    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x) sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
     pdl_wait();
     if (n_dev && b >= *n_dev) return;
     const int ob = slot_map ? slot_map[b] : b;
-    const int SW = W + 2, SH = CONV_BAND + 2;
-    float* sw = conv_smem + C * SH * SW;
-    for (int i = threadIdx.x; i < C * SH * SW; i += blockDim.x) {
-        const int xx = i % SW - 1, yy = (i / SW) % SH - 1 + y0, c = i / (SW * SH);
-        conv_smem[i] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? in[(((size_t)b * C + c) * H + yy) * W + xx] : 0.f;
+    const int SW = W + 8, SH = CONV_BAND + 2;
+    const int w4 = W / 4;
+    // interior: rows y0-1 .. y0+16, float4 granularity; halo columns are zero
+    for (int i = threadIdx.x; i < C * SH * (w4 + 2); i += blockDim.x) {
+        const int q = i % (w4 + 2), r = (i / (w4 + 2)) % SH, c = i / ((w4 + 2) * SH);
+        const int yy = y0 - 1 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q >= 1 && q <= w4 && yy >= 0 && yy < H)
+            v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * C + c) * H + yy) * W) + (q - 1));
+        *reinterpret_cast<float4*>(conv_smem + (c * SH + r) * SW + q * 4) = v;
     }
-    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x) sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
     __syncthreads();
-    for (int i = threadIdx.x; i < C * CONV_BAND * W; i += blockDim.x) {
-        const int xx = i % W, yy = (i / W) % CONV_BAND, co = i / (W * CONV_BAND);
-        float acc = sw[C * C * 9 + co];
+    for (int i = threadIdx.x; i < CONV_BAND * w4; i += blockDim.x) {
+        const int xq = i % w4, yy = i / w4;  // output pixels (y0+yy, 4*xq .. 4*xq+3)
+        float acc[C][4];
+#pragma unroll
+        for (int co = 0; co < C; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = sw[C * C * 9 + co];
+#pragma unroll
         for (int ci = 0; ci < C; ++ci) {
-            const float* sp = conv_smem + (ci * SH + yy) * SW + xx;
-            const float* wp = sw + (co * C + ci) * 9;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy) {
+                // smem column of pixel x is x + 4; the window needs x-1 .. x+4 -> columns 4*xq+3 .. 4*xq+8
+                const float* rp = conv_smem + (ci * SH + yy + dy) * SW + 4 * xq;
+                const float4 m = *reinterpret_cast<const float4*>(rp + 4);
+                const float l = rp[3], r = rp[8];
+                const float win[6] = {l, m.x, m.y, m.z, m.w, r};
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) acc = fmaf(wp[dy * 3 + dx], sp[dy * SW + dx], acc);
+                for (int co = 0; co < C; ++co) {
+                    const float* wp = sw + (co * C + ci) * 9 + dy * 3;
+                    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        acc[co][p] = fmaf(w0, win[p], fmaf(w1, win[p + 1], fmaf(w2, win[p + 2], acc[co][p])));
+                }
+            }
         }
-        out[(((size_t)ob * C + co) * H + y0 + yy) * W + xx] = acc;
+#pragma unroll
+        for (int co = 0; co < C; ++co)
+            *(reinterpret_cast<float4*>(out + (((size_t)ob * C + co) * H + y0 + yy) * W) + xq) =
+                make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
     }
 }
 

@@ -92,6 +92,13 @@ __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ stats, i
     mean_rstd = mean * rstd;
 }
 
+// EPI_DECODE store of one token: out[b, c, hh*P+p1, ww*P+p2] = LN-fixed acc[(p1*P+p2)*C + c]; warpgroup g takes the
+// patch rows p1 in [g*P/2, (g+1)*P/2) and writes each (c, p1) run of P pixels as one vector.
+struct GemmArgs;
+template <int C, int P>
+__device__ __forceinline__ void decode_store(const uint32_t (&acc)[2][32], const GemmArgs& a, float rstd,
+                                             float mean_rstd, int b, int hh, int ww, int g);
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmArgs a) {
     using Cfg = GemmCfg<BN>;
@@ -339,9 +346,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 }
             } else {
                 // ---------------------------------------------------------------- EPI_DECODE (BN == 64)
-                // warpgroup g handles columns [32g, 32g+32) of the (zero-padded) patch vector
-                uint32_t acc[32];
-                tmem_ld_32x32b_x32(t_row + g * 32, acc);
+                // every thread reads its token's whole (zero-padded) patch vector; warpgroup g stores the patch rows
+                // p1 in its half as P-wide vectors (un-patchify: feature (p1, p2, c), channel innermost)
+                uint32_t acc[2][32];
+                tmem_ld_32x32b_x32(t_row, acc[0]);
+                tmem_ld_32x32b_x32(t_row + 32, acc[1]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -351,18 +360,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                     if (l >= a.extras) {
                         const int n = l - a.extras;
                         const int hh = n / a.Wp, ww = n % a.Wp;
-#pragma unroll 4
-                        for (int e = 0; e < 32; ++e) {
-                            const int j = g * 32 + e;  // feature (p1, p2, c), channel innermost
-                            if (j < a.patch_dim) {
-                                const float bj = a.bias ? __ldg(a.bias + j) : 0.f;
-                                const float val =
-                                    fmaf(__uint_as_float(acc[e]), rstd, fmaf(-mean_rstd, __ldg(a.colsum + j), bj));
-                                const int ch = j % a.C, pp = j / a.C;
-                                const int p1 = pp / a.P, p2 = pp % a.P;
-                                a.img[(((size_t)b * a.C + ch) * a.H + hh * a.P + p1) * a.W + ww * a.P + p2] = val;
-                            }
-                        }
+                        if (a.C == 3 && a.P == 4)
+                            decode_store<3, 4>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                        else if (a.C == 3 && a.P == 2)
+                            decode_store<3, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                        else if (a.C == 4 && a.P == 2)
+                            decode_store<4, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                        else
+                            __trap();  // plan_decode_geometry() rejects other (in_chans, patch_size) pairs
                     }
                 }
             }
@@ -375,6 +380,33 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    }
+}
+
+template <int C, int P>
+__device__ __forceinline__ void decode_store(const uint32_t (&acc)[2][32], const GemmArgs& a, float rstd,
+                                             float mean_rstd, int b, int hh, int ww, int g) {
+    static_assert(P == 2 || P == 4, "patch size");
+#pragma unroll
+    for (int pr = 0; pr < P / 2; ++pr) {
+        const int p1 = g * (P / 2) + pr;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) {
+            float v[P];
+#pragma unroll
+            for (int p2 = 0; p2 < P; ++p2) {
+                // p1 is only known at run time through g: select between the two compile-time candidates
+                const int j0 = ((pr)*P + p2) * C + ch, j1 = ((P / 2 + pr) * P + p2) * C + ch;
+                const float raw = __uint_as_float(g ? acc[j1 >> 5][j1 & 31] : acc[j0 >> 5][j0 & 31]);
+                const int j = g ? j1 : j0;
+                v[p2] = fmaf(raw, rstd, fmaf(-mean_rstd, __ldg(a.colsum + j), a.bias ? __ldg(a.bias + j) : 0.f));
+            }
+            float* dst = a.img + (((size_t)b * C + ch) * a.H + hh * P + p1) * a.W + ww * P;
+            if constexpr (P == 4)
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else
+                *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+        }
     }
 }
 
