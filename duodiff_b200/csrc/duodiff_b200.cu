@@ -385,6 +385,8 @@ struct ddb_model {
     int L = 0, Np = 0, extras = 0, pd = 0, D = 0, Hh = 0, Mmax = 0, Mpad = 0;
     size_t chw = 0;
     Buf pe_wt, pe_bias, pos, label_emb;
+    Buf pe_w2, pos_patch, a_patch;  // tensor-core patch embed: [D,128] bf16 weight, bf16 pos rows, gathered patches
+    GemmArgs embed_gemm;
     std::vector<BlockW> blocks;
     HeadW final_head;
     std::vector<HeadW> ee_heads;
@@ -557,6 +559,15 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     CUDA_TRY(cudaMemcpy(m->pe_bias->p, pb, (size_t)D * 4, cudaMemcpyDeviceToDevice));
     DDB_TRY(new_buf(m->pos, (size_t)m->L * D * 4));
     CUDA_TRY(cudaMemcpy(m->pos->p, pos, (size_t)m->L * D * 4, cudaMemcpyDeviceToDevice));
+    DDB_TRY(new_buf(m->pe_w2, (size_t)D * 128 * 2));
+    pack_patch_embed_kernel<<<(D * 128 + 255) / 256, 256>>>(pw, D, m->pd, m->pe_w2->as<__nv_bfloat16>());
+    LAUNCH_CHECK();
+    DDB_TRY(new_buf(m->pos_patch, (size_t)m->Np * D * 2));
+    cast_bf16_kernel<<<(unsigned)(((size_t)m->Np * D + 255) / 256), 256>>>(pos + (size_t)m->extras * D,
+                                                                         m->pos_patch->as<__nv_bfloat16>(),
+                                                                         (size_t)m->Np * D);
+    LAUNCH_CHECK();
+    DDB_TRY(new_buf(m->a_patch, (size_t)cfg->max_batch * m->Np * 128 * 2));  // zero: the K padding stays zero
     if (cfg->num_classes > 0) {
         DDB_TRY(get_tensor(tm, up + "label_emb.weight", (int64_t)cfg->num_classes * D, &lab));
         DDB_TRY(new_buf(m->label_emb, (size_t)cfg->num_classes * D * 4));
@@ -639,6 +650,23 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     }
     DDB_TRY(plan_attention(m->attn, m->qkv->as<__nv_bfloat16>(), m->ao->as<__nv_bfloat16>(), cfg->max_batch, m->L,
                            m->Hh));
+    {
+        // patch embed as a GEMM: [B*256, 128] x [D, 128]^T, output rows scattered to the token buffer (3-D map)
+        GemmArgs& g = m->embed_gemm;
+        memset(&g, 0, sizeof(g));
+        const uint64_t rowsA = (uint64_t)cfg->max_batch * m->Np;
+        g.M = (int)rowsA, g.N = D, g.K0 = 128, g.K1 = 0;
+        g.bias = m->pe_bias->as<float>();
+        g.nparts = 1, g.ln_dim = D, g.ln_eps = cfg->ln_eps;
+        g.embed_mode = 1, g.tok_L = m->L, g.tok_extras = m->extras;
+        DDB_TRY(make_tmap_bf16(&g.tmA0, m->a_patch->p, rowsA, 128, 128, 128));
+        DDB_TRY(make_tmap_bf16(&g.tmB, m->pe_w2->p, D, 128, 128, 256));
+        DDB_TRY(make_tmap_bf16(&g.tmB2, m->pe_w2->p, D, 128, 128, 128));
+        DDB_TRY(make_tmap_bf16(&g.tmB3, m->pe_w2->p, D, 128, 128, 64));
+        DDB_TRY(make_tmap_bf16_3d(&g.tmOut, m->x0->as<__nv_bfloat16>() + (size_t)m->extras * D, D, m->Np,
+                                  cfg->max_batch, (uint64_t)D * 2, (uint64_t)m->L * D * 2, 128));
+        DDB_TRY(make_tmap_bf16(&g.tmRes, m->pos_patch->p, m->Np, D, D, 128));
+    }
     DDB_TRY(plan_gemm(m->final_dec, m, cur, D, nullptr, 0, m->final_head.dec, 64, nullptr, nullptr, st));
     plan_decode_geometry(m->final_dec, m, m->img_pre->as<float>());
     if (cfg->early_exit) {
@@ -715,9 +743,29 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     int* een = cp ? m->ee_n->as<int>() : nullptr;
     float2* st2 = m->stats->as<float2>();
 
-    // token assembly; outside the early-exit path it also writes the LayerNorm statistics of the first block
-    // (the early-exit path runs ln_stats_kernel anyway: it carries the MLP probe)
-    {
+    // ---- token assembly
+    float2* stp = m->stats_p->as<float2>();
+    const bool pair = (g_gemm_variant == 2);
+    if (pair && m->Np == 256) {
+        // tensor-core path: gather patches (bf16 hi + lo) -> CTA-pair GEMM (+bias +pos_embed, LayerNorm partials,
+        // rows scattered into the token buffer) -> time / label token rows
+        ProfScope ps(PC_EMBED);
+        const size_t n_thr = (size_t)B * c.in_chans * c.img_size * (c.img_size / c.patch_size);
+        CUDA_TRY(launch_pdl(patch_gather_kernel, dim3((unsigned)((n_thr + 255) / 256)), dim3(256), 0, st, x,
+                            m->a_patch->as<__nv_bfloat16>(), B, (int)c.in_chans, (int)c.img_size, (int)c.img_size,
+                            (int)c.patch_size));
+        LAUNCH_CHECK();
+        GemmArgs g = m->embed_gemm;
+        g.M = B * m->Np;
+        g.stats_out = stp;
+        DDB_TRY(launch_gemm2(g, EPI_RES, nsm, st));
+        CUDA_TRY(launch_pdl(token_extras_kernel, dim3(B), dim3(256), 0, st, t, reinterpret_cast<const long long*>(y),
+                            (const float*)m->pos->as<float>(),
+                            (const float*)(m->label_emb ? m->label_emb->as<float>() : nullptr),
+                            m->x0->as<__nv_bfloat16>(), stp, D, m->L, m->extras, (int)c.normalize_timesteps));
+        LAUNCH_CHECK();
+    } else {
+        // fp32 FMA path (single-CTA GEMM variant); writes one (mean, M2) per row
         ProfScope ps(PC_EMBED);
         const int grid = B * (c.img_size / c.patch_size);
         float2* emb_stats = ee ? nullptr : st2;
@@ -741,8 +789,6 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
 
     // LayerNorm statistics travel either as one (mean, M2) per row from ln_stats_kernel (kind 1) or as D/64
     // partials per row written by the producing CTA-pair GEMM's epilogue (kind 2).
-    float2* stp = m->stats_p->as<float2>();
-    const bool pair = (g_gemm_variant == 2);
     const int np_p = D / 64;
     int kind = 0;
     auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
@@ -756,7 +802,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         ProfScope ps(cat);
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
-    if (!ee) kind = 1;  // statistics of x0 were written by the token-assembly kernel
+    if (!ee) kind = (pair && m->Np == 256) ? 2 : 1;  // statistics of x0 were written by the token assembly
     if (cp) {
         ProfScope ps(PC_EE_OTHER);
         const int n = std::max(B, c.depth * B);

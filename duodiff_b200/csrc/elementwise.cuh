@@ -245,6 +245,99 @@ __global__ void __launch_bounds__(256, 2) embed_tokens_kernel(
 }
 
 // =====================================================================================================
+// Tensor-core patch embed (the model path): the per-patch linear runs on the CTA-pair tcgen05 GEMM.
+//   patch_gather_kernel  x_img fp32 -> A [B*256, 128] bf16: columns [0,64) = bf16(x) of the patch vector (c, p1, p2),
+//                        zero-padded; columns [64,128) = bf16(x - bf16(x)).  With W duplicated along K the GEMM
+//                        computes W_bf16 . (x_hi + x_lo): the input keeps ~16 mantissa bits, only the weights are bf16
+//                        like every other Linear of the path.
+//   token_extras_kernel  time / label token rows (+ pos_embed) and their 64-column LayerNorm partials.
+// The GEMM epilogue adds bias + pos_embed and writes the token rows and their LayerNorm partials (GemmArgs embed_mode).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ x_img,
+                                                           __nv_bfloat16* __restrict__ A, int B, int C, int H, int W,
+                                                           int P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    // one thread per (sample, channel, image row, patch column): P contiguous pixels
+    const int Wp = W / P;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * C * H * Wp) return;
+    const int ww = i % Wp;
+    size_t r = i / Wp;
+    const int yy = r % H;
+    r /= H;
+    const int c = r % C, b = r / C;
+    const int hh = yy / P, p1 = yy % P;
+    const float* src = x_img + (((size_t)b * C + c) * H + yy) * W + ww * P;
+    __nv_bfloat16* dst = A + ((size_t)b * (Wp * (H / P)) + hh * Wp + ww) * 128 + (c * P + p1) * P;
+    for (int p2 = 0; p2 < P; p2 += 2) {
+        const float2 v = *reinterpret_cast<const float2*>(src + p2);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x - __low2float(hi), v.y - __high2float(hi));
+        *reinterpret_cast<__nv_bfloat162*>(dst + p2) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(dst + 64 + p2) = lo;
+    }
+}
+
+// grid = B, 256 threads; D/64 LayerNorm partials per extras row (warp w handles chunks w, w+8, ...)
+__global__ void __launch_bounds__(256) token_extras_kernel(const float* __restrict__ tsteps,
+                                                           const long long* __restrict__ y,
+                                                           const float* __restrict__ pos,
+                                                           const float* __restrict__ label_emb,
+                                                           __nv_bfloat16* __restrict__ tokens,
+                                                           float2* __restrict__ stats_p, int D, int L, int extras,
+                                                           int normalize_t) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = D / 2;
+    float tau = tsteps[b];
+    if (normalize_t) tau = tau / 1000.f;
+    for (int row = 0; row < extras; ++row) {
+        const bool is_time = (row == extras - 1);
+        const float* src = is_time ? nullptr : label_emb + (size_t)y[b] * D;
+        for (int ch = warp; ch < D / 64; ch += 8) {
+            float v[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = ch * 64 + lane * 2 + u;
+                float x;
+                if (is_time) {
+                    // time token: [cos(tau f_i) | sin(tau f_i)], f_i = exp(-ln(1e4) i / half)
+                    const int i = (e < half) ? e : e - half;
+                    const float f = expf((-9.210340371976184f * (float)i) / (float)half);
+                    x = (e < half) ? cosf(tau * f) : sinf(tau * f);
+                } else {
+                    x = src[e];
+                }
+                v[u] = x + pos[(size_t)row * D + e];
+            }
+            const uint32_t pk = pack_bf16(v[0], v[1]);
+            *reinterpret_cast<uint32_t*>(tokens + ((size_t)b * L + row) * D + ch * 64 + lane * 2) = pk;
+            const float r0 = bf16_lo(pk), r1 = bf16_hi(pk);
+            float s = r0 + r1;
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * (1.f / 64.f);
+            float q = (r0 - mean) * (r0 - mean) + (r1 - mean) * (r1 - mean);
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            if (lane == 0 && stats_p) stats_p[((size_t)b * L + row) * (D / 64) + ch] = make_float2(mean, q);
+        }
+    }
+}
+
+// W_pe [D, pd] fp32 (conv weight flattened (c, p1, p2)) -> [D, 128] bf16: [W | 0 | W | 0]
+__global__ void pack_patch_embed_kernel(const float* __restrict__ W, int D, int pd, __nv_bfloat16* __restrict__ Wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D * 128) return;
+    const int e = i / 128, k = i % 128, kk = k & 63;
+    Wp[i] = __float2bfloat16_rn(kk < pd ? W[(size_t)e * pd + kk] : 0.f);
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// =====================================================================================================
 // LayerNorm row statistics (nn.LayerNorm, eps 1e-5; models/uvit.py:206-207,377) as (mean, M2) per row, and --
 // optionally -- the early-exit MLP probe's per-token sigmoid(w.x + b) (models/early_exit.py:34-37).
 // One warp per row, 16-byte loads, exact two-pass statistics in registers.

@@ -52,6 +52,10 @@ struct GemmArgs {
                         // 2 = MMA issue skipped (barrier traffic only), 4 = no TMA operand loads
     float2* stats_out;  // optional [M, N/64]: per-row (mean, M2) of every 64-column output chunk (gemm2 only)
     long long* trace;   // bench-only: cluster 0 / leader records clock64() per tile ([tile][16])
+    // Patch-embed mode (CTA-pair kernel): GEMM row r = (sample b = r / 256, patch l = r % 256).  The output goes to
+    // token row b*tok_L + tok_extras + l through a 3-D tensor map (tmOut: [B][256][N] view of the token buffer), the
+    // "residual" is the positional embedding of patch l (tmRes: [256, N], the same rows for every sample).
+    int embed_mode, tok_L, tok_extras;
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;

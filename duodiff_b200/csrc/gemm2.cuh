@@ -231,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             uint64_t* rb = &my_res[s % NBUF];
             mbar_expect_tx(rb, Cfg::OUT_BUF_BYTES);
             tma_load_2d(my_bufs + (s % NBUF) * Cfg::OUT_BUF_BYTES, &a.tmRes, rb, n_blk * BN + c * 64,
-                        m_blk * 256 + (int)rank * 128);
+                        (a.embed_mode ? 0 : m_blk * 256) + (int)rank * 128);
         };
         if (EPI == EPI_RES && et == 0 && traffic && !(a.debug & 1)) {
             for (uint32_t s = 0; s + 1 < NBUF; ++s) prefetch_res(s);
@@ -364,8 +364,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     f2_unpack(nshift, ns, ns_);
                     const float t1 = s1a + s1b, t2 = s2a + s2b;
                     const float dm = t1 * (1.f / 64.f);
-                    if (row < M)
-                        a.stats_out[(size_t)row * (a.N >> 6) + (col0 >> 6)] = make_float2(dm - ns, fmaf(-t1, dm, t2));
+                    if (row < M) {
+                        const size_t orow = a.embed_mode
+                                                ? (size_t)m_blk * a.tok_L + a.tok_extras + (int)rank * 128 + row_in_tile
+                                                : (size_t)row;
+                        a.stats_out[orow * (a.N >> 6) + (col0 >> 6)] = make_float2(dm - ns, fmaf(-t1, dm, t2));
+                    }
                 }
                 if (cc == CHUNKS_PER_WG - 1) {
                     __syncwarp();
@@ -374,7 +378,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (et == 0 && traffic) {
-                    tma_store_2d(&a.tmOut, sbuf, col0, row0);
+                    if (a.embed_mode)
+                        tma_store_3d(&a.tmOut, sbuf, col0, (int)rank * 128, m_blk);  // sample m_blk, patches rank*128..
+                    else
+                        tma_store_2d(&a.tmOut, sbuf, col0, row0);
                     tma_store_commit();
                     if constexpr (EPI == EPI_RES) {
                         // buffer (q + NBUF - 1) % NBUF was last used by chunk q-1: wait until its store has read it,
