@@ -56,6 +56,8 @@ struct AttRowState {
 // One block of up to 64 keys: S = Q K^T, online softmax, O += P V.  sK/sV: swizzled [key][64] bf16 tiles (shared
 // addresses) indexed by absolute key; keys >= kend are masked.  nt = number of 8-key n-tiles in the block (V must be
 // readable for an even number of them).
+// TOP_ONLY: rows g+8 of the block are padding (all-zero queries): their softmax math is skipped.
+template <bool TOP_ONLY = false>
 __device__ __forceinline__ void att_mma_block(uint32_t sK_u, uint32_t sV_u, int kb0, int nt, int kend,
                                               const uint32_t (&qf)[4][4], AttRowState& st, float scale_log2e,
                                               int lane) {
@@ -85,15 +87,18 @@ __device__ __forceinline__ void att_mma_block(uint32_t sK_u, uint32_t sV_u, int 
             if (key >= kend) s[j][0] = s[j][2] = -INFINITY;
             if (key + 1 >= kend) s[j][1] = s[j][3] = -INFINITY;
             bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
-            bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
+            if (!TOP_ONLY) bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
         }
     }
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float nm0 = fmaxf(st.m0, bm0), nm1 = fmaxf(st.m1, bm1);  // finite: every block has a valid key
-    const float corr0 = exp2f((st.m0 - nm0) * scale_log2e), corr1 = exp2f((st.m1 - nm1) * scale_log2e);
+    if (!TOP_ONLY) {
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    }
+    const float nm0 = fmaxf(st.m0, bm0), nm1 = TOP_ONLY ? 0.f : fmaxf(st.m1, bm1);  // finite: a valid key per block
+    const float corr0 = exp2f((st.m0 - nm0) * scale_log2e);
+    const float corr1 = TOP_ONLY ? 1.f : exp2f((st.m1 - nm1) * scale_log2e);
     st.m0 = nm0, st.m1 = nm1;
     const float ms0 = nm0 * scale_log2e, ms1 = nm1 * scale_log2e;
     float ps0 = 0.f, ps1 = 0.f;
@@ -103,22 +108,26 @@ __device__ __forceinline__ void att_mma_block(uint32_t sK_u, uint32_t sV_u, int 
         if (j < nt) {
             const float p0 = exp2f(fmaf(s[j][0], scale_log2e, -ms0));
             const float p1 = exp2f(fmaf(s[j][1], scale_log2e, -ms0));
-            const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -ms1));
-            const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -ms1));
             ps0 += p0 + p1;
-            ps1 += p2 + p3;
             pf[j][0] = pack_bf16(p0, p1);
-            pf[j][1] = pack_bf16(p2, p3);
+            if (!TOP_ONLY) {
+                const float p2 = exp2f(fmaf(s[j][2], scale_log2e, -ms1));
+                const float p3 = exp2f(fmaf(s[j][3], scale_log2e, -ms1));
+                ps1 += p2 + p3;
+                pf[j][1] = pack_bf16(p2, p3);
+            } else {
+                pf[j][1] = 0u;
+            }
         } else {
             pf[j][0] = pf[j][1] = 0u;
         }
     }
     st.l0 = st.l0 * corr0 + ps0;
-    st.l1 = st.l1 * corr1 + ps1;
+    if (!TOP_ONLY) st.l1 = st.l1 * corr1 + ps1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         st.o[i][0] *= corr0, st.o[i][1] *= corr0;
-        st.o[i][2] *= corr1, st.o[i][3] *= corr1;
+        if (!TOP_ONLY) st.o[i][2] *= corr1, st.o[i][3] *= corr1;
     }
     // O += P V  (k-steps of 16 keys)
 #pragma unroll
@@ -403,11 +412,12 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             rs.init();
             mbar_wait(&v_full[s], (it >> 1) & 1);
             // extras keys: the first 8 tokens of the X tile, of which [0, extras) are valid
-            att_mma_block(smem_u32(st + ATT3_OFF_KX), smem_u32(st + ATT3_OFF_VX), 0, 1, a.extras, qf, rs, a.scale_log2e,
-                          lane);
+            att_mma_block<true>(smem_u32(st + ATT3_OFF_KX), smem_u32(st + ATT3_OFF_VX), 0, 1, a.extras, qf, rs,
+                                a.scale_log2e, lane);
             const uint32_t sK_u = smem_u32(st + ATT3_OFF_K), sV_u = smem_u32(st + ATT3_OFF_V);
 #pragma unroll 1
-            for (int kb0 = 0; kb0 < 256; kb0 += 64) att_mma_block(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
+            for (int kb0 = 0; kb0 < 256; kb0 += 64)
+                att_mma_block<true>(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(&stage_empty[s]);  // this warp no longer reads the stage
             float l0 = rs.l0;
