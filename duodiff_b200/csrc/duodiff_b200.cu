@@ -226,6 +226,7 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     }
     const int tiles = ((a.M + 255) / 256) * (a.N / BN);
     if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
+    const_cast<GemmArgs&>(a).trace = g_gemm_trace;
     int clusters = num_sms / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return DDB_OK;

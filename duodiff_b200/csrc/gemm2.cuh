@@ -156,12 +156,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
+                long long* tr = (a.trace && cluster_id == 0 && it < 16) ? a.trace + it * 16 : nullptr;  // bench-only
+                if (tr) tr[0] = clock64();
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
+                if (tr) tr[1] = clock64();
                 const uint32_t d_tmem = tmem_base + as * BN;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (tr && kb == 0) tr[2] = clock64();
                     const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
                     const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
                     if (!(a.debug & 2)) {
@@ -176,6 +180,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     }
                 }
                 umma_commit_2cta(&tfull_bar[as], 0x3);
+                if (tr) tr[3] = clock64();
             }
         }
     } else if (warp >= kAllocWarp) {
@@ -248,7 +253,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             const float* sbias = reinterpret_cast<const float*>(ab + (kLN ? 1024 : 0));
             const float* scs = reinterpret_cast<const float*>(ab + 2048);
 
+            long long* tr = (a.trace && cluster_id == 0 && leader && threadIdx.x == 0 && it < 16) ? a.trace + it * 16
+                                                                                                   : nullptr;
+            if (tr) tr[4] = clock64();
             mbar_wait(&aux_full[as], aph);
+            if (tr) tr[5] = clock64();
             float rstd = 1.f, mean_rstd = 0.f;
             if constexpr (kLN) {
                 const float2 rs = reinterpret_cast<const float2*>(ab)[row_in_tile];
@@ -256,6 +265,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             }
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
+            if (tr) tr[6] = clock64();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
 
             if (a.debug & 1) {
@@ -289,6 +299,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     named_bar_sync(bar_id, 128);
                 }
                 tmem_ld_wait();
+                if (tr && cc < 2) tr[7 + cc * 4] = clock64();
                 if (cc == CHUNKS_PER_WG - 1) {
                     tc_fence_before();
                     __syncwarp();
@@ -375,8 +386,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&aux_empty[as]);  // this warp is done with the tile's smem vectors
                 }
+                if (tr && cc < 2) tr[8 + cc * 4] = clock64();
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
+                if (tr && cc < 2) tr[9 + cc * 4] = clock64();
                 if (et == 0 && traffic) {
                     if (a.embed_mode)
                         tma_store_3d(&a.tmOut, sbuf, col0, (int)rank * 128, m_blk);  // sample m_blk, patches rank*128..
@@ -390,6 +403,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                         prefetch_res(q + NBUF - 1);
                     }
                 }
+                if (tr && cc < 2) tr[10 + cc * 4] = clock64();
                 ++q;
             }
         }

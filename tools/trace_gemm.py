@@ -30,16 +30,9 @@ torch.cuda.synchronize()
 _lib.check(L.ddb_debug_set_ptr(b"gemm_trace", None))
 tc = tr.cpu(); t = tc[:256].view(16, 16); t0 = int(t[0, 0])
 print(f"{a.shape} debug={a.debug}: cycles relative to the MMA thread's first stamp")
-print("tile | MMA: start  tempty_ok  first_full  issued(all) | EPI(wg0,warp0): start aux_ok tfull_ok ld_done | h0: buf_ok math_done bar_done -- | h1: buf_ok math_done bar_done --")
+print("tile | MMA: start  tempty_ok  first_full  issued(all) | EPI(wg0,warp0): start aux_ok tfull_ok | c0: ld_done math_done bar_done store_issued | c1: ld_done math_done bar_done store_issued")
 for i in range(16):
     v = [int(x) - t0 if int(x) else -1 for x in t[i]]
     if v[0] < 0 and i > 0: break
     print(f"{i:4d} | {v[0]:8d} {v[1]:8d} {v[2]:8d} {v[3]:8d} | {v[4]:8d} {v[5]:8d} {v[6]:8d} | {v[7]:8d} {v[8]:8d} {v[9]:8d} {v[10]:8d} | {v[11]:8d} {v[12]:8d} {v[13]:8d} {v[14]:8d}")
-
-g = tc[256:].view(74, 4)
-g0 = int(g[:, 0].min())
-rows = [(int(g[c, 0]) - g0, int(g[c, 1]) - g0, int(g[c, 2]) - g0) for c in range(74)]
-print("per-cluster globaltimer ns (start, last-epilogue-done, stores-drained):")
-print(" ".join(f"{c}:{r[0]}/{r[1]}/{r[2]}" for c, r in enumerate(rows)))
-print("max end", max(r[2] for r in rows), "min end", min(r[2] for r in rows), "max start", max(r[0] for r in rows))
 
