@@ -9,7 +9,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libduodiff_b200.so"
 SOURCES = ["duodiff_b200.cu"]
-HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "attention.cuh", "elementwise.cuh"]
+HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "gemm3.cuh", "attention.cuh", "elementwise.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -19,6 +19,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
+#include "gemm3.cuh"
 
 using namespace ddb;
 
@@ -234,6 +235,29 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     LAUNCH_CHECK();
     return DDB_OK;
 }
+// CTA-pair GEMM with the A panel resident in TMEM (gemm3.cuh): K <= 512, one K source, 32-column SWIZZLE_64B output maps
+static int g_gemm_ts = 0;  // ddb_set_option "gemm_ts": measured no faster than gemm2 (the MMA takes ~165 clk in SS and TS form alike)
+template <int EPI, bool STATS>
+static int launch_gemm3_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
+    constexpr int kSmem = Gemm3Cfg<8, kLN>::SMEM_BYTES;
+    auto kfn = gemm3_tcgen05_kernel<EPI, STATS, 8>;
+    if (!configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        configured = true;
+    }
+    const int tiles = ((a.M + 255) / 256) * (a.N / 256);
+    if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
+    const_cast<GemmArgs&>(a).trace = g_gemm_trace;
+    int clusters = num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (clusters <= 0) return DDB_OK;
+    CUDA_TRY(launch_pdl(kfn, dim3(2 * clusters), dim3(G3_THREADS), kSmem, st, a));
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
 // CTA-pair GEMM: a.tmB2 must have been encoded with a 128-row box.  Pipeline shape per epilogue:
 //   LN / LN+GELU (K = embed_dim, epilogue-heavy): 4 operand stages, aux-staged row statistics + bias + colsum
 //   residual, K <= 512 (proj: epilogue-latency-bound): 4 stages, 3 staging buffers (residual prefetched 2 chunks ahead)
@@ -241,6 +265,16 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     const bool stats = a.stats_out != nullptr;
     const bool short_k = (a.K0 + a.K1) <= 512;
+    if (g_gemm_ts && short_k && a.K1 == 0 && !a.embed_mode) {
+        switch (epi) {
+            case EPI_LN: return launch_gemm3_t<EPI_LN, false>(a, num_sms, st);
+            case EPI_LN_GELU: return launch_gemm3_t<EPI_LN_GELU, false>(a, num_sms, st);
+            case EPI_RES:
+                return stats ? launch_gemm3_t<EPI_RES, true>(a, num_sms, st)
+                             : launch_gemm3_t<EPI_RES, false>(a, num_sms, st);
+            default: break;
+        }
+    }
     // Wave quantisation: with 256x256 tiles an N = 512 GEMM at M = 32 896 has 258 tiles for 74 CTA pairs (3.49 -> 4
     // rounds); 256x128 tiles give 516 (6.97 -> 7 half-size rounds).  Used whenever it removes at least 5 % of the
     // rounds' work.
@@ -1002,6 +1036,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "gemm_debug")) {
         g_gemm_debug = value;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "gemm_ts")) {
+        g_gemm_ts = value != 0;
         return DDB_OK;
     }
     if (!strcmp(name, "gemm_bn128")) {
