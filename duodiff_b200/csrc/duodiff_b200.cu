@@ -973,7 +973,8 @@ struct ddb_sampler {
     int switch_t = -1, B = 0, step_mode = 0, ee_mode = 0;
     float ee_threshold = -1.f;
     size_t n = 0;
-    Buf coef, t_dev, t_vec, eps, score_mean, x_buf, seed_dev;
+    Buf coef, t_dev, t_vec, eps, score_mean, x_buf, seed_dev, next_t;
+    std::vector<int> next_host, next_uploaded;  // successor table: staging / what the device currently holds
     // One captured step per backbone.  The graph works on the sampler-owned x_buf and reads t and the Philox seed
     // from device memory, so it is captured once and replayed for every call / seed / caller buffer.
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
@@ -1016,7 +1017,7 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y
                         (const float*)eps, z_all, s->n, s->n, (const float*)s->coef->as<float>(),
                         (const int*)s->t_dev->as<int>(), 0, s->step_mode, seed, seed_dev, x_save));
     LAUNCH_CHECK();
-    dec_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>());
+    next_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>(), s->next_t->as<int>());
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -1146,6 +1147,8 @@ int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int3
     DDB_TRY(new_buf(s->eps, s->n * 4));
     DDB_TRY(new_buf(s->x_buf, s->n * 4));
     DDB_TRY(new_buf(s->seed_dev, 8));
+    DDB_TRY(new_buf(s->next_t, 1000 * 4));
+    s->next_host.assign(1000, 0);
     *out = s.release();
     return DDB_OK;
 }
@@ -1157,20 +1160,31 @@ void ddb_sampler_destroy(ddb_sampler* s) {
     delete s;
 }
 
-int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
-                    int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
-                    int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream) {
-    if (!s || !x_dev) return fail(DDB_ERR_INVALID, "null argument");
-    if (t_first > 999 || t_last < 0 || t_last > t_first) return fail(DDB_ERR_INVALID, "bad step range");
-    cudaStream_t st = (cudaStream_t)stream;
+// Runs the model at the timesteps t_list[0..n) (late[k] != 0: on the late backbone) with the sampler's update rule.
+static int sampler_run_impl(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                            const int32_t* t_list, const uint8_t* late, int n, float* eps_trace_dev, float* x_trace_dev,
+                            int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph,
+                            cudaStream_t st) {
+    if (n <= 0) return DDB_OK;
+    for (int k = 0; k < n; ++k) {
+        if (t_list[k] < 0 || t_list[k] > 999) return fail(DDB_ERR_INVALID, "timestep %d outside [0, 999]", t_list[k]);
+        if (late[k] && !s->late) return fail(DDB_ERR_INVALID, "step %d asks for the late model but none was given", k);
+    }
     if (use_graph && (eps_trace_dev || x_trace_dev))
         return fail(DDB_ERR_INVALID, "per-step eps/x traces need use_graph=0");
-    set_t_kernel<<<1, 1, 0, st>>>(s->t_dev->as<int>(), t_first);
+    // the timestep sequence as a device-side successor table, so that a captured step needs no host argument
+    for (int k = 0; k < n; ++k) s->next_host[t_list[k]] = (k + 1 < n) ? t_list[k + 1] : t_list[k];
+    if (s->next_host != s->next_uploaded) {  // unchanged for repeated runs of the same schedule: no host sync
+        CUDA_TRY(cudaMemcpyAsync(s->next_t->p, s->next_host.data(), 1000 * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s->next_uploaded = s->next_host;
+    }
+    set_t_kernel<<<1, 1, 0, st>>>(s->t_dev->as<int>(), t_list[0]);
     LAUNCH_CHECK();
     if (!use_graph) {
-        for (int t = t_first, k = 0; t >= t_last; --t, ++k) {
-            ddb_model* m = (s->late && t < s->switch_t) ? s->late : s->early;
-            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, nullptr, t,
+        for (int k = 0; k < n; ++k) {
+            ddb_model* m = late[k] ? s->late : s->early;
+            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, nullptr, t_list[k],
                                  eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
                                  x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr,
                                  exit_idx_trace_dev, score_mean_trace_dev, st));
@@ -1220,13 +1234,36 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
             memcpy(s->graph_key[which], key, sizeof(key));
         }
     }
-    for (int t = t_first; t >= t_last; --t) {
-        const int which = (s->late && t < s->switch_t) ? 1 : 0;
+    for (int k = 0; k < n; ++k) {
+        const int which = late[k] ? 1 : 0;
         CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
         g_launches.fetch_add(s->graph_nodes[which], std::memory_order_relaxed);
     }
     CUDA_TRY(cudaMemcpyAsync(x_dev, xb, s->n * 4, cudaMemcpyDeviceToDevice, st));
     return DDB_OK;
+}
+
+int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                    int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
+                    int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream) {
+    if (!s || !x_dev) return fail(DDB_ERR_INVALID, "null argument");
+    if (t_first > 999 || t_last < 0 || t_last > t_first) return fail(DDB_ERR_INVALID, "bad step range");
+    std::vector<int32_t> ts;
+    std::vector<uint8_t> late;
+    for (int t = t_first; t >= t_last; --t) {
+        ts.push_back(t);
+        late.push_back((s->late && t < s->switch_t) ? 1 : 0);  // sampler.py:135-136
+    }
+    return sampler_run_impl(s, x_dev, y_dev, z_all_dev, seed, ts.data(), late.data(), (int)ts.size(), eps_trace_dev,
+                            x_trace_dev, exit_idx_trace_dev, score_mean_trace_dev, use_graph, (cudaStream_t)stream);
+}
+
+int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                         const int32_t* t_list_host, const uint8_t* late_host, int32_t n_steps, float* eps_trace_dev,
+                         float* x_trace_dev, int32_t use_graph, void* stream) {
+    if (!s || !x_dev || !t_list_host || !late_host) return fail(DDB_ERR_INVALID, "null argument");
+    return sampler_run_impl(s, x_dev, y_dev, z_all_dev, seed, t_list_host, late_host, n_steps, eps_trace_dev,
+                            x_trace_dev, nullptr, nullptr, use_graph, (cudaStream_t)stream);
 }
 
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {

@@ -465,8 +465,9 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 //   x' = ca[t]*x + cb[t]*model_out + cs[t]*z        (z ~ N(0,I), absent at t == 0)
 // The three per-timestep coefficients are tabulated on the host with the reference's own torch expressions:
 //   predict_noise:    x' = sqrt(1/a)*(x - ((1-a)/sqrt(1-abar))*eps) + sigma*z is evaluated in that exact order
-//   (mode 0) to stay within 1 ulp of the reference; mode 1 uses the generic two-term form for the other rules.
-// coef layout: [1000][4] = {c0, c1, sigma, unused}
+//   (mode 0) to stay within 1 ulp of the reference; mode 1 uses the generic two-term form for the other rules;
+//   mode 2 is the DDIM update (sampler.py:112-120) with a fourth coefficient d.
+// coef layout: [1000][4] = {c0, c1, sigma, d}
 // Noise: injected tensor z_all[t] (parity) or Philox4x32-10 + Box-Muller keyed by (seed, t, element).
 // =====================================================================================================
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
@@ -524,6 +525,13 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
         o.y = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.y, __fmul_rn(c1, ev.y))), __fmul_rn(sg, zv.y));
         o.z = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.z, __fmul_rn(c1, ev.z))), __fmul_rn(sg, zv.z));
         o.w = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.w, __fmul_rn(c1, ev.w))), __fmul_rn(sg, zv.w));
+    } else if (mode == 2) {
+        // DDIM (sampler.py:112-120): mean = c0*(x - c1*eps); mean += d*eps; x' = mean + sigma2*z, in that order
+        const float d = coef[t * 4 + 3];
+        o.x = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.x, __fmul_rn(c1, ev.x))), __fmul_rn(d, ev.x)), __fmul_rn(sg, zv.x));
+        o.y = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.y, __fmul_rn(c1, ev.y))), __fmul_rn(d, ev.y)), __fmul_rn(sg, zv.y));
+        o.z = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.z, __fmul_rn(c1, ev.z))), __fmul_rn(d, ev.z)), __fmul_rn(sg, zv.z));
+        o.w = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.w, __fmul_rn(c1, ev.w))), __fmul_rn(d, ev.w)), __fmul_rn(sg, zv.w));
     } else {
         // (c1*out + c0*x) + sigma*z   -- predict_original (sampler.py:69-72) / predict_previous (c0=0, c1=1)
         o.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.x), __fmul_rn(c0, xv.x)), __fmul_rn(sg, zv.x));
@@ -541,8 +549,9 @@ __global__ void fill_t_kernel(const int* __restrict__ t_dev, float* __restrict__
     if (i < B) t_vec[i] = (float)(*t_dev);
 }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
-__global__ void dec_t_kernel(int* t_dev) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev -= 1;
+// t <- next_t[t]: the timestep sequence of the run (t-1 for DDPM, the strided DDIM schedule, ...) lives in a table
+__global__ void next_t_kernel(int* t_dev, const int* __restrict__ next_t) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev = next_t[*t_dev];
 }
 
 // samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146)

@@ -8,7 +8,35 @@ import torch
 from . import _lib
 from .engine import Engine
 
+import numpy as np
+
 RULES = ("predict_noise", "predict_original", "predict_previous")
+
+
+def ddim_timesteps(ddim_steps: int) -> list:
+    """sampler.py:104 — np.linspace(0, 999, ddim_steps).astype(int)[::-1]."""
+    ts = [int(v) for v in np.linspace(0, 999, ddim_steps).astype(int)[::-1]]
+    if any(s >= t for t, s in zip(ts[:-1], ts[1:])):
+        raise ValueError(f"ddim_steps={ddim_steps}: the strided schedule must be strictly decreasing (sampler.py:106)")
+    return ts
+
+
+def ddim_coefficients(ddim_steps: int, ddim_eta: float):
+    """[1000,4] fp32 table {c0, c1, sigma2, d} for the DDIM update (sampler.py:110-120), mode 2 of the step kernel:
+        x' = (c0*(x - c1*eps) + d*eps) + sigma2*z,   c0 = sqrt(abar_s/abar_t), c1 = sqrt(1-abar_t),
+        d = sqrt(1 - abar_s - sigma2), sigma2 = betas_tilde[t]*eta (the reference adds sigma_t^2 * z), z = 0 if s == 0.
+    Rows of timesteps the schedule does not visit stay zero."""
+    sch = schedule()
+    ab, bt = sch["alphas_bar"], sch["betas_tilde"]
+    table = torch.zeros(1000, 4, dtype=torch.float32)
+    ts = ddim_timesteps(ddim_steps)
+    for t, s in zip(ts[:-1], ts[1:]):
+        sigma2 = bt[t] * ddim_eta
+        table[t, 0] = torch.sqrt(ab[s] / ab[t])
+        table[t, 1] = torch.sqrt(1 - ab[t])
+        table[t, 2] = sigma2 if s > 0 else 0.0
+        table[t, 3] = torch.sqrt(1 - ab[s] - sigma2)
+    return table.contiguous(), 2
 
 
 def schedule() -> dict:
@@ -87,7 +115,10 @@ class Sampler:
                  variance: str = "beta_tilde", ee_threshold: float | None = None, ee_mode: int = 0):
         self.lib = _lib.load()
         self.early, self.late, self.batch = early, late, batch
-        table, mode = step_coefficients(rule, variance)
+        if isinstance(rule, tuple) and rule[0] == "ddim":  # ("ddim", ddim_steps, ddim_eta)
+            table, mode = ddim_coefficients(int(rule[1]), float(rule[2]))
+        else:
+            table, mode = step_coefficients(rule, variance)
         self.coef = table
         handle = C.c_void_p()
         _lib.check(self.lib.ddb_sampler_create(
@@ -116,6 +147,26 @@ class Sampler:
             self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), t_first, t_last,
             _lib.ptr(eps_trace), _lib.ptr(x_trace), _lib.ptr(exit_log), _lib.ptr(score_log), int(graph),
             _lib.current_stream_ptr()))
+        return x
+
+    def run_list(self, x, t_list, late_flags, y=None, noise=None, seed: int = 0, eps_trace=None, x_trace=None,
+                 use_graph: bool = True):
+        """The same loop over an explicit timestep list (DDIM): model at t_list[k] (late backbone if late_flags[k]),
+        then the sampler's update with the coefficients of t_list[k]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.batch
+        n = len(t_list)
+        assert n == len(late_flags)
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
+            assert noise.shape[0] == 1000 and noise[0].numel() == x.numel()
+        if y is not None:
+            y = y.to(device=x.device, dtype=torch.int64).contiguous()
+        ts = (C.c_int32 * n)(*[int(t) for t in t_list])
+        lf = (C.c_uint8 * n)(*[1 if f else 0 for f in late_flags])
+        graph = bool(use_graph) and eps_trace is None and x_trace is None
+        _lib.check(self.lib.ddb_sampler_run_list(
+            self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), ts, lf, n,
+            _lib.ptr(eps_trace), _lib.ptr(x_trace), int(graph), _lib.current_stream_ptr()))
         return x
 
     def finalize(self, x):

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _io
-from .ddpm import RULES, cached_sampler
+from .ddpm import RULES, cached_sampler, ddim_timesteps
 from .uvit import UViT
 
 
@@ -51,6 +51,18 @@ def _rule_name(postprocessing) -> str:
     raise ValueError(f"unsupported postprocessing {postprocessing!r}; expected one of {RULES}")
 
 
+def _ddim_plan(ddim_steps: int, late_available: bool, t_switch):
+    """(timesteps, late flags) of the DDIM loop, sampler.py:103-123: pairs (t, s) of the strided schedule; the
+    hand-off `if t < 1000 - t_switch: model = late_model` happens AFTER the step at t."""
+    ts = ddim_timesteps(ddim_steps)
+    steps, flags, on_late = ts[:-1], [], False
+    for t in steps:
+        flags.append(on_late)
+        if late_available and t < 1000 - t_switch:
+            on_late = True
+    return steps, flags
+
+
 def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels: int, sample_height: int,
                 sample_width: int, use_ddim: bool = False, ddim_steps: int = 50, ddim_eta: float = 0.0,
                 timesteps_save: List[int] = (), y=None, autoencoder=None, late_model=None, t_switch=np.inf, *,
@@ -58,10 +70,9 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
     """sampler.py:82-155.  Returns (samples [B,H,W,C] f32 numpy un-clipped, [intermediate samples]).
 
     x_T is drawn on the CPU generator after ``seed_everything(seed)`` exactly like the reference (sampler.py:99-100);
-    the per-step z comes from an in-kernel Philox stream keyed by ``seed`` unless ``noise`` [1000,B,C,H,W] is
-    injected (parity tests).  DDIM and the KL autoencoder are later rows of SURVEY.md §8(f)."""
-    if use_ddim:
-        raise NotImplementedError("the DDIM branch (sampler.py:103-126) is a 'next' row, not built yet")
+    the per-step z comes from an in-kernel Philox stream keyed by ``seed`` unless ``noise`` [1000,B,C,H,W] (indexed
+    by t) is injected (parity tests).  ``use_ddim`` runs the strided DDIM branch (sampler.py:103-126, including the
+    reference's sigma_t^2 * z noise term).  The KL autoencoder is a later row of SURVEY.md §8(f)."""
     if autoencoder is not None:
         raise NotImplementedError("KL-autoencoder decode (sampler.py:141-143) is a 'next' row, not built yet")
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -71,25 +82,38 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
     with torch.cuda.device(dev):
         early = model.engine(batch_size)
         late = late_model.engine(batch_size) if late_model is not None else None
-        sampler = cached_sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
         if noise is not None:
             noise = noise.to(device=dev, dtype=torch.float32).contiguous()
-        # reference: `if 1000 - t in timesteps_save` after the update at t -> save x after step t = 1000 - s
-        save_at = sorted({1000 - int(s) for s in timesteps_save if 0 <= 1000 - int(s) <= 999}, reverse=True)
-        kept, t_first = {}, 999
-        for t_stop in save_at + [0]:
-            if t_stop > t_first:
-                continue
-            sampler.run(x, y=y, noise=noise, seed=seed, t_first=t_first, t_last=t_stop, use_graph=use_graph)
-            if t_stop in save_at:
-                kept[t_stop] = sampler.finalize(x)
-            t_first = t_stop - 1
-            if t_first < 0:
-                break
+        # reference: `if 1000 - t in timesteps_save` after the update at t -> save x after the step at t = 1000 - s
+        save_at = {1000 - int(s) for s in timesteps_save}
+        kept = []
+        if use_ddim:
+            sampler = cached_sampler(early, late, t_switch, batch_size, rule=("ddim", int(ddim_steps), float(ddim_eta)))
+            steps, flags = _ddim_plan(int(ddim_steps), late is not None, t_switch)
+            k0 = 0
+            for k, t in enumerate(steps):
+                if t in save_at or k == len(steps) - 1:
+                    sampler.run_list(x, steps[k0:k + 1], flags[k0:k + 1], y=y, noise=noise, seed=seed,
+                                     use_graph=use_graph)
+                    if t in save_at:
+                        kept.append(sampler.finalize(x))
+                    k0 = k + 1
+        else:
+            sampler = cached_sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
+            t_first = 999
+            for t_stop in sorted((t for t in save_at if 0 <= t <= 999), reverse=True) + [0]:
+                if t_stop > t_first:
+                    continue
+                sampler.run(x, y=y, noise=noise, seed=seed, t_first=t_first, t_last=t_stop, use_graph=use_graph)
+                if t_stop in save_at:
+                    kept.append(sampler.finalize(x))
+                t_first = t_stop - 1
+                if t_first < 0:
+                    break
         samples = sampler.finalize(x)
         out = samples.cpu().numpy()
         # the reference appends in loop order (descending t), one entry per matching step
-        inter = [kept[t].cpu().numpy() for t in sorted(kept, reverse=True)]
+        inter = [k.cpu().numpy() for k in kept]
     return out, inter
 
 

@@ -91,8 +91,9 @@ int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const i
                    float* outputs_dev, void* stream);
 
 /* One DDPM update (sampler.py:47-79 / eesampler.py:74-82 / ddpm_core.py:190-193), in place on x_dev.
- *   coef_dev [1000,4] f32 per-timestep {c0, c1, sigma, 0}; mode 0: c0*(x - c1*out) + sigma*z (predict_noise),
- *   mode 1: (c1*out + c0*x) + sigma*z (predict_original / predict_previous).
+ *   coef_dev [1000,4] f32 per-timestep {c0, c1, sigma, d}; mode 0: c0*(x - c1*out) + sigma*z (predict_noise),
+ *   mode 1: (c1*out + c0*x) + sigma*z (predict_original / predict_previous),
+ *   mode 2: (c0*(x - c1*out) + d*out) + sigma*z (DDIM, sampler.py:112-120; sigma holds the reference's sigma_t^2).
  *   z_dev: this step's noise [n] or NULL (Philox from `seed`); ignored at t == 0 (z = 0). */
 int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, const float* coef_dev, int32_t t,
                   int32_t mode, uint64_t seed, int64_t n, void* stream);
@@ -113,6 +114,12 @@ void ddb_sampler_destroy(ddb_sampler* s);
 int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
                     int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
                     int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream);
+/* Same loop over an explicit list of timesteps (host arrays of n_steps entries): the model runs at t_list[k] on the
+ * late backbone when late[k] != 0, then the sampler's update rule is applied with the coefficients of t_list[k].
+ * Used for the DDIM branch (sampler.py:103-126: strided schedule, hand-off `t < 1000 - t_switch` after the step). */
+int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
+                         const int32_t* t_list_host, const uint8_t* late_host, int32_t n_steps, float* eps_trace_dev,
+                         float* x_trace_dev, int32_t use_graph, void* stream);
 /* samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146). */
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 /* Runtime switches for A/B measurements: "gemm_variant" = 2 (CTA-pair kernel, default) or 1 (single-CTA kernel). */

@@ -258,6 +258,46 @@ def sample_ddpm(early, late, t_switch, x_T: torch.Tensor, noise, y=None, rule: s
     return x
 
 
+def ddim_timesteps(ddim_steps: int):
+    """sampler.py:104 — np.linspace(0, 999, ddim_steps).astype(int)[::-1] as a list of python ints."""
+    import numpy as np
+    return [int(v) for v in np.linspace(0, 999, ddim_steps).astype(int)[::-1]]
+
+
+def ddim_step(sch: dict, model_output, x, t: int, s: int, eta: float, z):
+    """sampler.py:112-120 (with the reference's quirk: the noise term is sigma_t^2 * z, not sigma_t * z)."""
+    ab = sch["alphas_bar"]
+    sigma_t_squared = sch["betas_tilde"][t] * eta
+    mean = torch.sqrt(ab[s] / ab[t]) * (x - torch.sqrt(1 - ab[t]) * model_output)
+    mean = mean + torch.sqrt(1 - ab[s] - sigma_t_squared) * model_output
+    return mean + sigma_t_squared * z if z is not None else mean
+
+
+def sample_ddim(early, late, t_switch, x_T: torch.Tensor, noise, ddim_steps: int, eta: float, y=None,
+                trace: dict | None = None, n_pairs: int | None = None) -> torch.Tensor:
+    """sampler.py:103-126 — the DDIM branch: strided timesteps, z = 0 for the last pair (s == 0), and the hand-off
+    `if t < 1000 - t_switch: model = late_model` AFTER the step at t (so the first step below the boundary still runs
+    on the early model).  `noise` as in sample_ddpm (indexed by t).  n_pairs truncates the loop (tests)."""
+    sch = ddpm_schedule(x_T.device)
+    ts = ddim_timesteps(ddim_steps)
+    x, model = x_T, early
+    pairs = list(zip(ts[:-1], ts[1:]))
+    for t, s in pairs[:n_pairs]:
+        time_tensor = t * torch.ones(x.shape[0], device=x.device)
+        with torch.no_grad():
+            out = model(x, time_tensor, y)
+        z = None
+        if s > 0:
+            z = noise(t) if callable(noise) else noise[t]
+        if trace is not None:
+            trace.setdefault("t", []).append(t)
+            trace.setdefault("late", []).append(model is late)
+        x = ddim_step(sch, out, x, t, s, eta, z)
+        if late is not None and t < 1000 - t_switch:
+            model = late
+    return x
+
+
 def to_samples_nhwc(x: torch.Tensor) -> torch.Tensor:
     """sampler.py:145-146 — (x + 1) / 2, 'b c h w -> b h w c' (un-clipped)."""
     return ((x + 1) / 2).permute(0, 2, 3, 1).contiguous()

@@ -131,6 +131,36 @@ def duodiff_sampler_fixture():
     np.savez_compressed(OUT / "duodiff_sampler_tiny.npz", **fx)
 
 
+def ddim_sampler_fixture():
+    """Unmodified sampler.get_samples(use_ddim=True): strided steps, eta 0 and 0.5, hand-off at t_switch=300."""
+    torch.manual_seed(21)
+    early = UViT(**TINY).eval()
+    late = UViT(**TINY_FULL).eval()
+    heat(early, 22)
+    heat(late, 23)
+    calls = {"early": [], "late": []}
+    early.register_forward_hook(lambda _m, i, _o: calls["early"].append(int(i[1][0])))
+    late.register_forward_hook(lambda _m, i, _o: calls["late"].append(int(i[1][0])))
+    fx = dict(**params_np(TINY), **{f"q::{k}": np.asarray(v) for k, v in TINY_FULL.items()}, **sd_np(early, "we::"),
+              **sd_np(late, "wl::"))
+    # (eta large enough makes sqrt(1 - abar_s - sigma^2) NaN near s = 0 in the reference: 20 steps, eta 0.5 -> NaN images)
+    for steps, eta in ((50, 0.0), (20, 0.05)):
+        calls["early"].clear(), calls["late"].clear()
+        samples, inter = ref_sampler.get_samples(
+            model=early, batch_size=2, postprocessing=ref_sampler.predict_noise_postprocessing, seed=7,
+            num_channels=3, sample_height=8, sample_width=8, use_ddim=True, ddim_steps=steps, ddim_eta=eta,
+            timesteps_save=[1, 1000 - int(np.linspace(0, 999, steps).astype(int)[::-1][3])], y=None, autoencoder=None,
+            late_model=late, t_switch=300)
+        key = f"{steps}_{eta}"
+        fx[f"samples_{key}"] = samples
+        for i, s in enumerate(inter):
+            fx[f"inter_{key}_{i}"] = s
+        fx[f"early_ts_{key}"] = np.asarray(calls["early"])
+        fx[f"late_ts_{key}"] = np.asarray(calls["late"])
+        print("ddim", key, samples.shape, float(np.abs(samples).max()), len(inter), calls["early"][-3:], calls["late"][:3])
+    np.savez_compressed(OUT / "ddim_sampler_tiny.npz", **fx)
+
+
 def ee_sampler_fixture(m):
     samples, err_log, idx_log = ref_ee.get_samples(model=m, batch_size=3, seed=9, num_channels=3, sample_height=8,
                                                    sample_width=8, threshold=0.35, depth=TINY_FULL["depth"])
@@ -149,9 +179,13 @@ def schedule_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "ddim":  # add the DDIM fixture without touching the others
+        ddim_sampler_fixture()
+        sys.exit(0)
     schedule_fixture()
     uvit_forward_fixture("uvit_forward_tiny", TINY, 1, False)
     uvit_forward_fixture("uvit_forward_tiny_cls", TINY_CLS, 3, True)
     ee_model = ee_forward_fixture()
     duodiff_sampler_fixture()
+    ddim_sampler_fixture()
     ee_sampler_fixture(ee_model)

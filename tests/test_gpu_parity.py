@@ -409,8 +409,57 @@ def test_get_samples_api_and_intermediates(dev):
     assert rel_l2(torch.from_numpy(inter[0]).to(dev), O.to_samples_nhwc(x_a)) <= 1e-3
     x_0 = O.sample_ddpm(f, None, np.inf, x_T.clone(), noise.to(dev))
     assert rel_l2(torch.from_numpy(out).to(dev), O.to_samples_nhwc(x_0)) <= IMG_REL_L2
-    with pytest.raises(NotImplementedError):
-        S.get_samples(early, 2, S.predict_noise_postprocessing, 0, 3, 32, 32, use_ddim=True)
+
+
+@pytest.mark.parametrize("steps,eta", [(50, 0.0), (20, 0.05)])
+def test_ddim_branch_matches_oracle(dev, steps, eta):
+    """sampler.py:103-126 through get_samples(use_ddim=True): strided schedule, hand-off rule, sigma^2*z quirk,
+    intermediates; free-running against the oracle with identical x_T and injected noise."""
+    from duodiff_b200 import sampler as S
+    from duodiff_b200.ddpm import ddim_timesteps
+    early, sde, se = _model("cifar10_3", 31, False, dev)
+    late, sdl, sl = _model("cifar10", 32, False, dev)
+    B = 2
+    g = torch.Generator().manual_seed(14)
+    noise = torch.randn(1000, B, 3, 32, 32, generator=g)
+    ts = ddim_timesteps(steps)
+    out, inter = S.get_samples(early, B, S.predict_noise_postprocessing, seed=3, num_channels=3, sample_height=32,
+                               sample_width=32, use_ddim=True, ddim_steps=steps, ddim_eta=eta,
+                               timesteps_save=[1, 1000 - ts[3]], late_model=late, t_switch=300, noise=noise)
+    assert out.shape == (B, 32, 32, 3) and len(inter) == 2
+    torch.manual_seed(3)
+    x_T = torch.randn(B, 3, 32, 32).to(dev)
+    f_e = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    f_l = lambda x, t, y: O.uvit_forward(sdl, sl, x, t, y)  # noqa: E731
+    nz = noise.to(dev)
+    trace = {}
+    x0 = O.sample_ddim(f_e, f_l, 300, x_T.clone(), nz, steps, eta, trace=trace)
+    assert any(trace["late"]) and not all(trace["late"])  # the hand-off happened inside the run
+    assert rel_l2(torch.from_numpy(out).to(dev), O.to_samples_nhwc(x0)) <= IMG_REL_L2
+    x1 = O.sample_ddim(f_e, f_l, 300, x_T.clone(), nz, steps, eta, n_pairs=1)
+    assert rel_l2(torch.from_numpy(inter[0]).to(dev), O.to_samples_nhwc(x1)) <= 1e-3
+    x4 = O.sample_ddim(f_e, f_l, 300, x_T.clone(), nz, steps, eta, n_pairs=4)
+    assert rel_l2(torch.from_numpy(inter[1]).to(dev), O.to_samples_nhwc(x4)) <= IMG_REL_L2
+
+
+def test_ddim_step_kernel_matches_reference_expression(dev):
+    """mode 2 of the update kernel against the oracle's restatement of sampler.py:110-120 (fp32, same op order)."""
+    lib, L = _lib()
+    from duodiff_b200.ddpm import ddim_coefficients, ddim_timesteps
+    sch = O.ddpm_schedule()
+    g = torch.Generator().manual_seed(0)
+    n = 4 * 3 * 32 * 32
+    for steps, eta in ((50, 0.0), (20, 0.05)):
+        table, mode = ddim_coefficients(steps, eta)
+        coef = table.to(dev)
+        ts = ddim_timesteps(steps)
+        for t, s in list(zip(ts[:-1], ts[1:]))[::5] + [(ts[-2], ts[-1])]:
+            x, e, z = (torch.randn(n, generator=g) for _ in range(3))
+            ref = O.ddim_step(sch, e, x, t, s, eta, z if s > 0 else None)
+            xd, ed, zd = x.to(dev), e.to(dev), z.to(dev)
+            lib.check(L.ddb_ddpm_step(xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), coef.data_ptr(), t, mode, 0, n,
+                                      lib.current_stream_ptr()))
+            assert rel_l2(xd.cpu(), ref) <= 1e-6, (steps, eta, t)
 
 
 def test_ee_sampler_logs(dev):

@@ -150,3 +150,26 @@ def test_bench_flop_model_matches_survey():
     assert abs(f3["total"] / 1e9 - 5.552) < 0.01 and abs(f13["total"] / 1e9 - 24.421) < 0.01
     f = bench.forward_flops(CONFIGS["imagenet256"])
     assert abs(f["total"] / 1e9 - 152.912) < 0.05
+
+
+def test_ddim_plan_matches_reference_call_pattern():
+    """Host-side DDIM plan (timesteps + which backbone) against the hooks recorded on the unmodified reference
+    (tests/golden/ddim_sampler_tiny.npz): strided schedule and the `t < 1000 - t_switch` hand-off after the step."""
+    from duodiff_b200.ddpm import ddim_coefficients, ddim_timesteps
+    from duodiff_b200.sampler import _ddim_plan
+    from tests.helpers import load_fixture
+    fx = load_fixture("ddim_sampler_tiny")
+    for steps, eta in ((50, 0.0), (20, 0.05)):
+        key = f"{steps}_{eta}"
+        ts, flags = _ddim_plan(steps, True, 300)
+        assert [t for t, f in zip(ts, flags) if not f] == fx[f"early_ts_{key}"].tolist()
+        assert [t for t, f in zip(ts, flags) if f] == fx[f"late_ts_{key}"].tolist()
+        table, mode = ddim_coefficients(steps, eta)
+        assert mode == 2 and table.shape == (1000, 4)
+        last_t = ddim_timesteps(steps)[-2]
+        assert table[last_t, 2].item() == 0.0  # z = 0 for the last pair (s == 0)
+        assert (table[[t for t in range(1000) if t not in ts]] == 0).all()
+    ts, flags = _ddim_plan(50, False, 300)
+    assert not any(flags)
+    with pytest.raises(ValueError):
+        ddim_timesteps(2000)

@@ -72,6 +72,33 @@ def test_duodiff_sampler_all_rules():
         assert np.abs(got - ref).max() <= 2e-4 * scale, rule  # 1000 chained fp32 steps
 
 
+def test_ddim_sampler():
+    """sampler.py:103-126 (use_ddim): strided schedule, hand-off rule `t < 1000 - t_switch` after the step, the
+    sigma^2 * z quirk, intermediates."""
+    fx = load_fixture("ddim_sampler_tiny")
+    sde, pe = split_fixture(fx, "we::", "p::")
+    sdl, pl = split_fixture(fx, "wl::", "q::")
+    se, sl = O.UViTSpec.from_params(pe), O.UViTSpec.from_params(pl)
+    early = lambda x, t, y: O.uvit_forward(sde, se, x, t, y)  # noqa: E731
+    late = lambda x, t, y: O.uvit_forward(sdl, sl, x, t, y)  # noqa: E731
+    for steps, eta in ((50, 0.0), (20, 0.05)):
+        key = f"{steps}_{eta}"
+        x_T, noise = _replay_reference_rng(7, (2, 3, 8, 8))
+        trace = {}
+        x0 = O.sample_ddim(early, late, 300, x_T, noise, steps, eta, trace=trace)
+        # which backbone ran at which t
+        assert [t for t, l in zip(trace["t"], trace["late"]) if not l] == fx[f"early_ts_{key}"].tolist()
+        assert [t for t, l in zip(trace["t"], trace["late"]) if l] == fx[f"late_ts_{key}"].tolist()
+        ref = fx[f"samples_{key}"]
+        assert np.isfinite(ref).all()
+        assert np.abs(O.to_samples_nhwc(x0).numpy() - ref).max() <= 2e-4 * np.abs(ref).max(), key
+        # timesteps_save=[1, 1000 - ts[3]] -> x after the pairs starting at t = 999 and t = ts[3], in loop order
+        x_T, noise = _replay_reference_rng(7, (2, 3, 8, 8))
+        x1 = O.sample_ddim(early, late, 300, x_T, noise, steps, eta, n_pairs=1)
+        ref1 = fx[f"inter_{key}_0"]
+        assert np.abs(O.to_samples_nhwc(x1).numpy() - ref1).max() <= 1e-5 * np.abs(ref1).max()
+
+
 def test_duodiff_sampler_intermediates():
     fx = load_fixture("duodiff_sampler_tiny")
     sde, pe = split_fixture(fx, "we::", "p::")
