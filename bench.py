@@ -332,7 +332,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         traffic = json.loads(tf.read_text()).get(dom)
-    roofline = dict(bound="tensor", kernel=f"{dom} (gemm_tcgen05_kernel)" if dom.startswith("gemm") else dom,
+    roofline = dict(bound="tensor", kernel=f"{dom} (gemm2_tcgen05_kernel, CTA pair)" if dom.startswith("gemm") else dom,
                     achieved=round(achieved, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(achieved / pk["tflops"], 4),
                     traffic=traffic, peak_source=pk["source"] + ", sustained bf16",
                     flops_per_launch=dom_flops, avg_launch_ms=round(dom_ms, 4),

@@ -233,6 +233,44 @@ def test_batch_invariance(dev):
         assert torch.equal(full[b:b + 1], net(x[b:b + 1].contiguous(), t[b:b + 1].contiguous()))
 
 
+def test_full_size_batch_shard_equivalence(dev):
+    """BASELINE size (CelebA full backbone, B = 128, M = 32 896 rows): the forward of the whole batch equals, bit for
+    bit, the forwards of its four 32-sample shards -- the property that makes N-GPU sampling identical to 1-GPU
+    sampling row for row -- and a slice of it matches the oracle."""
+    net, sd, spec = _model("celeba", 41, False, dev)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(128, 3, 64, 64, generator=g).to(dev)
+    t = torch.randint(0, 1000, (128,), generator=g).float().to(dev)
+    full = net(x, t)
+    assert torch.isfinite(full).all()
+    for r in range(4):
+        sl = slice(32 * r, 32 * r + 32)
+        assert torch.equal(full[sl], net(x[sl].contiguous(), t[sl].contiguous())), r
+    with torch.no_grad():
+        ref = O.uvit_forward(sd, spec, x[:4], t[:4], None)
+    assert rel_l2(full[:4], ref) <= EPS_REL_L2
+
+
+def test_full_size_duodiff_steps_are_shard_invariant(dev):
+    """40 free-running DuoDiff steps across the hand-off at B = 128 with injected noise: the sampler on the whole batch
+    and on two 64-sample shards give identical images (graph replay, both backbones)."""
+    from duodiff_b200.ddpm import Sampler
+    early, _, _ = _model("celeba_3", 42, False, dev)
+    late, _, _ = _model("celeba", 43, False, dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    x_T = torch.randn(128, 3, 64, 64, device=dev, generator=g)
+    noise = torch.zeros(1000, 128, 3, 64, 64, device=dev)
+    noise[680:720] = torch.randn(40, 128, 3, 64, 64, device=dev, generator=g)
+    whole = x_T.clone()
+    Sampler(early.engine(128), late.engine(128), 300, 128).run(whole, noise=noise, t_first=719, t_last=680)
+    for r in range(2):
+        sl = slice(64 * r, 64 * r + 64)
+        part = x_T[sl].clone()
+        Sampler(early.engine(128), late.engine(128), 300, 64).run(part, noise=noise[:, sl].contiguous(), t_first=719,
+                                                                  t_last=680)
+        assert torch.equal(whole[sl], part), r
+
+
 # ------------------------------------------------------------------------------------------------ early exit
 def _spread_probes(net, depth):
     """Random-init probes all sit near 0.5; spread them so that every exit layer occurs.  After
