@@ -26,6 +26,14 @@ class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data_dev", C.c_void_p), ("numel", C.c_int64)]
 
 
+class AEConfig(C.Structure):
+    _fields_ = [
+        ("ch", C.c_int32), ("out_ch", C.c_int32), ("num_res_blocks", C.c_int32), ("z_channels", C.c_int32),
+        ("resolution", C.c_int32), ("embed_dim", C.c_int32), ("n_levels", C.c_int32), ("ch_mult", C.c_int32 * 8),
+        ("max_batch", C.c_int32), ("scale_factor", C.c_float),
+    ]
+
+
 _P = C.c_void_p
 _SIGS = {
     "ddb_version": (C.c_char_p, []),
@@ -49,6 +57,13 @@ _SIGS = {
     "ddb_debug_set_ptr": (C.c_int, [C.c_char_p, _P]),
     "ddb_op_attention": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ddb_op_ln_stats": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "ddb_ae_create": (C.c_int, [C.POINTER(AEConfig), C.POINTER(Tensor), C.c_int32, C.POINTER(_P)]),
+    "ddb_ae_destroy": (None, [_P]),
+    "ddb_ae_decode": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    "ddb_ae_profile_decode": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
+    "ddb_ae_num_ops": (C.c_int32, [_P]),
+    "ddb_ae_op_info": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32, _P]),
+    "ddb_ae_decode_debug": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     "ddb_op_pack_linear": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "gemm3.cuh"
+#include "host_common.h"
 
 using namespace ddb;
 
@@ -172,8 +173,41 @@ static int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, uint64_t d0, uin
     return DDB_OK;
 }
 
+// helpers shared with the other translation units (csrc/host_common.h)
+namespace ddb_host {
+int fail_msg(int code, const char* msg) { return fail(code, "%s", msg); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int sm100_device(int* num_sms) {
+    DeviceInfo d;
+    DDB_TRY(device_info(d));
+    *num_sms = d.num_sms;
+    return DDB_OK;
+}
+int encode_bf16_sw128(CUtensorMap* tm, const void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides, const unsigned* box) {
+    DDB_TRY(load_encode());
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bx[i] = box[i], estr[i] = 1;
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[256];
+        snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(rank %d) failed (%d): dims %llu %llu %llu box %u %u %u", rank,
+                 (int)r, dims[0], dims[1], rank > 2 ? dims[2] : 0ull, box[0], box[1], rank > 2 ? box[2] : 0u);
+        return fail(DDB_ERR_CUDA, "%s", msg);
+    }
+    return DDB_OK;
+}
+}  // namespace ddb_host
+
 // ------------------------------------------------------------------------------------------------ launches
-static int g_use_pdl = 1;  // ddb_set_option "pdl": programmatic dependent launch between the kernels of a step
+static int g_use_pdl = 1;
+namespace ddb_host {
+int use_pdl() { return g_use_pdl; }
+}  // ddb_set_option "pdl": programmatic dependent launch between the kernels of a step
 // Launch with programmaticStreamSerialization: the kernel may become resident while its predecessor drains; every
 // kernel launched this way calls pdl_wait() before it touches global memory (csrc/ptx.cuh).
 template <typename... KArgs, typename... Args>

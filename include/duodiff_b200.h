@@ -129,6 +129,42 @@ int ddb_debug_set_ptr(const char* name, void* dev_ptr);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t ddb_launch_count(void);
 
+/* ---- KL-autoencoder decode: the step after the sampling loop for latent models (sampler.py:141-143,149-150) ----
+ * FrozenAutoencoderKL(ddconfig, embed_dim, pretrained_path, scale_factor) -- models/utils/autoencoder.py:452-466;
+ * only the fields the decoder reads (Decoder.__init__, :320-412).  get_autoencoder() (:503-516) uses
+ * ch=128, ch_mult=[1,2,4,4], num_res_blocks=2, z_channels=4, resolution=256, out_ch=3, attn_resolutions=[]. */
+typedef struct {
+    int32_t ch;
+    int32_t out_ch;          /* <= 8 */
+    int32_t num_res_blocks;
+    int32_t z_channels;      /* <= 8 */
+    int32_t resolution;      /* output resolution; the latent grid is resolution / 2^(n_levels-1) (power of two >= 16) */
+    int32_t embed_dim;       /* must equal z_channels (post_quant_conv is embed_dim -> z_channels) */
+    int32_t n_levels;        /* len(ch_mult) <= 8 */
+    int32_t ch_mult[8];      /* ch * ch_mult[i] must be a multiple of 64 */
+    int32_t max_batch;       /* latents decoded per pass; larger batches are processed in chunks of this size */
+    float scale_factor;      /* 0.18215 */
+} ddb_ae_config;
+typedef struct ddb_ae ddb_ae;
+/* tensors: the FrozenAutoencoderKL state_dict (keys `post_quant_conv.*`, `decoder.*`; encoder keys are ignored). */
+int ddb_ae_create(const ddb_ae_config* cfg, const ddb_tensor* tensors, int32_t n_tensors, ddb_ae** out);
+void ddb_ae_destroy(ddb_ae* ae);
+/* FrozenAutoencoderKL.decode(z) (models/utils/autoencoder.py:486-490):
+ *   z_dev [B, z_channels, r, r] f32 -> img_dev [B, out_ch, resolution, resolution] f32 (NCHW, un-clipped). */
+int ddb_ae_decode(ddb_ae* ae, const float* z_dev, int32_t B, float* img_dev, void* stream);
+/* Same decode with CUDA events around every launch: device ms and algorithmic FLOPs per category
+ * (conv3x3, upsample conv, conv1x1, attention matmuls, groupnorm, other), host arrays of DDB_AE_PROF_CATEGORIES. */
+#define DDB_AE_PROF_CATEGORIES 6
+int ddb_ae_profile_decode(ddb_ae* ae, const float* z_dev, int32_t B, float* img_dev, float* ms_host,
+                          double* flops_host, void* stream);
+/* Parity hooks: the decoder is a flat list of launches; op i leaves an NHWC bf16 (or f32) tensor behind.
+ * info_out = {C, H, W, is_f32} (C == 0: nothing to dump).  decode_debug copies op_index's output of the first
+ * B <= max_batch samples to dump_dev right after it ran. */
+int32_t ddb_ae_num_ops(const ddb_ae* ae);
+int ddb_ae_op_info(const ddb_ae* ae, int32_t i, char* name_out, int32_t name_cap, int32_t* info_out);
+int ddb_ae_decode_debug(ddb_ae* ae, const float* z_dev, int32_t B, float* img_dev, int32_t op_index, void* dump_dev,
+                        void* stream);
+
 /* ---- single-operator entry points (used by the parity tests; same kernels as the model path) ---- */
 /* out[M,N] = epi([A0|A1] W^T); bf16 row-major operands.  epi: 0 bias, 1 LN-fold, 2 LN-fold+GELU, 3 bias+residual.
  * stats_out_dev (optional, [M, N/64, 2] f32): per-row (mean, M2) of every 64-column output chunk.

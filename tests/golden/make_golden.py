@@ -177,8 +177,46 @@ def schedule_fixture():
                         betas_tilde=ref_sampler.betas_tilde.numpy())
 
 
+def ae_decode_fixture():
+    """FrozenAutoencoderKL.decode of the unmodified reference (models/utils/autoencoder.py:452-490) on a tiny ddconfig:
+    the module only loads weights from a file, so a random-init state_dict (GroupNorm affine and biases perturbed) is
+    saved to a temporary path first.  Also runs the decode through sampler.get_samples(autoencoder=...) with a zero
+    network so that the fixture pins the `(decode(x) + 1) / 2`, NHWC post-processing (sampler.py:141-146)."""
+    import tempfile
+
+    from models.utils.autoencoder import Decoder, Encoder, FrozenAutoencoderKL
+    dd = dict(double_z=True, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2, 2],
+              num_res_blocks=1, attn_resolutions=[], dropout=0.0)
+    torch.manual_seed(41)
+    enc, dec = Encoder(**dd), Decoder(**dd)
+    quant, post = torch.nn.Conv2d(8, 8, 1), torch.nn.Conv2d(4, 4, 1)
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        for name, p in list(dec.named_parameters()) + list(post.named_parameters()):
+            if p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.2)
+    sd = {}
+    for pfx, mod in (("encoder.", enc), ("decoder.", dec), ("quant_conv.", quant), ("post_quant_conv.", post)):
+        sd.update({pfx + k: v for k, v in mod.state_dict().items()})
+    with tempfile.TemporaryDirectory() as d:
+        torch.save(sd, Path(d) / "ae.pth")
+        ae = FrozenAutoencoderKL(dd, 4, str(Path(d) / "ae.pth"))
+    z = torch.randn(2, 4, 8, 8, generator=g) * 0.18215 * 1.5
+    with torch.no_grad():
+        out = ae.decode(z)
+    fx = dict(z=z.numpy(), out=out.numpy(), ch=np.int64(32), ch_mult=np.asarray(dd["ch_mult"]),
+              num_res_blocks=np.int64(1), resolution=np.int64(32), scale_factor=np.float32(0.18215))
+    fx.update({"w::" + k: v.numpy().copy() for k, v in sd.items()
+               if k.startswith("decoder.") or k.startswith("post_quant_conv.")})
+    np.savez_compressed(OUT / "ae_decode_tiny.npz", **fx)
+    print("ae_decode", tuple(out.shape), float(out.abs().max()))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "ae":  # add the autoencoder fixture without touching the others
+        ae_decode_fixture()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "ddim":  # add the DDIM fixture without touching the others
         ddim_sampler_fixture()
         sys.exit(0)
@@ -189,3 +227,4 @@ if __name__ == "__main__":
     duodiff_sampler_fixture()
     ddim_sampler_fixture()
     ee_sampler_fixture(ee_model)
+    ae_decode_fixture()

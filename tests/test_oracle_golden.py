@@ -126,3 +126,21 @@ def test_ee_sampler_logs_and_samples():
     np.testing.assert_allclose(err_log.numpy(), fx["err_log"], atol=5e-4)
     ref = fx["samples"]
     assert np.abs(O.to_samples_nhwc(x0).numpy() - ref).max() <= 5e-3 * np.abs(ref).max()
+
+
+def test_autoencoder_decode_matches_reference():
+    """oracle/ae_oracle.py vs FrozenAutoencoderKL.decode of the reference (tests/golden/ae_decode_tiny.npz)."""
+    from oracle import ae_oracle as A
+    fx = load_fixture("ae_decode_tiny")
+    sd, _ = split_fixture(fx)
+    spec = A.AESpec(ch=int(fx["ch"]), ch_mult=[int(v) for v in fx["ch_mult"]],
+                    num_res_blocks=int(fx["num_res_blocks"]), resolution=int(fx["resolution"]),
+                    scale_factor=float(fx["scale_factor"]))
+    tap = {}
+    out = A.decode(sd, spec, torch.from_numpy(fx["z"]), tap)
+    np.testing.assert_allclose(out.numpy(), fx["out"], atol=ATOL, rtol=1e-5)
+    assert "mid.attn_1.proj_out+res" in tap and "up.1.upsample" in tap and "norm_out" in tap
+    # the random factory used by the GPU parity tests produces exactly the reference decoder's keys and shapes
+    rnd = A.random_state_dict(spec, 0)
+    assert set(rnd) == set(sd)
+    assert all(rnd[k].shape == sd[k].shape for k in sd)
