@@ -32,8 +32,6 @@ class FrozenAutoencoderKL:
     def __init__(self, ddconfig: dict, embed_dim: int, pretrained_path: Optional[str] = None,
                  scale_factor: float = 0.18215, *, state_dict: Optional[Dict[str, torch.Tensor]] = None,
                  max_batch: int = 16):
-        if not torch.cuda.is_available():
-            raise _lib.DuoDiffError("duodiff_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         if ddconfig.get("attn_resolutions"):
             raise NotImplementedError("attn_resolutions != [] (the reference's get_autoencoder uses [])")
         if ddconfig.get("use_linear_attn") or ddconfig.get("attn_type", "vanilla") != "vanilla":
@@ -45,6 +43,8 @@ class FrozenAutoencoderKL:
             if pretrained_path is None:
                 raise ValueError("either pretrained_path or state_dict is required")
             state_dict = torch.load(pretrained_path, map_location="cpu")
+        if not torch.cuda.is_available():
+            raise _lib.DuoDiffError("duodiff_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         print(f"Create autoencoder with scale_factor={scale_factor}")
         self.lib = _lib.load()
         self.ddconfig = dict(ddconfig)

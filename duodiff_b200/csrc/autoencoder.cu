@@ -533,9 +533,14 @@ int run_op(const ddb_ae* ae, const Op& op, int B, const float* z, float* img, cu
             int rows = 4096 / units;  // ~4096 16-byte units (64 KB) per CTA
             if (rows < 1) rows = 1;
             if (rows > op.HW) rows = op.HW;
-            CUDA_TRY(ddb_host::launch_pdl(gn_apply_kernel, dim3((op.HW + rows - 1) / rows, B), dim3(256),
-                                          (size_t)op.C * sizeof(float2), st, op.x,
-                                          (const float2*)ae->affine_p(), op.HW, op.C, rows, op.swish, op.y));
+            const dim3 grid((op.HW + rows - 1) / rows, B);
+            if (256 % units == 0)
+                CUDA_TRY(ddb_host::launch_pdl(gn_apply_kernel<true>, grid, dim3(256), 0, st, op.x,
+                                              (const float2*)ae->affine_p(), op.HW, op.C, rows, op.swish, op.y));
+            else
+                CUDA_TRY(ddb_host::launch_pdl(gn_apply_kernel<false>, grid, dim3(256), (size_t)op.C * sizeof(float2),
+                                              st, op.x, (const float2*)ae->affine_p(), op.HW, op.C, rows, op.swish,
+                                              op.y));
             LAUNCH_CHECK();
             return DDB_OK;
         }

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _io
+from .autoencoder import get_autoencoder
 from .ddpm import cached_sampler
 from .early_exit import EarlyExitUViT
 from .uvit import UViT
@@ -24,8 +25,6 @@ def get_samples(model, batch_size: int, seed: int, num_channels: int, sample_hei
                 use_graph: bool = True, device=None):
     """eesampler.py:40-89 -> (samples [B,H,W,C] numpy, error_prediction_by_timestep [1000,depth],
     indices_by_timestep [1000,B]) with both logs as CPU float32 tensors indexed by t like the reference's."""
-    if autoencoder is not None:
-        raise NotImplementedError("KL-autoencoder decode is a 'next' row, not built yet")
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     _io.seed_everything(seed)
     x = torch.randn(batch_size, num_channels, sample_height, sample_width).pin_memory().to(dev, non_blocking=True)
@@ -38,6 +37,8 @@ def get_samples(model, batch_size: int, seed: int, num_channels: int, sample_hei
         if noise is not None:
             noise = noise.to(device=dev, dtype=torch.float32).contiguous()
         sampler.run(x, y=y, noise=noise, seed=seed, exit_log=exit_log, score_log=score_log, use_graph=use_graph)
+        if autoencoder:  # eesampler.py:84-85
+            x = autoencoder.decode(x).contiguous()
         samples = sampler.finalize(x).cpu().numpy()
     return samples, score_log.cpu(), exit_log.cpu().to(torch.float32)
 
@@ -89,12 +90,14 @@ def main(argv=None):
         if mp.get("num_classes", -1) > 0:
             y = y % mp["num_classes"]
         y = y.to(device)
-    if "autoencoder" in cfg:
-        raise NotImplementedError("latent (ImageNet-256) decode through the KL autoencoder is a 'next' row")
+    autoencoder = None
+    if "autoencoder" in cfg:  # eesampler.py:184-189
+        autoencoder = get_autoencoder(cfg["autoencoder"]["autoencoder_checkpoint_path"])
     tic = time.time()
     samples, err_log, idx_log = get_samples(
         model=model, batch_size=args.batch_size, seed=args.seed, num_channels=mp["in_chans"],
-        sample_height=mp["img_size"], sample_width=mp["img_size"], threshold=args.threshold, depth=mp["depth"], y=y)
+        sample_height=mp["img_size"], sample_width=mp["img_size"], threshold=args.threshold, depth=mp["depth"], y=y,
+        autoencoder=autoencoder)
     tac = time.time()
     dump_statistics(tac - tic, err_log, idx_log, out_dir)
     dump_samples(samples, out_dir)

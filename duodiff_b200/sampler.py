@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _io
+from .autoencoder import get_autoencoder
 from .ddpm import RULES, cached_sampler, ddim_timesteps
 from .uvit import UViT
 
@@ -72,9 +73,9 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
     x_T is drawn on the CPU generator after ``seed_everything(seed)`` exactly like the reference (sampler.py:99-100);
     the per-step z comes from an in-kernel Philox stream keyed by ``seed`` unless ``noise`` [1000,B,C,H,W] (indexed
     by t) is injected (parity tests).  ``use_ddim`` runs the strided DDIM branch (sampler.py:103-126, including the
-    reference's sigma_t^2 * z noise term).  The KL autoencoder is a later row of SURVEY.md §8(f)."""
-    if autoencoder is not None:
-        raise NotImplementedError("KL-autoencoder decode (sampler.py:141-143) is a 'next' row, not built yet")
+    reference's sigma_t^2 * z noise term).  ``autoencoder`` (duodiff_b200.autoencoder.get_autoencoder, or any object
+    with the reference's ``decode``) maps the final and the saved intermediate latents to images (sampler.py:141-143,
+    149-150)."""
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     _io.seed_everything(seed)
     x = torch.randn(batch_size, num_channels, sample_height, sample_width)
@@ -87,6 +88,12 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
         # reference: `if 1000 - t in timesteps_save` after the update at t -> save x after the step at t = 1000 - s
         save_at = {1000 - int(s) for s in timesteps_save}
         kept = []
+
+        def finalize(lat):
+            if autoencoder:
+                print("Decode the images...")
+                lat = autoencoder.decode(lat).contiguous()
+            return sampler.finalize(lat)
         if use_ddim:
             sampler = cached_sampler(early, late, t_switch, batch_size, rule=("ddim", int(ddim_steps), float(ddim_eta)))
             steps, flags = _ddim_plan(int(ddim_steps), late is not None, t_switch)
@@ -96,7 +103,7 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
                     sampler.run_list(x, steps[k0:k + 1], flags[k0:k + 1], y=y, noise=noise, seed=seed,
                                      use_graph=use_graph)
                     if t in save_at:
-                        kept.append(sampler.finalize(x))
+                        kept.append(finalize(x))
                     k0 = k + 1
         else:
             sampler = cached_sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
@@ -106,11 +113,11 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
                     continue
                 sampler.run(x, y=y, noise=noise, seed=seed, t_first=t_first, t_last=t_stop, use_graph=use_graph)
                 if t_stop in save_at:
-                    kept.append(sampler.finalize(x))
+                    kept.append(finalize(x))
                 t_first = t_stop - 1
                 if t_first < 0:
                     break
-        samples = sampler.finalize(x)
+        samples = finalize(x)
         out = samples.cpu().numpy()
         # the reference appends in loop order (descending t), one entry per matching step
         inter = [k.cpu().numpy() for k in kept]
@@ -178,13 +185,14 @@ def main(argv=None):
         if mp.get("num_classes", -1) > 0:
             y = y % mp["num_classes"]
         y = y.to(device)
-    if "autoencoder" in cfg:
-        raise NotImplementedError("latent (ImageNet-256) decode through the KL autoencoder is a 'next' row")
+    autoencoder = None
+    if "autoencoder" in cfg:  # sampler.py:320-325
+        autoencoder = get_autoencoder(cfg["autoencoder"]["autoencoder_checkpoint_path"])
     tic = time.time()
     samples, inter = get_samples(
         model=model, batch_size=args.batch_size, postprocessing=_BY_NAME[args.parametrization], seed=args.seed,
         num_channels=mp["in_chans"], sample_height=mp["img_size"], sample_width=mp["img_size"],
-        use_ddim=args.use_ddim, ddim_steps=args.ddim_steps, ddim_eta=args.ddim_eta, y=y, autoencoder=None,
+        use_ddim=args.use_ddim, ddim_steps=args.ddim_steps, ddim_eta=args.ddim_eta, y=y, autoencoder=autoencoder,
         late_model=late, t_switch=args.t_switch, timesteps_save=args.timesteps_save)
     tac = time.time()
     dump_statistics(tac - tic, out_dir)

@@ -173,3 +173,22 @@ def test_ddim_plan_matches_reference_call_pattern():
     assert not any(flags)
     with pytest.raises(ValueError):
         ddim_timesteps(2000)
+
+
+def test_autoencoder_shim_surface():
+    """duodiff_b200.autoencoder mirrors models/utils/autoencoder.py:452-516 for the decode side: same constructor
+    arguments and default ddconfig; unsupported decoder options raise; no CUDA device -> loud error, no fallback."""
+    from duodiff_b200 import _lib
+    from duodiff_b200.autoencoder import DEFAULT_DDCONFIG, FrozenAutoencoderKL, get_autoencoder
+    assert DEFAULT_DDCONFIG["ch_mult"] == [1, 2, 4, 4] and DEFAULT_DDCONFIG["resolution"] == 256
+    for bad in (dict(attn_resolutions=[16]), dict(use_linear_attn=True), dict(tanh_out=True)):
+        with pytest.raises(NotImplementedError):
+            FrozenAutoencoderKL(dict(DEFAULT_DDCONFIG, **bad), 4, state_dict={})
+    with pytest.raises(ValueError):
+        FrozenAutoencoderKL(DEFAULT_DDCONFIG, 4)
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DuoDiffError, match="no CPU fallback"):
+            FrozenAutoencoderKL(DEFAULT_DDCONFIG, 4, state_dict={})
+    with pytest.raises(FileNotFoundError):
+        get_autoencoder("/nonexistent/autoencoder_kl.pth")
+    assert _lib.AEConfig.ch_mult.size == 32  # int32[8], include/duodiff_b200.h
