@@ -47,9 +47,13 @@ def load_checkpoint_into(model: torch.nn.Module, path) -> None:
 
 
 def _save_png(path: Path, img01: np.ndarray) -> None:
+    """What ``plt.imsave(path, img)`` writes for a float RGB array in [0, 1] (sampler.py:174,184): matplotlib's
+    ``to_rgba(bytes=True)`` truncates ``x * 255`` to uint8 and appends an opaque alpha channel (RGBA PNG)."""
     from PIL import Image  # local import: only the CLI needs Pillow
-    arr = (np.clip(img01, 0, 1) * 255.0 + 0.5).astype(np.uint8)
-    if arr.shape[-1] == 1:
+    arr = (np.clip(img01, 0, 1) * 255).astype(np.uint8)
+    if arr.ndim == 3 and arr.shape[-1] == 3:
+        arr = np.concatenate([arr, np.full(arr.shape[:2] + (1,), 255, np.uint8)], axis=-1)
+    elif arr.ndim == 3 and arr.shape[-1] == 1:
         arr = arr[..., 0]
     Image.fromarray(arr).save(path)
 

@@ -192,3 +192,32 @@ def test_autoencoder_shim_surface():
     with pytest.raises(FileNotFoundError):
         get_autoencoder("/nonexistent/autoencoder_kl.pth")
     assert _lib.AEConfig.ch_mult.size == 32  # int32[8], include/duodiff_b200.h
+
+
+def test_output_side_files(tmp_path):
+    """sampler.py:158-189 / eesampler.py:92-111: file names, the sqrt-grid, clipping, statistics.txt and the .pt logs.
+    Pixel values follow plt.imsave (x * 255 truncated to uint8, opaque alpha)."""
+    from PIL import Image
+    from duodiff_b200 import eesampler, sampler
+    rng = np.random.default_rng(0)
+    samples = rng.uniform(-0.2, 1.2, size=(5, 8, 8, 3)).astype(np.float32)
+    sampler.dump_samples(samples, tmp_path)
+    sampler.dump_samples(samples[:2], tmp_path, 250)
+    sampler.dump_statistics(1.5, tmp_path)
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == sorted([f"{i}.png" for i in range(5)] + ["0_250.png", "1_250.png", "grid_image.png",
+                                                             "statistics.txt"])
+    img = np.asarray(Image.open(tmp_path / "3.png"))
+    assert img.shape == (8, 8, 4) and (img[..., 3] == 255).all()
+    assert np.array_equal(img[..., :3], (np.clip(samples[3], 0, 1) * 255).astype(np.uint8))
+    grid = np.asarray(Image.open(tmp_path / "grid_image.png"))
+    assert grid.shape == (16, 16, 4)  # the second call (2 samples -> ceil(sqrt(2)) = 2) overwrote the 3x3 grid
+    assert (tmp_path / "statistics.txt").read_text() == "Elapsed time: 1.5 s\n"
+    out = tmp_path / "ee"
+    out.mkdir()
+    eesampler.dump_samples(samples, out)
+    eesampler.dump_statistics(2.0, torch.zeros(1000, 3), torch.ones(1000, 5), out)
+    assert sorted(p.name for p in out.iterdir()) == sorted(
+        [f"{i}.png" for i in range(5)] + ["statistics.txt", "error_prediction_by_timestep.pt",
+                                          "indices_by_timestep.pt"])
+    assert torch.load(out / "indices_by_timestep.pt").shape == (1000, 5)
