@@ -309,6 +309,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 uint8_t* srow = sbuf + row_in_tile * 128;
                 const f32x2 rstd2 = f2_splat(rstd), nmr2 = f2_splat(-mean_rstd);
                 f32x2 s1 = f2_splat(0.f), s2 = f2_splat(0.f), nshift = f2_splat(0.f);
+                // per-column vectors of the next 8 columns are fetched one iteration ahead (the issue order of a warp is
+                // the program order: without this every j starts with an exposed shared-memory round trip)
+                float4 nb0 = *reinterpret_cast<const float4*>(sbias + c * 64);
+                float4 nb1 = *reinterpret_cast<const float4*>(sbias + c * 64 + 4);
+                float4 nc0 = make_float4(0.f, 0.f, 0.f, 0.f), nc1 = nc0;
+                if constexpr (kLN) {
+                    nc0 = *reinterpret_cast<const float4*>(scs + c * 64);
+                    nc1 = *reinterpret_cast<const float4*>(scs + c * 64 + 4);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int cl = c * 64 + j * 8;  // column inside the tile
@@ -316,14 +325,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
                         v[e] = f2_pack_u(acc[j >> 2][(j & 3) * 8 + 2 * e], acc[j >> 2][(j & 3) * 8 + 2 * e + 1]);
-                    const float4 b0 = *reinterpret_cast<const float4*>(sbias + cl);
-                    const float4 b1 = *reinterpret_cast<const float4*>(sbias + cl + 4);
+                    const float4 b0 = nb0, b1 = nb1, c0 = nc0, c1 = nc1;
+                    if (j < 7) {
+                        nb0 = *reinterpret_cast<const float4*>(sbias + cl + 8);
+                        nb1 = *reinterpret_cast<const float4*>(sbias + cl + 12);
+                        if constexpr (kLN) {
+                            nc0 = *reinterpret_cast<const float4*>(scs + cl + 8);
+                            nc1 = *reinterpret_cast<const float4*>(scs + cl + 12);
+                        }
+                    }
                     const f32x2 bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y),
                                          f2_pack(b1.z, b1.w)};
-                    if (a.debug & 16) {
-                    } else if constexpr (kLN) {
-                        const float4 c0 = *reinterpret_cast<const float4*>(scs + cl);
-                        const float4 c1 = *reinterpret_cast<const float4*>(scs + cl + 4);
+                    if constexpr (kLN) {
                         const f32x2 cs[4] = {f2_pack(c0.x, c0.y), f2_pack(c0.z, c0.w), f2_pack(c1.x, c1.y),
                                              f2_pack(c1.z, c1.w)};
 #pragma unroll
@@ -333,10 +346,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                         for (int e = 0; e < 4; ++e) v[e] = f2_add(v[e], bb[e]);
                     }
                     if constexpr (EPI == EPI_LN_GELU) {
-                        if (!(a.debug & 16)) {
+                        // (no run-time switches inside this loop: a branch per j splits the unrolled body into basic
+                        // blocks and the scheduler can no longer overlap the LDS / MUFU latency of one j with the math
+                        // of the next -- with only two epilogue warps per scheduler that halves the issue rate)
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = gelu_fast2(v[e]);
-                        }
+                        for (int e = 0; e < 4; ++e) v[e] = gelu_fast2(v[e]);
                     }
                     uint4* sp = reinterpret_cast<uint4*>(srow + ((j ^ (row_in_tile & 7)) << 4));
                     if constexpr (EPI == EPI_RES) {
