@@ -64,6 +64,8 @@ def _model(name, seed, hot, dev, ee=False):
     (128, 256, 64, 0, 0), (300, 512, 512, 0, 0), (1000, 512, 512, 512, 0), (1000, 1536, 512, 0, 1),
     (1000, 2048, 512, 0, 2), (1000, 512, 2048, 0, 3), (257 * 8, 768, 768, 0, 3), (1, 256, 64, 0, 0),
     (257 * 128, 512, 512, 0, 3),
+    # the other full-size shapes of the CelebA step: fc2, the two-source skip GEMM, qkv
+    (257 * 128, 512, 2048, 0, 3), (257 * 128, 512, 512, 512, 0), (257 * 128, 1536, 512, 0, 1),
 ])
 def test_op_gemm(dev, M, N, K0, K1, epi, variant):
     """variant 2 = CTA-pair (cta_group::2) kernel of the model path, 1 = single-CTA kernel."""
