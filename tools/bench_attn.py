@@ -17,8 +17,9 @@ ap.add_argument("--variants", default="2")
 ap.add_argument("--n", type=int, default=50)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--debug", default="0")
+ap.add_argument("--lib", default=None, help="alternative libduodiff_b200.so (A/B builds)")
 a = ap.parse_args()
-Lb = _lib.load()
+Lb = _lib.load(a.lib)
 dev = torch.device("cuda:0")
 B, L, H = a.B, a.L, a.H
 D = H * 64
