@@ -15,6 +15,7 @@ A "step" is one pass of the hot path over one batch: a full 1000-step DuoDiff sa
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import statistics
@@ -235,16 +236,24 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     if pf["num_classes"] > 0:
         y = torch.randint(0, min(ps["num_classes"], pf["num_classes"]), (B,), device=dev)
     lib = _lib.load()
+    ae = None
+    if args.decode:  # latent configs: KL-autoencoder decode after the loop (sampler.py:141-143), random-init weights
+        from duodiff_b200 import autoencoder as AE
+        assert C == 4 and H == 32, "--decode needs a latent config (imagenet256)"
+        with contextlib.redirect_stdout(sys.stderr):  # the shim prints like the reference; stdout carries the JSON line
+            ae = AE.FrozenAutoencoderKL(AE.DEFAULT_DDCONFIG, 4, state_dict=AE.random_init_state_dict(seed=4321),
+                                        max_batch=min(B, 32))
     smp = Sampler(early.engine(B), late.engine(B), T_SWITCH, B)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     n_total = args.warmup + args.steps
     x_all = [torch.randn(B, C, H, H, device=dev, generator=gen) for _ in range(min(n_total, 4))]
-    gathered = [torch.empty(B, H, H, C, device=dev) for _ in range(world)] if world > 1 else None
+    oshape = (B, 256, 256, 3) if ae is not None else (B, H, H, C)
+    gathered = [torch.empty(*oshape, device=dev) for _ in range(world)] if world > 1 else None
 
     def one_pass(i: int):
         x = x_all[i % len(x_all)].clone()
         smp.run(x, y=y, seed=rank * 7919 + i, use_graph=True)
-        out = smp.finalize(x)
+        out = smp.finalize(ae.decode(x) if ae is not None else x)
         if world > 1:
             dist.all_gather(gathered, out)  # the path's only collective: finished samples
         return out
@@ -272,9 +281,14 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     # ---- end-to-end through the public API (host x_T -> H2D -> 1000 steps -> NHWC -> D2H numpy)
     def e2e_pass(i: int):
+        with contextlib.redirect_stdout(sys.stderr):
+            return _e2e_pass(i)
+
+    def _e2e_pass(i: int):
         return S.get_samples(early, B, S.predict_noise_postprocessing, seed=rank * 104729 + i, num_channels=C,
                              sample_height=H, sample_width=H, use_ddim=False, ddim_steps=50, ddim_eta=0.0,
-                             timesteps_save=[], y=y, late_model=late, t_switch=T_SWITCH, device=dev)[0]
+                             timesteps_save=[], y=y, autoencoder=ae, late_model=late, t_switch=T_SWITCH,
+                             device=dev)[0]
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for i in range(min(args.warmup, 1)):
@@ -285,7 +299,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         host = e2e_pass(100 + i)
     barrier()
     e2e_s = time.perf_counter() - t0
-    assert host.shape == (B, H, H, C)
+    assert host.shape == oshape
 
     # ---- reduce over ranks (max time)
     tt = torch.tensor([ms, e2e_s * 1e3, float(launches)], device=dev, dtype=torch.float64)
@@ -342,16 +356,26 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     cpu = cpu_sample(args.config, 8, 1, use_reference=True) if world == 1 and not args.no_cpu else None
     nbytes = B * C * H * H * 4
+    out_bytes = B * 256 * 256 * 3 * 4 if ae is not None else nbytes
+    ae_info = None
+    if ae is not None:  # per-category device time of one decode of the batch (CUDA events around every launch)
+        prof = ae.profile_decode(x_all[0])
+        ae_info = dict(ms_per_batch=round(sum(v["ms"] for v in prof.values()), 3),
+                       gflop_per_image=round(sum(v["flops"] for v in prof.values()) / B / 1e9, 1),
+                       categories={k: round(v["ms"], 3) for k, v in prof.items()})
     line = dict(metric=METRIC, value=round(value, 3), unit="images/sec", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(ms_max / args.steps, 2), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, N(0,1) x_T, Philox z_t)",
-                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}",
+                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}"
+                            + (" + KL-autoencoder decode to 3x256x256" if ae is not None else ""),
                             batch_per_gpu=B, global_batch=B * world, t_switch=T_SWITCH, parallelism=f"dp{world}",
                             l2="no flush: one DDPM step touches ~1 GB of activations+weights (> 126 MB L2)"),
                 clocks=clocks.summary(),
                 e2e=dict(value=round(e2e_val, 3), unit="images/sec", h2d_bytes_per_step=nbytes,
-                         d2h_bytes_per_step=nbytes, steps=e2e_steps, api="duodiff_b200.sampler.get_samples"),
+                         d2h_bytes_per_step=out_bytes, steps=e2e_steps, api="duodiff_b200.sampler.get_samples"),
                 gpu_launches=int(tt[2].item()), roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+    if ae_info is not None:
+        line["autoencoder"] = ae_info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -367,6 +391,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the config's BASELINE batch)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--decode", action="store_true",
+                    help="latent configs: decode the samples with the KL autoencoder inside the timed regions")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -146,6 +146,50 @@ class FrozenAutoencoderKL:
         return out, dump.float().permute(0, 3, 1, 2).contiguous()
 
 
+def random_init_state_dict(ddconfig: dict = DEFAULT_DDCONFIG, embed_dim: int = 4, seed: int = 0):
+    """Decoder-side state_dict with the reference's keys and shapes (Decoder.__init__, autoencoder.py:320-412) and
+    PyTorch's default Conv2d / GroupNorm initialisation -- for throughput runs, since no autoencoder checkpoint ships
+    with the reference (random-init weights of the configured architecture)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(key, cout, cin, k):
+        bound = 1.0 / (cin * k * k) ** 0.5  # kaiming_uniform(a=sqrt(5)) and the bias bound coincide
+        sd[key + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+        sd[key + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def norm(key, c):
+        sd[key + ".weight"], sd[key + ".bias"] = torch.ones(c), torch.zeros(c)
+
+    def res(key, cin, cout):
+        norm(key + ".norm1", cin)
+        conv(key + ".conv1", cout, cin, 3)
+        norm(key + ".norm2", cout)
+        conv(key + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(key + ".nin_shortcut", cout, cin, 1)
+
+    mult, ch, zc = ddconfig["ch_mult"], ddconfig["ch"], ddconfig["z_channels"]
+    conv("post_quant_conv", zc, embed_dim, 1)
+    c = ch * mult[-1]
+    conv("decoder.conv_in", c, zc, 3)
+    res("decoder.mid.block_1", c, c)
+    norm("decoder.mid.attn_1.norm", c)
+    for name in ("q", "k", "v", "proj_out"):
+        conv(f"decoder.mid.attn_1.{name}", c, c, 1)
+    res("decoder.mid.block_2", c, c)
+    for lvl in reversed(range(len(mult))):
+        co = ch * mult[lvl]
+        for j in range(ddconfig["num_res_blocks"] + 1):
+            res(f"decoder.up.{lvl}.block.{j}", c, co)
+            c = co
+        if lvl != 0:
+            conv(f"decoder.up.{lvl}.upsample.conv", c, c, 3)
+    norm("decoder.norm_out", c)
+    conv("decoder.conv_out", ddconfig["out_ch"], c, 3)
+    return sd
+
+
 def get_autoencoder(pretrained_path, scale_factor=0.18215, *, max_batch: int = 16):
     """models/utils/autoencoder.py:503-516."""
     return FrozenAutoencoderKL(DEFAULT_DDCONFIG, 4, pretrained_path, scale_factor, max_batch=max_batch)
