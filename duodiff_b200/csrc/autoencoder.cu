@@ -111,6 +111,7 @@ struct ddb_ae {
     Buf part[3];            // GroupNorm partials ring
     Buf affine;             // [maxB, Cmax] float2
     Buf qkv, vT, S, P, O;   // AttnBlock workspace
+    Buf zero_bias;          // bias of the plain matrix products (the conv epilogue always adds one)
     std::vector<Op> ops;
     float2* affine_p() const { return reinterpret_cast<float2*>(affine->p); }
 };
@@ -157,23 +158,30 @@ int tile_shape(int H, int W, int* BW, int* BH) {
     return DDB_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 int launch_conv_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
-    auto kfn = conv_igemm_kernel<BN, EPI>;
+    auto kfn = conv_igemm_kernel<BN, EPI, MT>;
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, MT>::SMEM_BYTES));
         configured = true;
     }
-    const long long tiles = (long long)a.B * ((a.H * a.W) >> 7) * (a.subpixel ? 4 : 1) * (a.N / BN);
-    const int grid = tiles < num_sms ? (int)tiles : num_sms;
+    const long long units = (long long)a.B * ((a.H * a.W) >> 7) * (a.subpixel ? 4 : 1) / MT * (a.N / BN);
+    const int grid = units < num_sms ? (int)units : num_sms;
     if (grid <= 0) return DDB_OK;
-    CUDA_TRY(ddb_host::launch_pdl(kfn, dim3(grid), dim3(384), (size_t)ConvCfg<BN>::SMEM_BYTES, st, a));
+    CUDA_TRY(ddb_host::launch_pdl(kfn, dim3(grid), dim3(384), (size_t)ConvCfg<BN, MT>::SMEM_BYTES, st, a));
     LAUNCH_CHECK();
     return DDB_OK;
 }
 
+int g_conv_mt2 = 1;  // two pixel tiles per work unit for the N = 128 layers (conv_gemm.cuh, MT)
+
 int launch_conv(const ConvArgs& a, int BN, int epi, int num_sms, cudaStream_t st) {
+    // N = 128: two pixel tiles share each weight tile (less shared-memory fill per MMA); needs an even tile count
+    if (g_conv_mt2 && BN == 128 && !a.subpixel && ((a.B * ((a.H * a.W) >> 7)) % 2 == 0)) {
+        if (epi == CEPI_BIAS) return launch_conv_t<128, CEPI_BIAS, 2>(a, num_sms, st);
+        if (epi == CEPI_RES) return launch_conv_t<128, CEPI_RES, 2>(a, num_sms, st);
+    }
 #define CONV_CASE(bn, e) \
     if (BN == bn && epi == e) return launch_conv_t<bn, e>(a, num_sms, st);
     CONV_CASE(256, CEPI_BIAS) CONV_CASE(256, CEPI_RES) CONV_CASE(256, CEPI_F32)
@@ -381,6 +389,8 @@ struct Builder {
             DDB_TRY(tile_shape(H, W, &a.BW, &a.BH));
             a.tw = 1, a.taps = 1, a.wmode = 1;
             o.BN = pick_bn(C), o.epi = CEPI_BIAS;
+            DDB_TRY(new_buf(ae->zero_bias, (size_t)C * 4, true));
+            a.bias = reinterpret_cast<const float*>(ae->zero_bias->p);
             DDB_TRY(tmap_act(&a.tmA0, ae->P->p, T, T, W, H, B, a.BW, a.BH));
             DDB_TRY(tmap_w(&a.tmB, ae->vT->p, T, T, C, B, (size_t)C * T, o.BN));
             DDB_TRY(tmap_2d(&a.tmOut, ae->O->p, (size_t)B * T, C));
@@ -599,6 +609,16 @@ int decode_impl(ddb_ae* ae, const float* z, int B, float* img, cudaStream_t st, 
 }
 
 }  // namespace
+
+namespace ddb_host {
+bool ae_set_option(const char* name, int value) {
+    if (!strcmp(name, "conv_mt2")) {
+        g_conv_mt2 = value != 0;
+        return true;
+    }
+    return false;
+}
+}  // namespace ddb_host
 
 extern "C" {
 

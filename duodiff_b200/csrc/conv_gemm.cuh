@@ -57,29 +57,35 @@ struct ConvArgs {
     int img_C;
 };
 
-template <int BN>
+// MT = pixel tiles per work unit.  With MT = 2 a CTA computes two 128-pixel tiles against the SAME weight tile: per
+// 64-channel K chunk it stages 2 x 16 KB of activations + BN x 128 B of weights for 2 x 4 MMAs.  For the N = 128 layers
+// (the 256 x 256 level, 40 % of the decoder's FLOPs) that is 6 KB of shared-memory fill per MMA instead of 8 KB; those
+// layers are paced by the SM's TMA fill rate (ncu: tensor pipe 41 % active with MT = 1), not by the tensor pipe.
+template <int BN, int MT = 1>
 struct ConvCfg {
     static constexpr int BM = 128;
     static constexpr int BK = 64;
-    static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+    static constexpr int STAGES = (144 * 1024) / STAGE_BYTES;  // 144 KB of operand ring: 3 / 4 / 6 stages
     static constexpr int OUT_BUF_BYTES = 128 * 128;  // 128 rows x 64 bf16
     static constexpr int NUM_OUT_BUFS = 4;           // 2 per epilogue warpgroup
-    static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+    static constexpr int ACC_COLS = MT * BN;         // TMEM columns of one accumulator stage
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512);
     static constexpr int OFF_A = 0;
-    static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
+    static constexpr int OFF_B = OFF_A + STAGES * MT * A_BYTES;
     static constexpr int OFF_OUT = OFF_B + STAGES * B_BYTES;
     static constexpr int OFF_BAR = OFF_OUT + NUM_OUT_BUFS * OUT_BUF_BYTES;
     static constexpr int OFF_RED = OFF_BAR + 256;
     static constexpr int SMEM_BYTES = OFF_RED + 2 * 4 * 32 * 8 + 1024;  // + alignment slack
+    static_assert(2 * ACC_COLS <= 512, "TMEM budget");
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT = 1>
 __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constant__ ConvArgs a) {
-    using Cfg = ConvCfg<BN>;
+    using Cfg = ConvCfg<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool kTmaStore = (EPI == CEPI_BIAS || EPI == CEPI_RES);
 
@@ -104,8 +110,8 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     const int ncls = a.subpixel ? 4 : 1;
     const int tps = (a.H * a.W) >> 7;  // source-grid tiles per sample
     const int nblk_n = a.N / BN;
-    const int nblk_m = a.B * tps * ncls;
-    const int num_tiles = nblk_m * nblk_n;
+    const int nblk_m = a.B * tps * ncls;            // pixel tiles (MT > 1: host guarantees nblk_m % MT == 0)
+    const int num_units = (nblk_m / MT) * nblk_n;   // work units: MT consecutive pixel tiles x one N tile
     const int cpk = a.C0 / Cfg::BK;  // 64-channel chunks per tap
     const int nkb0 = a.taps * cpk;
     const int nkb = nkb0 + a.C1 / Cfg::BK;
@@ -141,26 +147,36 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mb = tile / nblk_n, n_blk = tile % nblk_n;
-                const int cls = mb % ncls, rem = mb / ncls;
-                const int b = rem / tps, p0 = (rem % tps) << 7;
-                const int y0 = p0 / a.W, x0 = p0 % a.W;
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int mb0 = (unit / nblk_n) * MT, n_blk = unit % nblk_n;
+                int tb[MT], ty0[MT], tx0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int rem = (mb0 + mt) / ncls;
+                    const int p0 = (rem % tps) << 7;
+                    tb[mt] = rem / tps, ty0[mt] = p0 / a.W, tx0[mt] = p0 % a.W;
+                }
+                const int cls = mb0 % ncls;  // (MT > 1 only without sub-pixel classes)
                 const int dy0 = a.subpixel ? (cls >> 1) - 1 : a.dy0;
                 const int dx0 = a.subpixel ? (cls & 1) - 1 : a.dx0;
-                const int wz = a.wmode == 1 ? b : (a.wmode == 2 ? cls : 0);
+                const int wz = a.wmode == 1 ? tb[0] : (a.wmode == 2 ? cls : 0);
                 int tap = 0, cc = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* dA = sA + stage * (MT * Cfg::A_BYTES);
                     if (kb < nkb0) {
                         const int ty = tap / a.tw, tx = tap - ty * a.tw;
-                        tma_load_4d(sA + stage * Cfg::A_BYTES, &a.tmA0, &full_bar[stage], cc * Cfg::BK, x0 + dx0 + tx,
-                                    y0 + dy0 + ty, b);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            tma_load_4d(dA + mt * Cfg::A_BYTES, &a.tmA0, &full_bar[stage], cc * Cfg::BK,
+                                        tx0[mt] + dx0 + tx, ty0[mt] + dy0 + ty, tb[mt]);
                         if (++cc == cpk) cc = 0, ++tap;
                     } else {
-                        tma_load_4d(sA + stage * Cfg::A_BYTES, &a.tmA1, &full_bar[stage], (kb - nkb0) * Cfg::BK, x0,
-                                    y0, b);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            tma_load_4d(dA + mt * Cfg::A_BYTES, &a.tmA1, &full_bar[stage], (kb - nkb0) * Cfg::BK,
+                                        tx0[mt], ty0[mt], tb[mt]);
                     }
                     tma_load_3d(sB + stage * Cfg::B_BYTES, &a.tmB, &full_bar[stage], kb * Cfg::BK, n_blk * BN, wz);
                     if (++stage == STAGES) {
@@ -177,20 +193,24 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_COLS;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t a_desc = umma_desc_kmajor_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
                     const uint64_t b_desc = umma_desc_kmajor_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
-                    for (int k = 0; k < Cfg::BK / 16; ++k)
-                        umma_f16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t a_desc =
+                            umma_desc_kmajor_sw128(smem_u32(sA + stage * (MT * Cfg::A_BYTES) + mt * Cfg::A_BYTES));
+#pragma unroll
+                        for (int k = 0; k < Cfg::BK / 16; ++k)
+                            umma_f16_ss(d_tmem + mt * BN, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
@@ -209,33 +229,35 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         const uint32_t bar_id = 1 + g;
         uint8_t* my_bufs = sOut + g * 2 * Cfg::OUT_BUF_BYTES;
         float2* my_red = red + g * 128;
-        constexpr int NCH = BN / 64;                               // 64-column chunks per tile
-        const int my_chunks = (NCH > g) ? (NCH - g + 1) / 2 : 0;   // chunks g, g+2, ...
+        constexpr int NCH = BN / 64;      // 64-column chunks per pixel tile
+        constexpr int UCH = MT * NCH;     // chunks per work unit; warpgroup g takes chunks g, g+2, ...
+        const int my_chunks = (UCH > g) ? (UCH - g + 1) / 2 : 0;
         uint32_t q = 0;
 
-        if (EPI == CEPI_RES && et == 0 && my_chunks > 0) {
-            const int tile = blockIdx.x;
-            if (tile < num_tiles) {
-                const int mb = tile / nblk_n, n_blk = tile % nblk_n;
-                mbar_expect_tx(&res_bar[g * 2 + 0], Cfg::OUT_BUF_BYTES);
-                tma_load_2d(my_bufs, &a.tmRes, &res_bar[g * 2 + 0], n_blk * BN + g * 64, mb * Cfg::BM);
-            }
+        // chunk k of this warpgroup inside a unit -> (pixel tile mb, column chunk c)
+        auto res_coords = [&](int unit, int k, int& col, int& row0) {
+            const int ch = g + 2 * k;
+            col = (unit % nblk_n) * BN + (ch % NCH) * 64;
+            row0 = ((unit / nblk_n) * MT + ch / NCH) * Cfg::BM;
+        };
+        if (EPI == CEPI_RES && et == 0 && my_chunks > 0 && (int)blockIdx.x < num_units) {
+            int col, row0;
+            res_coords(blockIdx.x, 0, col, row0);
+            mbar_expect_tx(&res_bar[g * 2 + 0], Cfg::OUT_BUF_BYTES);
+            tma_load_2d(my_bufs, &a.tmRes, &res_bar[g * 2 + 0], col, row0);
         }
 
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int mb = tile / nblk_n, n_blk = tile % nblk_n;
-            const int cls = mb % ncls, rem = mb / ncls;
-            const int b = rem / tps, r = rem % tps;
-            const int p0 = r << 7;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int mb0 = (unit / nblk_n) * MT, n_blk = unit % nblk_n;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
 
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
+            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + as * Cfg::ACC_COLS;
 
-            if (my_chunks == 0) {  // BN == 64: the second warpgroup has no columns
+            if (my_chunks == 0) {  // BN == 64, MT == 1: the second warpgroup has no columns
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -243,11 +265,16 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
             }
 #pragma unroll 1
             for (int cc = 0; cc < my_chunks; ++cc) {
-                const int c = g + 2 * cc;
+                const int ch = g + 2 * cc;
+                const int mt = ch / NCH, c = ch % NCH;
+                const int mb = mb0 + mt;
+                const int cls = mb % ncls, rem = mb / ncls;
+                const int b = rem / tps, r = rem % tps;
+                const int p0 = r << 7;
                 const int col0 = n_blk * BN + c * 64;
                 uint32_t acc[2][32];
-                tmem_ld_32x32b_x32(t_row + c * 64, acc[0]);
-                tmem_ld_32x32b_x32(t_row + c * 64 + 32, acc[1]);
+                tmem_ld_32x32b_x32(t_row + mt * BN + c * 64, acc[0]);
+                tmem_ld_32x32b_x32(t_row + mt * BN + c * 64 + 32, acc[1]);
 
                 if constexpr (kTmaStore) {
                     const int buf = q & 1;
@@ -265,18 +292,16 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
                         if (lane == 0) mbar_arrive(&tempty_bar[as]);
                     }
                     uint8_t* srow = sbuf + row_in_tile * 128;
+                    const float* bias = a.bias + col0;  // never null on this path (zero vector for plain matmuls)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int cbase = col0 + j * 8;
                         float v[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[j >> 2][(j & 3) * 8 + e]);
-                        if (a.bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cbase + 4));
-                            v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w;
-                            v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
-                        }
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + j * 8));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + j * 8 + 4));
+                        v[0] += b0.x, v[1] += b0.y, v[2] += b0.z, v[3] += b0.w;
+                        v[4] += b1.x, v[5] += b1.y, v[6] += b1.z, v[7] += b1.w;
                         uint4* sp = reinterpret_cast<uint4*>(srow + ((j ^ (row_in_tile & 7)) << 4));
                         if constexpr (EPI == CEPI_RES) {
                             const uint4 rr = *sp;
@@ -301,18 +326,18 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
                             tma_store_2d(&a.tmOut, sbuf, col0, mb * Cfg::BM);
                         tma_store_commit();
                         if constexpr (EPI == CEPI_RES) {
-                            int ncc = cc + 1, ntile = tile;
+                            int ncc = cc + 1, nunit = unit;
                             if (ncc == my_chunks) {
                                 ncc = 0;
-                                ntile = tile + gridDim.x;
+                                nunit = unit + gridDim.x;
                             }
-                            if (ntile < num_tiles) {
+                            if (nunit < num_units) {
                                 tma_store_wait_read<1>();
-                                const int nm = ntile / nblk_n, nn = ntile % nblk_n;
+                                int col, row0;
+                                res_coords(nunit, ncc, col, row0);
                                 uint64_t* rb = &res_bar[g * 2 + (buf ^ 1)];
                                 mbar_expect_tx(rb, Cfg::OUT_BUF_BYTES);
-                                tma_load_2d(my_bufs + (buf ^ 1) * Cfg::OUT_BUF_BYTES, &a.tmRes, rb,
-                                            nn * BN + (g + 2 * ncc) * 64, nm * Cfg::BM);
+                                tma_load_2d(my_bufs + (buf ^ 1) * Cfg::OUT_BUF_BYTES, &a.tmRes, rb, col, row0);
                             }
                         }
                     }
@@ -367,10 +392,10 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
                         const size_t plane = (size_t)a.H * a.W;
                         float* dst = a.img + (size_t)b * a.img_C * plane + p0 + row_in_tile;
 #pragma unroll
-                        for (int ch = 0; ch < 8; ++ch) {
-                            if (col0 + ch < a.img_C)
-                                dst[(size_t)(col0 + ch) * plane] =
-                                    __uint_as_float(acc[0][ch]) + (a.bias ? __ldg(a.bias + col0 + ch) : 0.f);
+                        for (int chn = 0; chn < 8; ++chn) {
+                            if (col0 + chn < a.img_C)
+                                dst[(size_t)(col0 + chn) * plane] =
+                                    __uint_as_float(acc[0][chn]) + __ldg(a.bias + col0 + chn);
                         }
                     }
                 }

@@ -1085,6 +1085,7 @@ int ddb_set_option(const char* name, int32_t value) {
         g_use_pdl = value != 0;
         return DDB_OK;
     }
+    if (ddb_host::ae_set_option(name, value)) return DDB_OK;
     return fail(DDB_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -14,7 +14,8 @@
 namespace ddb_host {
 DDB_HIDDEN int fail_msg(int code, const char* msg);  // stores the thread-local ddb_last_error() text, returns code
 DDB_HIDDEN void count_launch();                      // ddb_launch_count()
-DDB_HIDDEN int use_pdl();                            // ddb_set_option "pdl"
+DDB_HIDDEN int use_pdl();
+DDB_HIDDEN bool ae_set_option(const char* name, int value);  // autoencoder.cu's share of ddb_set_option                            // ddb_set_option "pdl"
 DDB_HIDDEN int sm100_device(int* num_sms);           // DDB_ERR_CUDA unless the current device is sm_100
 // cuTensorMapEncodeTiled for a bf16 tensor of `rank` dims (dims[0] contiguous; strides[i] = byte stride of dim i+1),
 // 128-byte swizzle, zero fill outside the tensor

@@ -80,5 +80,11 @@ if __name__ == "__main__":
         layerwise(A.AESpec(ch=64, ch_mult=[1, 2, 2], num_res_blocks=1, resolution=128), B=3, seed=5)
     elif mode == "full":
         layerwise(A.AESpec(), B=2)
+    elif mode == "ab":  # A/B of the MT = 2 work units for the N = 128 layers
+        from duodiff_b200 import _lib
+        for v in (0, 1, 0, 1):
+            _lib.check(_lib.load().ddb_set_option(b"conv_mt2", v))
+            print("conv_mt2 =", v)
+            bench(64, 32)
     elif mode == "bench":
         bench(int(sys.argv[2]) if len(sys.argv) > 2 else 32, int(sys.argv[3]) if len(sys.argv) > 3 else 16)
