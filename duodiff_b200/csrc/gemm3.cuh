@@ -332,8 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
                     const float4 b1 = *reinterpret_cast<const float4*>(sbias + cl + 4);
                     const f32x2 bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y),
                                          f2_pack(b1.z, b1.w)};
-                    if (a.debug & 16) {
-                    } else if constexpr (kLN) {
+                    if constexpr (kLN) {
                         const float4 c0 = *reinterpret_cast<const float4*>(scs + cl);
                         const float4 c1 = *reinterpret_cast<const float4*>(scs + cl + 4);
                         const f32x2 cs[4] = {f2_pack(c0.x, c0.y), f2_pack(c0.z, c0.w), f2_pack(c1.x, c1.y),
@@ -344,11 +343,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G3_THREADS, 1)
 #pragma unroll
                         for (int e = 0; e < 4; ++e) v[e] = f2_add(v[e], bb[e]);
                     }
-                    if constexpr (EPI == EPI_LN_GELU) {
-                        if (!(a.debug & 16)) {
+                    if constexpr (EPI == EPI_LN_GELU) {  // (no run-time switches in this loop, see gemm2.cuh)
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = gelu_fast2(v[e]);
-                        }
+                        for (int e = 0; e < 4; ++e) v[e] = gelu_fast2(v[e]);
                     }
                     uint4* sp = reinterpret_cast<uint4*>(srow + (((uint32_t)j ^ swz) << 4));
                     if constexpr (EPI == EPI_RES) {
