@@ -875,8 +875,8 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     if (cp) {
         ProfScope ps(PC_EE_OTHER);
         const int n = std::max(B, c.depth * B);
-        ee_reset_kernel<<<(n + 255) / 256, 256, 0, st>>>(een, m->ee_slot->as<int>(), B, m->L, m->scores->as<float>(),
-                                                        c.depth, cp->exit_idx, cp->t_dev, cp->exit_log);
+        CUDA_TRY(launch_pdl(ee_reset_kernel, dim3((n + 255) / 256), dim3(256), 0, st, een, m->ee_slot->as<int>(), B, m->L, m->scores->as<float>(),
+                                                        c.depth, cp->exit_idx, cp->t_dev, cp->exit_log));
         LAUNCH_CHECK();
     }
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
@@ -890,15 +890,15 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             kind = 1;
             {
                 ProfScope ps(PC_EE_OTHER);
-                ee_decide_kernel<<<1, 1024, 0, st>>>(m->probe_sig->as<float>(), m->L, cp->threshold, i, B, c.depth, een,
+                CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(1), dim3(1024), 0, st, m->probe_sig->as<float>(), m->L, cp->threshold, i, B, c.depth, een,
                                                      m->ee_slot->as<int>(), m->ee_keep_src->as<int>(),
                                                      m->ee_exit_src->as<int>(), m->ee_exit_slot->as<int>(),
                                                      m->scores->as<float>(), cp->exit_idx, cp->t_dev, cp->exit_log,
-                                                     cp->score_mean_log);
+                                                     cp->score_mean_log));
                 LAUNCH_CHECK();
-                ee_gather_exit_kernel<<<m->L, 128, 0, st>>>(cur, st2, een, m->ee_exit_src->as<int>(),
+                CUDA_TRY(launch_pdl(ee_gather_exit_kernel, dim3(m->L, EE_GATHER_Y), dim3(128), 0, st, cur, st2, een, m->ee_exit_src->as<int>(),
                                                             m->xe->as<__nv_bfloat16>(), m->stats_e->as<float2>(), m->L,
-                                                            D);
+                                                            D));
                 LAUNCH_CHECK();
             }
             {
@@ -911,8 +911,8 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                              m->ee_exit_slot->as<int>()));
             {
                 ProfScope ps(PC_EE_OTHER);
-                ee_compact_kernel<<<dim3(m->L, m->ee_live_n[i] + 1), 128, 0, st>>>(
-                    m->ee_live[i], m->ee_live_n[i], st2, een, m->ee_keep_src->as<int>(), m->L, D);
+                CUDA_TRY(launch_pdl(ee_compact_kernel, dim3(m->L, m->ee_live_n[i] + 1), dim3(128), 0, st, 
+                    m->ee_live[i], m->ee_live_n[i], st2, een, m->ee_keep_src->as<int>(), m->L, D));
                 LAUNCH_CHECK();
             }
         } else if (ee) {
@@ -922,8 +922,8 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             kind = 1;
             {
                 ProfScope ps(PC_EE_OTHER);
-                probe_mean_kernel<<<B, 128, 0, st>>>(m->probe_sig->as<float>(), m->L,
-                                                     m->scores->as<float>() + (size_t)i * B);
+                CUDA_TRY(launch_pdl(probe_mean_kernel, dim3(B), dim3(128), 0, st, m->probe_sig->as<float>(), m->L,
+                                                     m->scores->as<float>() + (size_t)i * B));
                 LAUNCH_CHECK();
             }
             DDB_TRY(run_gemm(m->head_dec[i], EPI_DECODE, PC_GEMM_DECODE, true, false));

@@ -575,6 +575,8 @@ __global__ void finalize_nhwc_kernel(const float* __restrict__ x, float* __restr
 // probe_sig [M] (one layer) -> score[b] = mean_l sig[b*L + l]; deterministic tree order.
 __global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict__ sig, int L,
                                                          float* __restrict__ score /*[B]*/) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x;
     float s = 0.f;
     for (int l = threadIdx.x; l < L; l += blockDim.x) s += sig[(size_t)b * L + l];
@@ -617,6 +619,8 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
 __global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, int B, int L,
                                 float* __restrict__ scores, int depth, int* __restrict__ exit_idx,
                                 const int* __restrict__ t_dev, int* __restrict__ exit_log) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) ee_n[0] = B, ee_n[1] = B * L, ee_n[2] = 0, ee_n[3] = 0;
     if (i < B) {
@@ -634,27 +638,31 @@ __global__ void __launch_bounds__(1024) ee_decide_kernel(
     int* __restrict__ slot, int* __restrict__ keep_src, int* __restrict__ exit_src, int* __restrict__ exit_slot,
     float* __restrict__ scores, int* __restrict__ exit_idx, const int* __restrict__ t_dev,
     int* __restrict__ exit_log, float* __restrict__ score_mean_log) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sc[1024];
     __shared__ int new_slot[1024];
     __shared__ int wtot[2][32];
     __shared__ float wsum[32];
-    __shared__ float part[8][4];
+    __shared__ float part[1024][4];
     const int n = ee_n[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // score = mean over tokens, with exactly the summation order of probe_mean_kernel (128 threads per sample), so the
-    // exit decisions of the two modes can never differ by rounding
+    // exit decisions of the two modes can never differ by rounding.  Eight groups of 128 threads walk the samples
+    // without any block-wide synchronisation in between (the samples' loads overlap); one barrier at the end.
     const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127;
-    for (int b0 = 0; b0 < n; b0 += 8) {
-        const int b = b0 + grp;
+#pragma unroll 4
+    for (int b = grp; b < n; b += 8) {
         float s = 0.f;
-        if (b < n)
-            for (int l = gt; l < L; l += 128) s += sig[(size_t)b * L + l];
+        for (int l = gt; l < L; l += 128) s += sig[(size_t)b * L + l];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) part[grp][(gt >> 5)] = s;
-        __syncthreads();
-        if (gt == 0 && b < n) sc[b] = (part[grp][0] + part[grp][1] + part[grp][2] + part[grp][3]) / (float)L;
-        __syncthreads();
+        if (lane == 0) part[b][(gt >> 5)] = s;
     }
+    __syncthreads();
+    if ((int)threadIdx.x < n)
+        sc[threadIdx.x] = (part[threadIdx.x][0] + part[threadIdx.x][1] + part[threadIdx.x][2] + part[threadIdx.x][3]) /
+                          (float)L;
+    __syncthreads();
     const int b = threadIdx.x;
     const bool live = b < n;
     const float myscore = live ? sc[b] : 0.f;
@@ -711,22 +719,28 @@ __global__ void __launch_bounds__(1024) ee_decide_kernel(
     }
 }
 
-// rows of the leaving samples -> scratch batch [n_exit*L, D] (+ their LayerNorm statistics); grid = L CTAs
+// rows of the leaving samples -> scratch batch [n_exit*L, D] (+ their LayerNorm statistics); grid = (L, EE_GATHER_Y):
+// the two halves of a CTA and the CTAs along y take different leavers, a thread copies one 16-byte chunk of a row.
+constexpr int EE_GATHER_Y = 4;
 __global__ void __launch_bounds__(128) ee_gather_exit_kernel(const __nv_bfloat16* __restrict__ x,
                                                              const float2* __restrict__ stats,
                                                              const int* __restrict__ ee_n,
                                                              const int* __restrict__ exit_src,
                                                              __nv_bfloat16* __restrict__ xe,
                                                              float2* __restrict__ stats_e, int L, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n_exit = ee_n[2];
+    if (n_exit == 0) return;  // nobody leaves at this layer
     const int l = blockIdx.x;
     const int chunks = D / 8;  // 16-byte chunks per row
-    for (int j = 0; j < n_exit; ++j) {
+    const int half = threadIdx.x >> 6, t = threadIdx.x & 63;
+    for (int j = blockIdx.y * 2 + half; j < n_exit; j += 2 * EE_GATHER_Y) {
         const size_t src = (size_t)exit_src[j] * L + l, dst = (size_t)j * L + l;
         const uint4* sp = reinterpret_cast<const uint4*>(x + src * D);
         uint4* dp = reinterpret_cast<uint4*>(xe + dst * D);
-        for (int c = threadIdx.x; c < chunks; c += blockDim.x) dp[c] = sp[c];
-        if (threadIdx.x == 0) stats_e[dst] = stats[src];
+        for (int c = t; c < chunks; c += 64) dp[c] = sp[c];
+        if (t == 0) stats_e[dst] = stats[src];
     }
 }
 
@@ -740,6 +754,8 @@ struct EeBufList {
 __global__ void __launch_bounds__(128) ee_compact_kernel(EeBufList bufs, int nbuf, float2* __restrict__ stats,
                                                          const int* __restrict__ ee_n,
                                                          const int* __restrict__ keep_src, int L, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (ee_n[2] == 0) return;  // nobody left at this layer
     const int n_keep = ee_n[0];
     const int l = blockIdx.x;
