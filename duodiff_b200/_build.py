@@ -9,7 +9,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libduodiff_b200.so"
 SOURCES = ["duodiff_b200.cu", "autoencoder.cu"]
-HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "gemm3.cuh", "attention.cuh", "elementwise.cuh", "conv_gemm.cuh",
+HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "gemm3.cuh", "attention.cuh", "attention2.cuh", "elementwise.cuh", "conv_gemm.cuh",
            "host_common.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

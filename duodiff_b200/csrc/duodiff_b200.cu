@@ -16,6 +16,7 @@
 
 #include "../../include/duodiff_b200.h"
 #include "attention.cuh"
+#include "attention2.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
@@ -382,19 +383,25 @@ static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* 
 }
 static long long* g_attn_trace = nullptr;  // bench-only (ddb_debug_set_ptr "attn_trace")
 // persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
-static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st) {
+static int g_attn_x2 = 0;  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
+static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, int force_x2 = -1) {
     static bool configured = false;
     if (!configured) {
         CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ATT3_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ATT4_SMEM));
         configured = true;
     }
     if (B <= 0) return DDB_OK;
     a.B = B;
     a.trace = g_attn_trace;
     const int items = B * a.H;
-    CUDA_TRY(launch_pdl(attention_tcgen05_kernel, dim3(items < num_sms ? items : num_sms), dim3(ATT3_THREADS),
-                        ATT3_SMEM, st, a));
+    const dim3 grid(items < num_sms ? items : num_sms);
+    if (force_x2 >= 0 ? force_x2 != 0 : g_attn_x2 != 0)
+        CUDA_TRY(launch_pdl(attention_tcgen05_x2_kernel, grid, dim3(ATT4_THREADS), ATT4_SMEM, st, a));
+    else
+        CUDA_TRY(launch_pdl(attention_tcgen05_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, st, a));
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -1077,6 +1084,10 @@ int ddb_set_option(const char* name, int32_t value) {
         g_gemm_ts = value != 0;
         return DDB_OK;
     }
+    if (!strcmp(name, "attn_x2")) {
+        g_attn_x2 = value != 0;
+        return DDB_OK;
+    }
     if (!strcmp(name, "gemm_bn128")) {
         g_gemm_bn128 = value != 0;
         return DDB_OK;
@@ -1351,12 +1362,12 @@ int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, i
     DeviceInfo di;
     DDB_TRY(device_info(di));
     const bool tc_ok = (L == 257 || L == 258);
-    if (variant == 2 && !tc_ok) return fail(DDB_ERR_INVALID, "tcgen05 attention needs L = 256 + {1,2}");
-    if (variant == 2 || (variant == 0 && tc_ok)) {
+    if ((variant == 2 || variant == 3) && !tc_ok) return fail(DDB_ERR_INVALID, "tcgen05 attention needs L = 256 + {1,2}");
+    if (variant == 2 || variant == 3 || (variant == 0 && tc_ok)) {
         AttnArgs a;
         DDB_TRY(plan_attention(a, reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
                                reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H));
-        return launch_attention_tc(a, B, di.num_sms, (cudaStream_t)stream);
+        return launch_attention_tc(a, B, di.num_sms, (cudaStream_t)stream, variant == 0 ? -1 : (variant == 3));
     }
     return launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv_dev),
                             reinterpret_cast<__nv_bfloat16*>(out_dev), B, L, H, (cudaStream_t)stream);

@@ -1,5 +1,6 @@
 """Phase timeline of the persistent attention kernel (CTA 0): clock64 stamps per item and query tile."""
 import sys
+VAR = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
@@ -12,10 +13,10 @@ qkv = [(torch.randn(B * L, 3 * D, device=dev) * 1.5).bfloat16() for _ in range(3
 out = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
 tr = torch.zeros(8, 2, 16, dtype=torch.int64, device=dev)
 for i in range(3):
-    _lib.check(Lb.ddb_op_attention(_lib.ptr(qkv[i]), _lib.ptr(out), B, L, H, 2, _lib.current_stream_ptr()))
+    _lib.check(Lb.ddb_op_attention(_lib.ptr(qkv[i]), _lib.ptr(out), B, L, H, VAR, _lib.current_stream_ptr()))
 torch.cuda.synchronize()
 _lib.check(Lb.ddb_debug_set_ptr(b"attn_trace", tr.data_ptr()))
-_lib.check(Lb.ddb_op_attention(_lib.ptr(qkv[0]), _lib.ptr(out), B, L, H, 2, _lib.current_stream_ptr()))
+_lib.check(Lb.ddb_op_attention(_lib.ptr(qkv[0]), _lib.ptr(out), B, L, H, VAR, _lib.current_stream_ptr()))
 torch.cuda.synchronize()
 _lib.check(Lb.ddb_debug_set_ptr(b"attn_trace", None))
 t = tr.cpu()
