@@ -221,3 +221,26 @@ def test_output_side_files(tmp_path):
         [f"{i}.png" for i in range(5)] + ["statistics.txt", "error_prediction_by_timestep.pt",
                                           "indices_by_timestep.pt"])
     assert torch.load(out / "indices_by_timestep.pt").shape == (1000, 5)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line with the contract's keys,
+    the GPU arm's metric / unit / config, e2e == value with zero copy bytes, a cpu_baseline describing the sample."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    res = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/sec" and d["higher_is_better"] is True
+    assert d["metric"].startswith("images/sec (DuoDiff sampling") and "celeba" in d["config"]["workload"]
+    assert d["config"]["batch_per_gpu"] == 128 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["e2e"] == dict(value=d["value"], unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["value"] > 0 and d["gpu_launches"] == 0
