@@ -263,6 +263,7 @@ struct AttnArgs {
     int L, H, extras, B;
     float scale_log2e;
     const int* b_dev;  // optional live batch size (early-exit compaction)
+    int reverse;       // walk the (sample, head) items from the last to the first (see GemmArgs::reverse)
     long long* trace;  // bench-only: CTA 0 records clock64() at the phase boundaries of every item ([it][tile][8])
 };
 
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         // ================================================================= TMA producer
         if (lane == 0) {
             for (int it = 0; it < my_items; ++it) {
-                const int item = blockIdx.x + it * gridDim.x;
+                const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
                 const int b = item / a.H, h = item % a.H;
                 const int s = it & 1;
                 uint8_t* st = smem + s * ATT3_STAGE;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         // ================================================================= extras query rows on mma.sync
         const int g = lane >> 2, t = lane & 3;
         for (int it = 0; it < my_items; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
+            const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
             const int b = item / a.H, h = item % a.H;
             const int s = it & 1;
             const uint8_t* st = smem + s * ATT3_STAGE;
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         float se0 = 0.f, se1 = 0.f;
         if (my_items > 0) extras_scores(0, se0, se1);
         for (int it = 0; it < my_items; ++it) {
-            const int item = blockIdx.x + it * gridDim.x;
+            const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
             const int b = item / a.H, h = item % a.H;
             const int s = it & 1;
             const uint32_t ph = it & 1;

@@ -248,6 +248,7 @@ static int g_gemm_variant = 2;
 static int g_gemm_debug = 0;
 static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
+static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
 template <int EPI, bool STATS, int STAGES, int NBUF, int BN = 256>
@@ -867,8 +868,14 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     // partials per row written by the producing CTA-pair GEMM's epilogue (kind 2).
     const int np_p = D / 64;
     int kind = 0;
+    // consecutive kernels walk the rows in alternating directions (GemmArgs::reverse): L2 reuse between kernels
+    bool rev = false;
     auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
         g.M = M;
+        if (g_alt_dir && pair && epi != EPI_DECODE) {
+            g.reverse = rev ? 1 : 0;
+            rev = !rev;
+        }
         if (cp && !g.m_dev) g.m_dev = een + 1;
         if (ln_in) {
             g.stats = kind == 2 ? stp : st2;
@@ -951,6 +958,10 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             ProfScope ps(PC_ATTENTION);
             AttnArgs aa = m->attn;
             aa.b_dev = een;  // live sample count (compaction) or null
+            if (g_alt_dir) {
+                aa.reverse = rev ? 1 : 0;
+                rev = !rev;
+            }
             DDB_TRY(launch_attention_tc(aa, B, nsm, st));
         }
         DDB_TRY(run_gemm(op.proj, EPI_RES, PC_GEMM_PROJ, false, true));
@@ -1086,6 +1097,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "attn_x2")) {
         g_attn_x2 = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "alt_dir")) {
+        g_alt_dir = value != 0;
         return DDB_OK;
     }
     if (!strcmp(name, "gemm_bn128")) {

@@ -56,6 +56,10 @@ struct GemmArgs {
     // token row b*tok_L + tok_extras + l through a 3-D tensor map (tmOut: [B][256][N] view of the token buffer), the
     // "residual" is the positional embedding of patch l (tmRes: [256, N], the same rows for every sample).
     int embed_mode, tok_L, tok_extras;
+    // Row blocks are walked from the last to the first (CTA-pair kernel).  Consecutive kernels of a transformer block
+    // alternate the direction, so a consumer starts with the rows its producer wrote LAST -- the part of a tensor larger
+    // than what the L2 can hold (qkv 101 MB, MLP hidden 135 MB of 126 MB) that is still resident.
+    int reverse;
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;

@@ -122,7 +122,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+                const int m_blk = a.reverse ? nblk_m - 1 - tile / nblk_n : tile / nblk_n, n_blk = tile % nblk_n;
                 const int row0 = m_blk * 256 + (int)rank * 128;
                 const int wrow0 = n_blk * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -188,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const int t = threadIdx.x - kAllocWarp * 32;  // 0..63
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-            const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+            const int m_blk = a.reverse ? nblk_m - 1 - tile / nblk_n : tile / nblk_n, n_blk = tile % nblk_n;
             const int buf = it & 1;
             const uint32_t ph = (it >> 1) & 1;
             uint8_t* ab = sAux + buf * Cfg::AUX_BYTES;
@@ -231,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         auto prefetch_res = [&](uint32_t s) {
             const int tile = cluster_id + (int)(s / CHUNKS_PER_WG) * num_clusters;
             if (tile >= num_tiles) return;
-            const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+            const int m_blk = a.reverse ? nblk_m - 1 - tile / nblk_n : tile / nblk_n, n_blk = tile % nblk_n;
             const int c = g + 2 * (int)(s % CHUNKS_PER_WG);
             uint64_t* rb = &my_res[s % NBUF];
             mbar_expect_tx(rb, Cfg::OUT_BUF_BYTES);
@@ -244,7 +244,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
         int it = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-            const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+            const int m_blk = a.reverse ? nblk_m - 1 - tile / nblk_n : tile / nblk_n, n_blk = tile % nblk_n;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int row0 = m_blk * 256 + (int)rank * 128;
