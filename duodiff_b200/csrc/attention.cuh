@@ -264,6 +264,7 @@ struct AttnArgs {
     float scale_log2e;
     const int* b_dev;  // optional live batch size (early-exit compaction)
     int reverse;       // walk the (sample, head) items from the last to the first (see GemmArgs::reverse)
+    int discard;       // drop the consumed q|k|v lines from L2 instead of letting them be written back (model path only)
     long long* trace;  // bench-only: CTA 0 records clock64() at the phase boundaries of every item ([it][tile][8])
 };
 
@@ -322,14 +323,33 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     pdl_wait();  // qkv is the predecessor's output
 
     if (warp == 8) {
-        // ================================================================= TMA producer
-        if (lane == 0) {
-            for (int it = 0; it < my_items; ++it) {
-                const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
+        // ================================================================= TMA producer (+ L2 discard of consumed q|k|v)
+        // a.discard: the q|k|v slice of a finished item is dead (the next block's qkv GEMM rewrites the whole buffer),
+        // but its lines sit dirty in L2 and would be written back to HBM on eviction -- 101 MB per launch.  Once the
+        // stage of item it-2 is released (all MMAs retired, extras warp done, stores read) its 3 x L lines of 128 bytes
+        // (one head's slice of one token: exclusively this item's) are dropped with discard.global.L2.
+        auto item_of = [&](int it) {
+            return a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
+        };
+        auto discard_item = [&](int it) {
+            const int item = item_of(it);
+            const int b = item / a.H, h = item % a.H;
+            const __nv_bfloat16* base = a.qkv + (size_t)b * a.L * 3 * D + h * 64;
+            for (int l = lane; l < a.L; l += 32) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    asm volatile("discard.global.L2 [%0], 128;" ::"l"(base + (size_t)l * 3 * D + k * D) : "memory");
+            }
+        };
+        for (int it = 0; it < my_items + (a.discard ? 2 : 0); ++it) {
+            const int s = it & 1;
+            if (lane == 0) mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
+            __syncwarp();
+            if (a.discard && it >= 2) discard_item(it - 2);
+            if (it < my_items && lane == 0) {
+                const int item = item_of(it);
                 const int b = item / a.H, h = item % a.H;
-                const int s = it & 1;
                 uint8_t* st = smem + s * ATT3_STAGE;
-                mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qk_full[s], ATT3_QK_BYTES);
                 tma_load_3d(st + ATT3_OFF_K, &a.tmKV, &qk_full[s], D + h * 64, a.extras, b);
                 tma_load_3d(st, &a.tmQKV, &qk_full[s], h * 64, a.extras, b);
@@ -340,6 +360,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 tma_load_3d(st + ATT3_OFF_V, &a.tmKV, &v_full[s], 2 * D + h * 64, a.extras, b);
                 tma_load_3d(st + ATT3_OFF_VX, &a.tmX, &v_full[s], 2 * D + h * 64, 0, b);
             }
+            __syncwarp();
         }
     } else if (warp == 9 || warp == 11) {
         // ================================================================= MMA issuers: one thread per query tile

@@ -248,6 +248,7 @@ static int g_gemm_variant = 2;
 static int g_gemm_debug = 0;
 static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
+static int g_attn_discard = 1;  // ddb_set_option "attn_discard": discard consumed q|k|v lines from L2 (attention.cuh)
 static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
@@ -962,6 +963,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                 aa.reverse = rev ? 1 : 0;
                 rev = !rev;
             }
+            aa.discard = g_attn_discard;  // qkv is the library's own scratch: dead once attention has read it
             DDB_TRY(launch_attention_tc(aa, B, nsm, st));
         }
         DDB_TRY(run_gemm(op.proj, EPI_RES, PC_GEMM_PROJ, false, true));
@@ -1097,6 +1099,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "attn_x2")) {
         g_attn_x2 = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "attn_discard")) {
+        g_attn_discard = value != 0;
         return DDB_OK;
     }
     if (!strcmp(name, "alt_dir")) {

@@ -15,7 +15,13 @@ ap.add_argument("--config", default="celeba")
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--which", default="full")
+ap.add_argument("--opt", default="", help="runtime options, e.g. alt_dir=0,pdl=1")
 a = ap.parse_args()
+if a.opt:
+    from duodiff_b200 import _lib
+    for kv in a.opt.split(","):
+        k, v = kv.split("=")
+        _lib.check(_lib.load().ddb_set_option(k.encode(), int(v)))
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 names = {"full": [a.config], "shallow": [a.config + "_3"], "both": [a.config + "_3", a.config]}[a.which]
