@@ -249,6 +249,9 @@ static int g_gemm_debug = 0;
 static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
 static int g_attn_discard = 1;  // ddb_set_option "attn_discard": discard consumed q|k|v lines from L2 (attention.cuh)
+static int g_mlp_split = 0;  // ddb_set_option "mlp_split": fc1 -> fc2 in two half batches (hidden stays in L2).  Parity-green but
+                             // measured SLOWER at CelebA B = 128 (42.8 -> 41.7 images/s): two partial GEMM rounds and two more
+                             // kernel boundaries per block cost more than the ~3 GB of HBM traffic per step it removes.
 static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
@@ -483,6 +486,11 @@ struct ddb_model {
     std::vector<GemmArgs> head_dec;
     AttnArgs attn;
     std::vector<Buf> keep;  // misc allocations
+    // MLP in two half batches (see forward_impl): per batch size, the fc1 / fc2 descriptors of both halves of every block
+    struct HalfOps {
+        GemmArgs fc1[2], fc2[2];
+    };
+    std::map<int, std::vector<HalfOps>> mlp_split;
 };
 
 typedef std::map<std::string, const ddb_tensor*> TensorMap;
@@ -588,6 +596,27 @@ static int plan_gemm(GemmArgs& g, const ddb_model* m, const void* A0, int K0, co
     if (res && BN == 256) DDB_TRY(make_tmap_bf16_sw64(&g.tmRes2, res, m->Mpad, W.N, W.N, 128));
     return DDB_OK;
 }
+// Copy of a planned GEMM restricted to `rows` rows starting at row `row0` of its A / out / residual tensors.  The maps
+// cover exactly those rows, so the partial last tile is clipped by TMA (it must not touch the other half's rows).
+static int retarget_rows(GemmArgs& g, const GemmArgs& src, const void* A0, const void* out, const void* res, int row0,
+                         int rows) {
+    g = src;
+    g.M = rows;
+    const char* a = reinterpret_cast<const char*>(A0) + (size_t)row0 * src.K0 * 2;
+    DDB_TRY(make_tmap_bf16(&g.tmA0, a, rows, src.K0, src.K0, 128));
+    if (out) {
+        char* o = reinterpret_cast<char*>(const_cast<void*>(out)) + (size_t)row0 * src.N * 2;
+        DDB_TRY(make_tmap_bf16(&g.tmOut, o, rows, src.N, src.N, 128));
+        DDB_TRY(make_tmap_bf16_sw64(&g.tmOut2, o, rows, src.N, src.N, 128));
+    }
+    if (res) {
+        const char* r = reinterpret_cast<const char*>(res) + (size_t)row0 * src.N * 2;
+        DDB_TRY(make_tmap_bf16(&g.tmRes, r, rows, src.N, src.N, 128));
+        DDB_TRY(make_tmap_bf16_sw64(&g.tmRes2, r, rows, src.N, src.N, 128));
+    }
+    return DDB_OK;
+}
+
 static void plan_decode_geometry(GemmArgs& g, const ddb_model* m, float* img) {
     g.img = img;
     g.L = m->L, g.extras = m->extras, g.C = m->cfg.in_chans, g.P = m->cfg.patch_size;
@@ -894,6 +923,31 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                                                         c.depth, cp->exit_idx, cp->t_dev, cp->exit_log));
         LAUNCH_CHECK();
     }
+    const std::vector<ddb_model::HalfOps>* split = nullptr;
+    const int rows_h0 = (B / 2) * m->L;
+    if (g_mlp_split && pair && !cp && B >= 2) {
+        auto it = m->mlp_split.find(B);
+        if (it == m->mlp_split.end()) {
+            std::vector<ddb_model::HalfOps> v(c.depth);
+            for (int i = 0; i < c.depth; ++i) {
+                const BlockOps& op = m->ops[i];
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int row0 = hlf ? rows_h0 : 0, rows = hlf ? M - rows_h0 : rows_h0;
+                    // fc1: A = xm rows [row0, +rows), out = hidden rows [0, rows);  fc2: A = hidden rows [0, rows),
+                    // residual = xm rows [row0, ..), out = xo[i] rows [row0, ..)
+                    DDB_TRY(retarget_rows(v[i].fc1[hlf], op.fc1, m->xm->p, nullptr, nullptr, row0, rows));
+                    GemmArgs& g1 = v[i].fc1[hlf];
+                    DDB_TRY(make_tmap_bf16(&g1.tmOut, m->hbuf->p, rows, g1.N, g1.N, 128));
+                    DDB_TRY(make_tmap_bf16_sw64(&g1.tmOut2, m->hbuf->p, rows, g1.N, g1.N, 128));
+                    DDB_TRY(retarget_rows(v[i].fc2[hlf], op.fc2, m->hbuf->p, m->xo[i]->p, m->xm->p, row0, rows));
+                    GemmArgs& g2 = v[i].fc2[hlf];
+                    DDB_TRY(make_tmap_bf16(&g2.tmA0, m->hbuf->p, rows, g2.K0, g2.K0, 128));
+                }
+            }
+            it = m->mlp_split.emplace(B, std::move(v)).first;
+        }
+        split = &it->second;
+    }
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     for (int i = 0; i < c.depth; ++i) {
         const BlockOps& op = m->ops[i];
@@ -973,8 +1027,30 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
             kind = 1;
         }
-        DDB_TRY(run_gemm(op.fc1, EPI_LN_GELU, PC_GEMM_FC1, true, false));
-        DDB_TRY(run_gemm(op.fc2, EPI_RES, PC_GEMM_FC2, false, true));
+        if (split) {
+            // fc1 -> fc2 on the first half of the samples, then on the second half THROUGH THE SAME hidden rows: a half's
+            // hidden (67 MB at CelebA B = 128) stays in L2 between the two GEMMs, and the second half overwrites the
+            // first half's dirty lines before they are written back -- the 135 MB hidden never travels to HBM and back.
+            const ddb_model::HalfOps& ho = (*split)[i];
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const int row0 = hlf ? rows_h0 : 0;
+                GemmArgs g1 = ho.fc1[hlf], g2 = ho.fc2[hlf];
+                g1.stats = stp + (size_t)row0 * np_p, g1.nparts = np_p;
+                g2.stats_out = stp + (size_t)row0 * np_p;
+                if (g_alt_dir) g1.reverse = 0, g2.reverse = 1;
+                {
+                    ProfScope ps(PC_GEMM_FC1);
+                    DDB_TRY(launch_gemm2(g1, EPI_LN_GELU, nsm, st));
+                }
+                {
+                    ProfScope ps(PC_GEMM_FC2);
+                    DDB_TRY(launch_gemm2(g2, EPI_RES, nsm, st));
+                }
+            }
+        } else {
+            DDB_TRY(run_gemm(op.fc1, EPI_LN_GELU, PC_GEMM_FC1, true, false));
+            DDB_TRY(run_gemm(op.fc2, EPI_RES, PC_GEMM_FC2, false, true));
+        }
         kind = pair ? 2 : 0;
         cur = m->xo[i]->as<__nv_bfloat16>();
     }
@@ -1103,6 +1179,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "attn_discard")) {
         g_attn_discard = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "mlp_split")) {
+        g_mlp_split = value != 0;
         return DDB_OK;
     }
     if (!strcmp(name, "alt_dir")) {
