@@ -252,6 +252,7 @@ static int g_attn_discard = 1;  // ddb_set_option "attn_discard": discard consum
 static int g_mlp_split = 0;  // ddb_set_option "mlp_split": fc1 -> fc2 in two half batches (hidden stays in L2).  Parity-green but
                              // measured SLOWER at CelebA B = 128 (42.8 -> 41.7 images/s): two partial GEMM rounds and two more
                              // kernel boundaries per block cost more than the ~3 GB of HBM traffic per step it removes.
+static int g_l2_hints = 0;  // ddb_set_option "l2_hints": bit 0 fc2 A evict_first, bit 1 fc1 out evict_last, bit 2 qkv out evict_last
 static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
@@ -906,6 +907,9 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             g.reverse = rev ? 1 : 0;
             rev = !rev;
         }
+        if (cat == PC_GEMM_FC2 && (g_l2_hints & 1)) g.l2_hints |= 1;
+        if (cat == PC_GEMM_FC1 && (g_l2_hints & 2)) g.l2_hints |= 2;
+        if (cat == PC_GEMM_QKV && (g_l2_hints & 4)) g.l2_hints |= 2;
         if (cp && !g.m_dev) g.m_dev = een + 1;
         if (ln_in) {
             g.stats = kind == 2 ? stp : st2;
@@ -1183,6 +1187,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "mlp_split")) {
         g_mlp_split = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "l2_hints")) {
+        g_l2_hints = value;
         return DDB_OK;
     }
     if (!strcmp(name, "alt_dir")) {

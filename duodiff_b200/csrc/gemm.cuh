@@ -60,6 +60,9 @@ struct GemmArgs {
     // alternate the direction, so a consumer starts with the rows its producer wrote LAST -- the part of a tensor larger
     // than what the L2 can hold (qkv 101 MB, MLP hidden 135 MB of 126 MB) that is still resident.
     int reverse;
+    // L2 eviction priority of the CTA-pair kernel's TMA traffic: bit 0 = A loads evict_first (the operand is dead after
+    // this GEMM), bit 1 = output stores evict_last (the next kernel re-reads them)
+    int l2_hints;
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;

@@ -119,6 +119,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     if (warp == kProducerWarp) {
         // ===================================================================== TMA producer (both CTAs)
         if (lane == 0) {
+            const uint64_t pol_first = l2_policy_evict_first();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -132,9 +133,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                         if (leader) mbar_arrive(&full_bar[stage]);
                     } else {
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-                        if (kb < nkb0)
-                            tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &a.tmA0, fb, kb * Cfg::BK, row0);
-                        else
+                        if (kb < nkb0) {
+                            if (a.l2_hints & 1)
+                                tma_load_2d_2cta_hint(sA + stage * Cfg::A_BYTES, &a.tmA0, fb, kb * Cfg::BK, row0, pol_first);
+                            else
+                                tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &a.tmA0, fb, kb * Cfg::BK, row0);
+                        } else
                             tma_load_2d_2cta(sA + stage * Cfg::A_BYTES, &a.tmA1, fb, (kb - nkb0) * Cfg::BK, row0);
                         tma_load_2d_2cta(sB + stage * Cfg::B_BYTES, BN == 256 ? &a.tmB2 : &a.tmB3, fb, kb * Cfg::BK,
                                          wrow0);
@@ -407,6 +411,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 if (et == 0 && traffic) {
                     if (a.embed_mode)
                         tma_store_3d(&a.tmOut, sbuf, col0, (int)rank * 128, m_blk);  // sample m_blk, patches rank*128..
+                    else if (a.l2_hints & 2)
+                        tma_store_2d_hint(&a.tmOut, sbuf, col0, row0, l2_policy_evict_last());
                     else
                         tma_store_2d(&a.tmOut, sbuf, col0, row0);
                     tma_store_commit();

@@ -124,6 +124,26 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// L2 eviction-priority policies for TMA traffic (createpolicy): evict_first for operands that are dead after this read,
+// evict_last for tensors the next kernel re-reads.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, const void* smem_src, int c0, int c1,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // Every kernel of the sampling step is launched with programmaticStreamSerialization: it may become resident while its
 // predecessor is still draining.  pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as this
@@ -296,6 +316,14 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
                  : "memory");
 }
 // TMA load into this CTA's smem whose completion bytes are credited to the leader CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2cta_hint(void* smem_dst, const CUtensorMap* tm, uint32_t leader_bar, int c0,
+                                                      int c1, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorMap* tm, uint32_t leader_bar, int c0,
                                                  int c1) {
     asm volatile(
