@@ -226,6 +226,28 @@ def test_gemm_variants_agree_on_the_forward(dev):
     assert rel_l2(a, b) <= EPS_REL_L2
 
 
+def test_scheduling_options_do_not_change_a_bit(dev):
+    """Alternating row direction, the q|k|v discard and the MLP half-batch split only change the ORDER in which tiles and
+    items are processed (and what stays in L2): the forward must be bit-identical with every combination."""
+    lib, L = _lib()
+    net, _sd, _spec = _model("celeba", 9, True, dev)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(21, 3, 64, 64, generator=g).to(dev)  # 21 x 257 rows: 22 row blocks, odd split 10 / 11 samples
+    t = torch.full((21,), 321.0, device=dev)
+    base = net(x, t)
+    defaults = {b"alt_dir": 1, b"attn_discard": 1, b"mlp_split": 0}
+    try:
+        for opts in ({b"alt_dir": 0}, {b"attn_discard": 0}, {b"alt_dir": 0, b"attn_discard": 0}, {b"mlp_split": 1},
+                     {b"mlp_split": 1, b"alt_dir": 0}):
+            for k, v in {**defaults, **opts}.items():
+                lib.check(L.ddb_set_option(k, v))
+            assert torch.equal(net(x, t), base), opts
+    finally:
+        for k, v in defaults.items():
+            lib.check(L.ddb_set_option(k, v))
+    assert torch.equal(net(x, t), base)
+
+
 def test_batch_invariance(dev):
     """Row b of a batched forward equals the same sample run alone (needed for N-GPU == 1-GPU sharding parity)."""
     net, sd, spec = _model("celeba_3", 3, True, dev)
