@@ -235,10 +235,11 @@ def test_scheduling_options_do_not_change_a_bit(dev):
     x = torch.randn(21, 3, 64, 64, generator=g).to(dev)  # 21 x 257 rows: 22 row blocks, odd split 10 / 11 samples
     t = torch.full((21,), 321.0, device=dev)
     base = net(x, t)
-    defaults = {b"alt_dir": 1, b"attn_discard": 1, b"mlp_split": 0}
+    defaults = {b"alt_dir": 1, b"attn_discard": 1, b"mlp_split": 0, b"gemm_ts": 0}
     try:
+        # (gemm_ts: the K <= 512 GEMMs with the A panel resident in TMEM accumulate in the same order -> same bits)
         for opts in ({b"alt_dir": 0}, {b"attn_discard": 0}, {b"alt_dir": 0, b"attn_discard": 0}, {b"mlp_split": 1},
-                     {b"mlp_split": 1, b"alt_dir": 0}):
+                     {b"mlp_split": 1, b"alt_dir": 0}, {b"gemm_ts": 1}, {b"gemm_ts": 1, b"alt_dir": 0}):
             for k, v in {**defaults, **opts}.items():
                 lib.check(L.ddb_set_option(k, v))
             assert torch.equal(net(x, t), base), opts
