@@ -253,6 +253,7 @@ static int g_mlp_split = 0;  // ddb_set_option "mlp_split": fc1 -> fc2 in two ha
                              // measured SLOWER at CelebA B = 128 (42.8 -> 41.7 images/s): two partial GEMM rounds and two more
                              // kernel boundaries per block cost more than the ~3 GB of HBM traffic per step it removes.
 static int g_l2_hints = 0;  // ddb_set_option "l2_hints": bit 0 fc2 A evict_first, bit 1 fc1 out evict_last, bit 2 qkv out evict_last
+static int g_gemm_ln_cfg = 0;  // ddb_set_option "gemm_ln_cfg": 1 = 5 operand stages + 1 staging buffer per warpgroup for qkv / fc1
 static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
@@ -335,8 +336,12 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
         case EPI_BIAS:
             return stats ? launch_gemm2_t<EPI_BIAS, true, 5, 2>(a, num_sms, st)
                          : launch_gemm2_t<EPI_BIAS, false, 5, 2>(a, num_sms, st);
-        case EPI_LN: return launch_gemm2_t<EPI_LN, false, 4, 2>(a, num_sms, st);
-        case EPI_LN_GELU: return launch_gemm2_t<EPI_LN_GELU, false, 4, 2>(a, num_sms, st);
+        case EPI_LN:
+            if (g_gemm_ln_cfg == 1) return launch_gemm2_t<EPI_LN, false, 5, 1>(a, num_sms, st);
+            return launch_gemm2_t<EPI_LN, false, 4, 2>(a, num_sms, st);
+        case EPI_LN_GELU:
+            if (g_gemm_ln_cfg == 1) return launch_gemm2_t<EPI_LN_GELU, false, 5, 1>(a, num_sms, st);
+            return launch_gemm2_t<EPI_LN_GELU, false, 4, 2>(a, num_sms, st);
         case EPI_RES:
             if (short_k)
                 return stats ? launch_gemm2_t<EPI_RES, true, 4, 3>(a, num_sms, st)
@@ -1191,6 +1196,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "l2_hints")) {
         g_l2_hints = value;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "gemm_ln_cfg")) {
+        g_gemm_ln_cfg = value;
         return DDB_OK;
     }
     if (!strcmp(name, "alt_dir")) {

@@ -19,11 +19,13 @@ ap.add_argument("--pdl", type=int, default=1)
 ap.add_argument("--bn128", type=int, default=0)
 ap.add_argument("--ts", type=int, default=1)
 ap.add_argument("--n", type=int, default=20)
+ap.add_argument("--lncfg", type=int, default=0)
 a = ap.parse_args()
 L = _lib.load()
 _lib.check(L.ddb_set_option(b"pdl", a.pdl))
 _lib.check(L.ddb_set_option(b"gemm_bn128", a.bn128))
 _lib.check(L.ddb_set_option(b"gemm_ts", a.ts))
+_lib.check(L.ddb_set_option(b"gemm_ln_cfg", a.lncfg))
 dev = torch.device("cuda:0")
 M, D = a.M, a.D
 shapes = [("qkv", 3 * D, D, 0, 1), ("proj", D, D, 0, 3), ("fc1", 4 * D, D, 0, 2), ("fc2", D, 4 * D, 0, 3),
