@@ -61,21 +61,23 @@ class FrozenAutoencoderKL:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         used = {k: v for k, v in state_dict.items() if k.startswith("decoder.") or k.startswith("post_quant_conv.")}
-        keep, arr = [], (_lib.Tensor * len(used))()
-        for i, (name, t) in enumerate(used.items()):
-            t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
-            keep.append(t)
-            arr[i] = _lib.Tensor(name.encode(), t.data_ptr(), t.numel())
-        torch.cuda.synchronize()
-        handle = C.c_void_p()
-        _lib.check(self.lib.ddb_ae_create(C.byref(self.cfg), arr, len(used), C.byref(handle)))
-        self.handle = handle
-        del keep
+        with torch.cuda.device(dev):
+            keep, arr = [], (_lib.Tensor * len(used))()
+            for i, (name, t) in enumerate(used.items()):
+                t = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(t)
+                arr[i] = _lib.Tensor(name.encode(), t.data_ptr(), t.numel())
+            torch.cuda.synchronize(dev)
+            handle = C.c_void_p()
+            _lib.check(self.lib.ddb_ae_create(C.byref(self.cfg), arr, len(used), C.byref(handle)))
+            self.handle = handle
+            del keep
 
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
-            self.lib.ddb_ae_destroy(h)
+            with torch.cuda.device(self.device):
+                self.lib.ddb_ae_destroy(h)
             self.handle = None
 
     # nn.Module surface the reference's callers touch
@@ -91,6 +93,8 @@ class FrozenAutoencoderKL:
     def _check(self, z):
         if not (z.is_cuda and z.dtype == torch.float32 and z.dim() == 4):
             raise _lib.DuoDiffError("z must be a CUDA float32 tensor [B, z_channels, r, r]")
+        if z.device != self.device:
+            raise _lib.DuoDiffError(f"z is on {z.device} but the autoencoder lives on {self.device}")
         if tuple(z.shape[1:]) != (self.z_channels, self.z_res, self.z_res):
             raise _lib.DuoDiffError(f"z has shape {tuple(z.shape)}, autoencoder expects "
                                     f"[B,{self.z_channels},{self.z_res},{self.z_res}]")
@@ -100,8 +104,9 @@ class FrozenAutoencoderKL:
         """autoencoder.py:486-490: ``decoder(post_quant_conv(z / scale_factor))`` -> [B, out_ch, res, res] fp32."""
         z = self._check(z)
         out = torch.empty(z.shape[0], self.out_ch, self.resolution, self.resolution, device=z.device)
-        _lib.check(self.lib.ddb_ae_decode(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(),
-                                          _lib.current_stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_ae_decode(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(),
+                                              _lib.current_stream_ptr()))
         return out
 
     def forward(self, inputs, fn):  # autoencoder.py:492-500
@@ -122,8 +127,9 @@ class FrozenAutoencoderKL:
         out = torch.empty(z.shape[0], self.out_ch, self.resolution, self.resolution, device=z.device)
         n = len(self.PROF_CATEGORIES)
         ms, fl = (C.c_float * n)(), (C.c_double * n)()
-        _lib.check(self.lib.ddb_ae_profile_decode(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(), ms, fl,
-                                                  _lib.current_stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_ae_profile_decode(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(), ms, fl,
+                                                      _lib.current_stream_ptr()))
         return {k: dict(ms=float(ms[i]), flops=float(fl[i])) for i, k in enumerate(self.PROF_CATEGORIES)}
 
     def ops(self):
@@ -141,8 +147,9 @@ class FrozenAutoencoderKL:
         name, c, h, w, f32 = self.ops()[op_index]
         out = torch.empty(z.shape[0], self.out_ch, self.resolution, self.resolution, device=z.device)
         dump = torch.empty(z.shape[0], h, w, c, device=z.device, dtype=torch.float32 if f32 else torch.bfloat16)
-        _lib.check(self.lib.ddb_ae_decode_debug(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(), op_index,
-                                                dump.data_ptr(), _lib.current_stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_ae_decode_debug(self.handle, z.data_ptr(), z.shape[0], out.data_ptr(), op_index,
+                                                    dump.data_ptr(), _lib.current_stream_ptr()))
         return out, dump.float().permute(0, 3, 1, 2).contiguous()
 
 

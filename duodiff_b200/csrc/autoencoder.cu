@@ -160,11 +160,11 @@ int tile_shape(int H, int W, int* BW, int* BH) {
 
 template <int BN, int EPI, int MT = 1>
 int launch_conv_t(const ConvArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static ddb_host::DeviceOnce configured;
     auto kfn = conv_igemm_kernel<BN, EPI, MT>;
-    if (!configured) {
+    if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, MT>::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     const long long units = (long long)a.B * ((a.H * a.W) >> 7) * (a.subpixel ? 4 : 1) / MT * (a.N / BN);
     const int grid = units < num_sms ? (int)units : num_sms;

@@ -16,12 +16,23 @@
 
 #include "../../include/duodiff_b200.h"
 #include "attention.cuh"
-#include "attention2.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
-#include "gemm3.cuh"
 #include "host_common.h"
+// Measured-and-rejected kernel variants (A-in-TMEM GEMM, two-threads-per-row attention, generic mma.sync attention,
+// fp32-FMA token assembly, single-CTA GEMM for the block linears) are only part of -DDDB_EXPERIMENTAL builds; the
+// product library contains the path that runs.
+#ifdef DDB_EXPERIMENTAL
+#include "experimental/attention2.cuh"
+#include "experimental/attention_mma.cuh"
+#include "experimental/embed_tokens.cuh"
+#include "experimental/gemm3.cuh"
+#define DDB_NEEDS_EXPERIMENTAL(what) ((void)0)
+#else
+#define DDB_NEEDS_EXPERIMENTAL(what) \
+    return fail(DDB_ERR_INVALID, "%s is an experimental variant: rebuild with DDB_EXPERIMENTAL=1", what)
+#endif
 
 using namespace ddb;
 
@@ -62,8 +73,9 @@ static int fail(int code, const char* fmt, ...) {
 // stream around every kernel and accumulated per category.
 enum ProfCat : int {
     PC_EMBED = 0, PC_LN_STATS, PC_GEMM_QKV, PC_ATTENTION, PC_GEMM_PROJ, PC_GEMM_FC1, PC_GEMM_FC2, PC_GEMM_SKIP,
-    PC_GEMM_DECODE, PC_CONV, PC_EE_OTHER, PC_DDPM, PC_COUNT
+    PC_GEMM_DECODE, PC_CONV, PC_EE_OTHER, PC_DDPM, PC_TAIL, PC_COUNT
 };
+static_assert(PC_COUNT == DDB_PROF_CATEGORIES, "include/duodiff_b200.h lists the categories");
 struct Profiler {
     bool active = false;
     cudaStream_t st = nullptr;
@@ -87,7 +99,7 @@ struct Profiler {
         if (active) cudaEventRecord(next(), st);
     }
 };
-static Profiler g_prof;
+static thread_local Profiler g_prof;  // per calling thread: ddb_profile_forward() of distinct handles may run concurrently
 struct ProfScope {
     explicit ProfScope(int cat) { g_prof.begin(cat); }
     ~ProfScope() { g_prof.end(); }
@@ -205,7 +217,10 @@ int encode_bf16_sw128(CUtensorMap* tm, const void* base, int rank, const unsigne
 }  // namespace ddb_host
 
 // ------------------------------------------------------------------------------------------------ launches
-static int g_use_pdl = 1;
+// ---- process-wide runtime options (ddb_set_option).  They are A/B switches for measurements, read when a kernel is
+// launched or a step graph is captured; g_option_epoch invalidates captured graphs when one of them changes.
+static std::atomic<int> g_option_epoch{0};
+static std::atomic<int> g_use_pdl{1};
 namespace ddb_host {
 int use_pdl() { return g_use_pdl; }
 }  // ddb_set_option "pdl": programmatic dependent launch between the kernels of a step
@@ -230,11 +245,11 @@ static cudaError_t launch_pdl(void (*kfn)(KArgs...), dim3 grid, dim3 block, size
 // ------------------------------------------------------------------------------------------------ GEMM launch
 template <int BN, int EPI>
 static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static ddb_host::DeviceOnce configured;
     auto kfn = gemm_tcgen05_kernel<BN, EPI>;
-    if (!configured) {
+    if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
-        configured = true;
+        configured.mark();
     }
     const int tiles = ((a.M + 127) / 128) * (a.N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -244,28 +259,28 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     return DDB_OK;
 }
 // runtime options (ddb_set_option): gemm_variant 2 = CTA-pair kernel (default), 1 = single-CTA kernel
-static int g_gemm_variant = 2;
-static int g_gemm_debug = 0;
-static long long* g_gemm_trace = nullptr;  // bench-only (ddb_debug_set_ptr "gemm_trace")
+static std::atomic<int> g_gemm_variant{2};
+static std::atomic<int> g_gemm_debug{0};
+static std::atomic<long long*> g_gemm_trace{nullptr};  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
-static int g_attn_discard = 1;  // ddb_set_option "attn_discard": discard consumed q|k|v lines from L2 (attention.cuh)
-static int g_mlp_split = 0;  // ddb_set_option "mlp_split": fc1 -> fc2 in two half batches (hidden stays in L2).  Parity-green but
+static std::atomic<int> g_attn_discard{1};  // ddb_set_option "attn_discard": discard consumed q|k|v lines from L2 (attention.cuh)
+static std::atomic<int> g_mlp_split{0};  // ddb_set_option "mlp_split": fc1 -> fc2 in two half batches (hidden stays in L2).  Parity-green but
                              // measured SLOWER at CelebA B = 128 (42.8 -> 41.7 images/s): two partial GEMM rounds and two more
                              // kernel boundaries per block cost more than the ~3 GB of HBM traffic per step it removes.
-static int g_l2_hints = 0;  // ddb_set_option "l2_hints": bit 0 fc2 A evict_first, bit 1 fc1 out evict_last, bit 2 qkv out evict_last
-static int g_gemm_ln_cfg = 0;  // ddb_set_option "gemm_ln_cfg": 1 = 5 operand stages + 1 staging buffer per warpgroup for qkv / fc1
-static int g_alt_dir = 1;  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
-static int g_gemm_bn128 = 0;  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
+static std::atomic<int> g_l2_hints{0};  // ddb_set_option "l2_hints": bit 0 fc2 A evict_first, bit 1 fc1 out evict_last, bit 2 qkv out evict_last
+static std::atomic<int> g_gemm_ln_cfg{0};  // ddb_set_option "gemm_ln_cfg": 1 = 5 operand stages + 1 staging buffer per warpgroup for qkv / fc1
+static std::atomic<int> g_alt_dir{1};  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
+static std::atomic<int> g_gemm_bn128{0};  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
 template <int EPI, bool STATS, int STAGES, int NBUF, int BN = 256>
 static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static ddb_host::DeviceOnce configured;
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
     constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN, BN>::SMEM_BYTES;
     auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF, BN>;
-    if (!configured) {
+    if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        configured = true;
+        configured.mark();
     }
     const int tiles = ((a.M + 255) / 256) * (a.N / BN);
     if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
@@ -277,17 +292,18 @@ static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     LAUNCH_CHECK();
     return DDB_OK;
 }
-// CTA-pair GEMM with the A panel resident in TMEM (gemm3.cuh): K <= 512, one K source, 32-column SWIZZLE_64B output maps
-static int g_gemm_ts = 0;  // ddb_set_option "gemm_ts": measured no faster than gemm2 (the MMA takes ~165 clk in SS and TS form alike)
+// CTA-pair GEMM with the A panel resident in TMEM (experimental/gemm3.cuh): K <= 512, one K source, 32-column SWIZZLE_64B output maps
+static std::atomic<int> g_gemm_ts{0};
+#ifdef DDB_EXPERIMENTAL  // ddb_set_option "gemm_ts": measured no faster than gemm2 (the MMA takes ~165 clk in SS and TS form alike)
 template <int EPI, bool STATS>
 static int launch_gemm3_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static ddb_host::DeviceOnce configured;
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
     constexpr int kSmem = Gemm3Cfg<8, kLN>::SMEM_BYTES;
     auto kfn = gemm3_tcgen05_kernel<EPI, STATS, 8>;
-    if (!configured) {
+    if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        configured = true;
+        configured.mark();
     }
     const int tiles = ((a.M + 255) / 256) * (a.N / 256);
     if (g_gemm_debug) const_cast<GemmArgs&>(a).debug = g_gemm_debug;
@@ -299,6 +315,7 @@ static int launch_gemm3_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     LAUNCH_CHECK();
     return DDB_OK;
 }
+#endif
 
 // CTA-pair GEMM: a.tmB2 must have been encoded with a 128-row box.  Pipeline shape per epilogue:
 //   LN / LN+GELU (K = embed_dim, epilogue-heavy): 4 operand stages, aux-staged row statistics + bias + colsum
@@ -307,6 +324,7 @@ static int launch_gemm3_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     const bool stats = a.stats_out != nullptr;
     const bool short_k = (a.K0 + a.K1) <= 512;
+#ifdef DDB_EXPERIMENTAL
     if (g_gemm_ts && short_k && a.K1 == 0 && !a.embed_mode) {
         switch (epi) {
             case EPI_LN: return launch_gemm3_t<EPI_LN, false>(a, num_sms, st);
@@ -317,6 +335,7 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
             default: break;
         }
     }
+#endif
     // Wave quantisation: with 256x256 tiles an N = 512 GEMM at M = 32 896 has 258 tiles for 74 CTA pairs (3.49 -> 4
     // rounds); 256x128 tiles give 516 (6.97 -> 7 half-size rounds).  Used whenever it removes at least 5 % of the
     // rounds' work.
@@ -324,6 +343,7 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
         const int clusters = num_sms / 2, mb = (a.M + 255) / 256;
         const int t256 = mb * (a.N / 256), t128 = mb * (a.N / 128);
         const double r256 = (double)((t256 + clusters - 1) / clusters), r128 = 0.5 * ((t128 + clusters - 1) / clusters);
+#ifdef DDB_EXPERIMENTAL
         if (g_gemm_bn128 && a.N % 128 == 0 && r128 < 0.95 * r256 && (epi == EPI_BIAS || epi == EPI_RES)) {
             if (epi == EPI_BIAS)
                 return stats ? launch_gemm2_t<EPI_BIAS, true, 6, 2, 128>(a, num_sms, st)
@@ -331,16 +351,23 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
             return stats ? launch_gemm2_t<EPI_RES, true, 6, 2, 128>(a, num_sms, st)
                          : launch_gemm2_t<EPI_RES, false, 6, 2, 128>(a, num_sms, st);
         }
+#else
+        (void)r256, (void)r128;
+#endif
     }
     switch (epi) {
         case EPI_BIAS:
             return stats ? launch_gemm2_t<EPI_BIAS, true, 5, 2>(a, num_sms, st)
                          : launch_gemm2_t<EPI_BIAS, false, 5, 2>(a, num_sms, st);
         case EPI_LN:
+#ifdef DDB_EXPERIMENTAL
             if (g_gemm_ln_cfg == 1) return launch_gemm2_t<EPI_LN, false, 5, 1>(a, num_sms, st);
+#endif
             return launch_gemm2_t<EPI_LN, false, 4, 2>(a, num_sms, st);
         case EPI_LN_GELU:
+#ifdef DDB_EXPERIMENTAL
             if (g_gemm_ln_cfg == 1) return launch_gemm2_t<EPI_LN_GELU, false, 5, 1>(a, num_sms, st);
+#endif
             return launch_gemm2_t<EPI_LN_GELU, false, 4, 2>(a, num_sms, st);
         case EPI_RES:
             if (short_k)
@@ -352,15 +379,19 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
     return fail(DDB_ERR_INVALID, "unknown CTA-pair GEMM epilogue %d", epi);
 }
 
+// single-CTA kernel (gemm.cuh): the narrow-N decode head of the model path; the 128x256 variants for the block linears
+// (gemm_variant = 1) only exist in experimental builds
 static int launch_gemm(const GemmArgs& a, int epi, int num_sms, cudaStream_t st) {
     switch (epi) {
+#ifdef DDB_EXPERIMENTAL
         case EPI_BIAS: return launch_gemm_t<256, EPI_BIAS>(a, num_sms, st);
         case EPI_LN: return launch_gemm_t<256, EPI_LN>(a, num_sms, st);
         case EPI_LN_GELU: return launch_gemm_t<256, EPI_LN_GELU>(a, num_sms, st);
         case EPI_RES: return launch_gemm_t<256, EPI_RES>(a, num_sms, st);
+#endif
         case EPI_DECODE: return launch_gemm_t<64, EPI_DECODE>(a, num_sms, st);
     }
-    return fail(DDB_ERR_INVALID, "unknown GEMM epilogue %d", epi);
+    return fail(DDB_ERR_INVALID, "single-CTA GEMM epilogue %d is not part of this build", epi);
 }
 
 static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_dev, float2* stats, const float* pw,
@@ -392,44 +423,54 @@ static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* 
     DDB_TRY(make_tmap_bf16_3d(&a.tmOut, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 128));
     return DDB_OK;
 }
-static long long* g_attn_trace = nullptr;  // bench-only (ddb_debug_set_ptr "attn_trace")
+static std::atomic<long long*> g_attn_trace{nullptr};  // bench-only (ddb_debug_set_ptr "attn_trace")
 // persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
-static int g_attn_x2 = 0;  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
+static std::atomic<int> g_attn_x2{0};  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
 static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, int force_x2 = -1) {
-    static bool configured = false;
-    if (!configured) {
+    static ddb_host::DeviceOnce configured;
+    if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ATT3_SMEM));
+#ifdef DDB_EXPERIMENTAL
         CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       ATT4_SMEM));
-        configured = true;
+#endif
+        configured.mark();
     }
     if (B <= 0) return DDB_OK;
     a.B = B;
     a.trace = g_attn_trace;
     const int items = B * a.H;
     const dim3 grid(items < num_sms ? items : num_sms);
-    if (force_x2 >= 0 ? force_x2 != 0 : g_attn_x2 != 0)
+    if (force_x2 >= 0 ? force_x2 != 0 : g_attn_x2 != 0) {
+#ifdef DDB_EXPERIMENTAL
         CUDA_TRY(launch_pdl(attention_tcgen05_x2_kernel, grid, dim3(ATT4_THREADS), ATT4_SMEM, st, a));
-    else
+#else
+        DDB_NEEDS_EXPERIMENTAL("attn_x2 (two softmax threads per query row)");
+#endif
+    } else {
         CUDA_TRY(launch_pdl(attention_tcgen05_kernel, grid, dim3(ATT3_THREADS), ATT3_SMEM, st, a));
+    }
     LAUNCH_CHECK();
     return DDB_OK;
 }
 
+// generic-L mma.sync attention (experimental builds only: no reference config has L != 256 + extras)
 static int launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int L, int H, cudaStream_t st) {
-    static int configured_bytes = 0;
+#ifdef DDB_EXPERIMENTAL
     const int Lp = (L + 15) & ~15;
     const int smem = 2 * Lp * 128;
     if (smem > 227 * 1024) return fail(DDB_ERR_INVALID, "sequence length %d too long for the resident-KV kernel", L);
-    if (smem > configured_bytes) {
-        CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_bytes = smem;
-    }
+    CUDA_TRY(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (B <= 0) return DDB_OK;
     attention_mma_kernel<<<B * H, ATT_THREADS, smem, st>>>(qkv, out, L, H, 0.125f * 1.4426950408889634f);
     LAUNCH_CHECK();
     return DDB_OK;
+#else
+    (void)qkv, (void)out, (void)B, (void)H, (void)st;
+    return fail(DDB_ERR_INVALID, "attention with L = %d needs the generic mma.sync kernel: rebuild with DDB_EXPERIMENTAL=1 "
+                                 "(the model path needs L = 256 + {1, 2})", L);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ model
@@ -808,7 +849,8 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
             bl.p[n++] = reinterpret_cast<__nv_bfloat16*>(cur_in);
             for (int k = 0; k <= last_skip; ++k) {
                 if (m->xo[k]->p == cur_in) continue;
-                if (n >= 8) return fail(DDB_ERR_INVALID, "depth %d needs more than 8 live buffers", cfg->depth);
+                if (n >= EE_MAX_LIVE)
+                    return fail(DDB_ERR_INVALID, "depth %d needs more than %d live buffers", cfg->depth, EE_MAX_LIVE);
                 bl.p[n++] = m->xo[k]->as<__nv_bfloat16>();
             }
             m->ee_live_n[i] = n;
@@ -844,13 +886,53 @@ struct EeCompact {
     float* score_mean_log; // [1000,depth] by t (or null)
 };
 
+// Inside the sampler (plain U-ViT path) a step is fused at both ends: the previous step's tail kernel has already
+// written this forward's patch matrix and time / label token rows, and this forward ends in step_tail_kernel (3x3
+// conv + DDPM update + the head of the next step) instead of conv3x3.  `tail` carries that kernel's arguments.
+struct StepFuse {
+    TailArgs tail;
+};
+static int launch_patch_gather(const ddb_model* m, const float* x, int B, cudaStream_t st) {
+    const ddb_uvit_config& c = m->cfg;
+    const size_t n_thr = (size_t)B * c.in_chans * c.img_size * (c.img_size / c.patch_size);
+    CUDA_TRY(launch_pdl(patch_gather_kernel, dim3((unsigned)((n_thr + 255) / 256)), dim3(256), 0, st, x,
+                        m->a_patch->as<__nv_bfloat16>(), B, (int)c.in_chans, (int)c.img_size, (int)c.img_size,
+                        (int)c.patch_size));
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+static int launch_token_extras(const ddb_model* m, const float* t_vec, const int* t_dev, const int64_t* y, int B,
+                               cudaStream_t st) {
+    CUDA_TRY(launch_pdl(token_extras_kernel, dim3(B), dim3(256), 0, st, t_vec, t_dev,
+                        reinterpret_cast<const long long*>(y), (const float*)m->pos->as<float>(),
+                        (const float*)(m->label_emb ? m->label_emb->as<float>() : nullptr),
+                        m->x0->as<__nv_bfloat16>(), m->stats_p->as<float2>(), m->D, m->L, m->extras,
+                        (int)m->cfg.normalize_timesteps, (int)m->cfg.num_classes));
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+static int launch_step_tail(const ddb_model* m, const TailArgs& ta, int B, cudaStream_t st) {
+    const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
+    const size_t smem = (size_t)C * (CONV_BAND + 2) * (W + 8) * 4;
+    const dim3 grid(B * (H / CONV_BAND));
+    ProfScope ps(PC_TAIL);
+    switch (C) {
+        case 3: CUDA_TRY(launch_pdl(step_tail_kernel<3>, grid, dim3(256), smem, st, ta)); break;
+        case 4: CUDA_TRY(launch_pdl(step_tail_kernel<4>, grid, dim3(256), smem, st, ta)); break;
+        default: return fail(DDB_ERR_INVALID, "in_chans %d unsupported by the final 3x3 conv (3 or 4)", C);
+    }
+    LAUNCH_CHECK();
+    return DDB_OK;
+}
+
 static int forward_impl(ddb_model* m, const float* x, const float* t, const int64_t* y, int B, float* eps, bool ee,
-                        cudaStream_t st, const EeCompact* cp = nullptr) {
+                        cudaStream_t st, const EeCompact* cp = nullptr, const StepFuse* fuse = nullptr) {
     const ddb_uvit_config& c = m->cfg;
     if (B < 1 || B > c.max_batch) return fail(DDB_ERR_INVALID, "batch %d outside [1, max_batch=%d]", B, c.max_batch);
     if (m->extras == 2 && !y) return fail(DDB_ERR_INVALID, "class-conditional model needs y (models/uvit.py:361)");
     if (ee && !c.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
     if (cp && (!ee || B > 1024)) return fail(DDB_ERR_INVALID, "compaction needs an early-exit model and batch <= 1024");
+    if (fuse && (ee || g_gemm_variant != 2)) return fail(DDB_ERR_INVALID, "the fused step needs the plain CTA-pair path");
     const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
     // compaction: live sample / row counts are read from device memory by every kernel after the token assembly
     int* een = cp ? m->ee_n->as<int>() : nullptr;
@@ -863,21 +945,16 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         // tensor-core path: gather patches (bf16 hi + lo) -> CTA-pair GEMM (+bias +pos_embed, LayerNorm partials,
         // rows scattered into the token buffer) -> time / label token rows
         ProfScope ps(PC_EMBED);
-        const size_t n_thr = (size_t)B * c.in_chans * c.img_size * (c.img_size / c.patch_size);
-        CUDA_TRY(launch_pdl(patch_gather_kernel, dim3((unsigned)((n_thr + 255) / 256)), dim3(256), 0, st, x,
-                            m->a_patch->as<__nv_bfloat16>(), B, (int)c.in_chans, (int)c.img_size, (int)c.img_size,
-                            (int)c.patch_size));
-        LAUNCH_CHECK();
+        if (!fuse) DDB_TRY(launch_patch_gather(m, x, B, st));
         GemmArgs g = m->embed_gemm;
         g.M = B * m->Np;
         g.stats_out = stp;
         DDB_TRY(launch_gemm2(g, EPI_RES, nsm, st));
-        CUDA_TRY(launch_pdl(token_extras_kernel, dim3(B), dim3(256), 0, st, t, reinterpret_cast<const long long*>(y),
-                            (const float*)m->pos->as<float>(),
-                            (const float*)(m->label_emb ? m->label_emb->as<float>() : nullptr),
-                            m->x0->as<__nv_bfloat16>(), stp, D, m->L, m->extras, (int)c.normalize_timesteps));
-        LAUNCH_CHECK();
+        if (!fuse) DDB_TRY(launch_token_extras(m, t, nullptr, y, B, st));
     } else {
+#ifndef DDB_EXPERIMENTAL
+        DDB_NEEDS_EXPERIMENTAL("gemm_variant = 1 (fp32-FMA token assembly + single-CTA GEMMs)");
+#else
         // fp32 FMA path (single-CTA GEMM variant); writes one (mean, M2) per row
         ProfScope ps(PC_EMBED);
         const int grid = B * (c.img_size / c.patch_size);
@@ -898,6 +975,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         }
 #undef DDB_EMBED
         LAUNCH_CHECK();
+#endif
     }
 
     // LayerNorm statistics travel either as one (mean, M2) per row from ln_stats_kernel (kind 1) or as D/64
@@ -1069,6 +1147,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         kind = 1;
     }
     DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
+    if (fuse) return launch_step_tail(m, fuse->tail, B, st);
     if (cp)  // the samples that never left: full-model output, written to their original slots
         DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st, een, m->ee_slot->as<int>()));
     else
@@ -1109,19 +1188,31 @@ static int ee_forward_impl(ddb_model* m, const float* x, const float* t, const i
 struct ddb_sampler {
     ddb_model* early = nullptr;
     ddb_model* late = nullptr;
-    int switch_t = -1, B = 0, step_mode = 0, ee_mode = 0;
-    float ee_threshold = -1.f;
+    int switch_t = -1, B = 0, step_mode = 0, ee_mode = -1;
+    float ee_threshold = 0.f;  // any value is meaningful (eesampler.py:67); early exit is switched by ee_mode >= 0
     size_t n = 0;
-    Buf coef, t_dev, t_vec, eps, score_mean, x_buf, seed_dev, next_t;
-    std::vector<int> next_host, next_uploaded;  // successor table: staging / what the device currently holds
-    // One captured step per backbone.  The graph works on the sampler-owned x_buf and reads t and the Philox seed
-    // from device memory, so it is captured once and replayed for every call / seed / caller buffer.
+    unsigned long long noise_row0 = 0;  // index of this shard's first sample in the global batch (Philox keying)
+    Buf coef, t_dev, t_vec, eps, x_buf, seed_dev, next_t, ticket;
+    // sampler-owned staging, so that a captured step never depends on caller pointers: labels, early-exit logs
+    Buf y_buf, exit_log, score_log;
+    std::vector<int> next_host, next_uploaded;  // [0,1000) successor of t, [1000,2000) backbone of the successor step
+    // One captured step per backbone.  The graph works on the sampler-owned x_buf / y_buf / logs and reads t and the
+    // Philox key from device memory, so it is captured once and replayed for every call / seed / caller buffer.  It is
+    // re-captured when the injected-noise pointer, the presence of labels or a ddb_set_option() switch changes.
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_nodes[2] = {0, 0};
-    const void* graph_key[2][4] = {{nullptr}};
+    struct Key {
+        const void* z_all = nullptr;
+        int has_y = 0, epoch = -1;
+        bool operator==(const Key& o) const { return z_all == o.z_all && has_y == o.has_y && epoch == o.epoch; }
+    } graph_key[2];
+    bool early_exit() const { return ee_mode >= 0 && early->cfg.early_exit; }
 };
 
 __global__ void set_t_kernel(int* t_dev, int t) { *t_dev = t; }
+__global__ void set_seed_kernel(unsigned long long* p, unsigned long long seed, unsigned long long off4) {
+    p[0] = seed, p[1] = off4;
+}
 // eesampler.py:71  error_prediction_by_timestep[t] = classifier_outputs.mean(axis=1)[:depth]
 __global__ void score_mean_kernel(const float* __restrict__ scores, int depth, int B, const int* __restrict__ t_dev,
                                   float* __restrict__ out /*[1000,depth] by t*/) {
@@ -1132,43 +1223,85 @@ __global__ void score_mean_kernel(const float* __restrict__ scores, int depth, i
     if (threadIdx.x == 0) out[(size_t)(*t_dev) * depth + i] = s / (float)B;
 }
 
-// one sampling step on the stream: forward + update (+ bookkeeping). t comes from s->t_dev (device).
-static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, const int64_t* y, const float* z_all,
-                        unsigned long long seed, const unsigned long long* seed_dev, int t_host, float* eps_save,
-                        float* x_save, int32_t* exit_save, float* score_save, cudaStream_t st) {
+static void tail_target(TailTarget& tg, const ddb_model* m) {
+    tg.a_patch = m->a_patch->as<__nv_bfloat16>();
+    tg.tokens = m->x0->as<__nv_bfloat16>();
+    tg.stats_p = m->stats_p->as<float2>();
+    tg.pos = m->pos->as<float>();
+    tg.label_emb = m->label_emb ? m->label_emb->as<float>() : nullptr;
+    tg.P = m->cfg.patch_size, tg.D = m->D, tg.L = m->L, tg.extras = m->extras;
+    tg.normalize_t = m->cfg.normalize_timesteps, tg.num_classes = m->cfg.num_classes;
+}
+
+// One sampling step on the stream: forward + update + bookkeeping.  t comes from s->t_dev, the Philox key from
+// s->seed_dev (device memory), labels from s->y_buf.
+//   plain U-ViT:  embed GEMM -> blocks -> decode GEMM -> step_tail_kernel (conv + update + head of the next step)
+//   early exit:   fill_t -> EarlyExitUViT forward + selection -> ddpm_step -> next_t
+static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, bool has_y, const float* z_all, float* eps_save,
+                        float* x_save, cudaStream_t st) {
     const int B = s->B;
-    fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->t_dev->as<int>(), s->t_vec->as<float>(), B);
-    LAUNCH_CHECK();
-    float* eps = eps_save ? eps_save : s->eps->as<float>();
-    if (s->ee_threshold >= 0.f && m->cfg.early_exit) {
-        DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, nullptr,
-                                nullptr, nullptr, s->t_dev->as<int>(), exit_save, score_save, st));
-        if (score_save && s->ee_mode == 0) {
+    const int64_t* y = has_y ? s->y_buf->as<int64_t>() : nullptr;
+    if (s->early_exit() && m->cfg.early_exit) {
+        fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->t_dev->as<int>(), s->t_vec->as<float>(), B);
+        LAUNCH_CHECK();
+        float* eps = eps_save ? eps_save : s->eps->as<float>();
+        DDB_TRY(ee_forward_impl(m, x, s->t_vec->as<float>(), y, B, s->ee_threshold, s->ee_mode, eps, nullptr, nullptr,
+                                nullptr, s->t_dev->as<int>(), s->exit_log->as<int32_t>(), s->score_log->as<float>(),
+                                st));
+        if (s->ee_mode == 0) {
             score_mean_kernel<<<m->cfg.depth, 32, 0, st>>>(m->scores->as<float>(), m->cfg.depth, B,
-                                                           s->t_dev->as<int>(), score_save);
+                                                           s->t_dev->as<int>(), s->score_log->as<float>());
             LAUNCH_CHECK();
         }
-    } else {
-        DDB_TRY(forward_impl(m, x, s->t_vec->as<float>(), y, B, eps, false, st));
+        {
+            ProfScope ps(PC_DDPM);
+            CUDA_TRY(launch_pdl(ddpm_step_kernel, dim3((unsigned)((s->n / 4 + 255) / 256)), dim3(256), 0, st, x,
+                                (const float*)eps, z_all, s->n, s->n, (const float*)s->coef->as<float>(),
+                                (const int*)s->t_dev->as<int>(), 0, s->step_mode, 0ull,
+                                (const unsigned long long*)s->seed_dev->as<unsigned long long>(), x_save));
+            LAUNCH_CHECK();
+        }
+        next_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>(), s->next_t->as<int>());
+        LAUNCH_CHECK();
+        return DDB_OK;
     }
-    (void)t_host;
-    CUDA_TRY(launch_pdl(ddpm_step_kernel, dim3((unsigned)((s->n / 4 + 255) / 256)), dim3(256), 0, st, x,
-                        (const float*)eps, z_all, s->n, s->n, (const float*)s->coef->as<float>(),
-                        (const int*)s->t_dev->as<int>(), 0, s->step_mode, seed, seed_dev, x_save));
-    LAUNCH_CHECK();
-    next_t_kernel<<<1, 32, 0, st>>>(s->t_dev->as<int>(), s->next_t->as<int>());
-    LAUNCH_CHECK();
-    return DDB_OK;
+    StepFuse f;
+    memset(&f, 0, sizeof(f));
+    TailArgs& ta = f.tail;
+    ta.img_pre = m->img_pre->as<float>();
+    ta.conv_w = m->final_head.conv_w->as<float>(), ta.conv_b = m->final_head.conv_b->as<float>();
+    ta.x = x, ta.z_all = z_all, ta.coef = s->coef->as<float>();
+    ta.t_dev = s->t_dev->as<int>(), ta.next_t = s->next_t->as<int>();
+    ta.seed_dev = s->seed_dev->as<unsigned long long>();
+    ta.y = reinterpret_cast<const long long*>(y);
+    ta.eps_out = eps_save, ta.x_save = x_save;
+    ta.ticket = s->ticket->as<unsigned>();
+    ta.n = s->n, ta.H = m->cfg.img_size, ta.W = m->cfg.img_size, ta.mode = s->step_mode;
+    tail_target(ta.tgt[0], s->early);
+    tail_target(ta.tgt[1], s->late ? s->late : s->early);
+    return forward_impl(m, x, nullptr, y, B, nullptr, false, st, nullptr, &f);
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
-const char* ddb_version(void) { return "duodiff_b200 0.1.0 (sm_100a)"; }
+const char* ddb_version(void) {
+#ifdef DDB_EXPERIMENTAL
+    return "duodiff_b200 0.2.0 (sm_100a) +experimental";
+#else
+    return "duodiff_b200 0.2.0 (sm_100a)";
+#endif
+}
 const char* ddb_last_error(void) { return g_err; }
 int64_t ddb_launch_count(void) { return g_launches.load(); }
 int ddb_set_option(const char* name, int32_t value) {
     if (!name) return fail(DDB_ERR_INVALID, "null option name");
+    g_option_epoch.fetch_add(1);  // captured step graphs bake the options in: re-capture on the next run
+#ifndef DDB_EXPERIMENTAL
+    for (const char* ex : {"gemm_ts", "attn_x2", "gemm_bn128", "gemm_ln_cfg"})
+        if (!strcmp(name, ex) && value != 0) DDB_NEEDS_EXPERIMENTAL(name);
+    if (!strcmp(name, "gemm_variant") && value == 1) DDB_NEEDS_EXPERIMENTAL("gemm_variant = 1");
+#endif
     if (!strcmp(name, "gemm_variant")) {
         if (value != 1 && value != 2) return fail(DDB_ERR_INVALID, "gemm_variant must be 1 or 2");
         g_gemm_variant = value;
@@ -1299,7 +1432,12 @@ int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int3
     if (!early || !coef_host || !out) return fail(DDB_ERR_INVALID, "null argument");
     if (B < 1 || B > early->cfg.max_batch || (late && B > late->cfg.max_batch))
         return fail(DDB_ERR_INVALID, "batch %d exceeds a model's max_batch", B);
-    if (late && late->chw != early->chw) return fail(DDB_ERR_SHAPE, "early/late models disagree on C*H*W");
+    if (late && (late->cfg.in_chans != early->cfg.in_chans || late->cfg.img_size != early->cfg.img_size))
+        return fail(DDB_ERR_SHAPE, "early/late models disagree on the sample shape [C,H,W]");
+    if (ee_mode < -1 || ee_mode > 1) return fail(DDB_ERR_INVALID, "ee_mode must be -1 (off), 0 (simulate) or 1 (compact)");
+    if (ee_mode >= 0 && !early->cfg.early_exit)
+        return fail(DDB_ERR_INVALID, "early exit requested but the model was not created with early_exit=1");
+    if (step_mode < 0 || step_mode > 2) return fail(DDB_ERR_INVALID, "step_mode must be 0, 1 or 2");
     std::unique_ptr<ddb_sampler> s(new ddb_sampler());
     s->early = early, s->late = late, s->switch_t = switch_t, s->B = B, s->step_mode = step_mode;
     s->ee_threshold = ee_threshold, s->ee_mode = ee_mode;
@@ -1310,9 +1448,15 @@ int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int3
     DDB_TRY(new_buf(s->t_vec, (size_t)B * 4));
     DDB_TRY(new_buf(s->eps, s->n * 4));
     DDB_TRY(new_buf(s->x_buf, s->n * 4));
-    DDB_TRY(new_buf(s->seed_dev, 8));
-    DDB_TRY(new_buf(s->next_t, 1000 * 4));
-    s->next_host.assign(1000, 0);
+    DDB_TRY(new_buf(s->seed_dev, 16));
+    DDB_TRY(new_buf(s->next_t, 2000 * 4));
+    DDB_TRY(new_buf(s->ticket, 4));
+    DDB_TRY(new_buf(s->y_buf, (size_t)B * 8));
+    if (ee_mode >= 0) {
+        DDB_TRY(new_buf(s->exit_log, (size_t)1000 * B * 4));
+        DDB_TRY(new_buf(s->score_log, (size_t)1000 * early->cfg.depth * 4));
+    }
+    s->next_host.assign(2000, 0);
     *out = s.release();
     return DDB_OK;
 }
@@ -1323,12 +1467,18 @@ void ddb_sampler_destroy(ddb_sampler* s) {
         if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     delete s;
 }
+int ddb_sampler_set_noise_offset(ddb_sampler* s, uint64_t first_row) {
+    if (!s) return fail(DDB_ERR_INVALID, "null argument");
+    s->noise_row0 = first_row;
+    return DDB_OK;
+}
 
 // Runs the model at the timesteps t_list[0..n) (late[k] != 0: on the late backbone) with the sampler's update rule.
+// log_lo..log_hi: rows (timesteps) of the early-exit logs copied to the caller's buffers afterwards.
 static int sampler_run_impl(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
                             const int32_t* t_list, const uint8_t* late, int n, float* eps_trace_dev, float* x_trace_dev,
-                            int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph,
-                            cudaStream_t st) {
+                            int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int log_lo, int log_hi,
+                            int32_t use_graph, cudaStream_t st) {
     if (n <= 0) return DDB_OK;
     for (int k = 0; k < n; ++k) {
         if (t_list[k] < 0 || t_list[k] > 999) return fail(DDB_ERR_INVALID, "timestep %d outside [0, 999]", t_list[k]);
@@ -1336,47 +1486,64 @@ static int sampler_run_impl(ddb_sampler* s, float* x_dev, const int64_t* y_dev, 
     }
     if (use_graph && (eps_trace_dev || x_trace_dev))
         return fail(DDB_ERR_INVALID, "per-step eps/x traces need use_graph=0");
-    // the timestep sequence as a device-side successor table, so that a captured step needs no host argument
-    for (int k = 0; k < n; ++k) s->next_host[t_list[k]] = (k + 1 < n) ? t_list[k + 1] : t_list[k];
+    if ((exit_idx_trace_dev || score_mean_trace_dev) && !s->early_exit())
+        return fail(DDB_ERR_INVALID, "early-exit logs requested from a sampler without early exit");
+    const bool has_y = y_dev != nullptr;
+    if (!has_y && ((s->early->extras == 2) || (s->late && s->late->extras == 2)))
+        return fail(DDB_ERR_INVALID, "class-conditional model needs y (models/uvit.py:361)");
+    // the timestep sequence as device-side tables, so that a captured step needs no host argument: the successor of
+    // every t and the backbone the successor step runs on (the tail of a step prepares the head of the next one)
+    for (int k = 0; k < n; ++k) {
+        s->next_host[t_list[k]] = (k + 1 < n) ? t_list[k + 1] : t_list[k];
+        s->next_host[1000 + t_list[k]] = (k + 1 < n) ? (late[k + 1] ? 1 : 0) : (late[k] ? 1 : 0);
+    }
     if (s->next_host != s->next_uploaded) {  // unchanged for repeated runs of the same schedule: no host sync
-        CUDA_TRY(cudaMemcpyAsync(s->next_t->p, s->next_host.data(), 1000 * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpyAsync(s->next_t->p, s->next_host.data(), 2000 * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // the staging vector is pageable host memory owned by the handle
         s->next_uploaded = s->next_host;
     }
     set_t_kernel<<<1, 1, 0, st>>>(s->t_dev->as<int>(), t_list[0]);
     LAUNCH_CHECK();
+    set_seed_kernel<<<1, 1, 0, st>>>(s->seed_dev->as<unsigned long long>(), seed,
+                                     (unsigned long long)(s->noise_row0 * (s->early->chw / 4)));
+    LAUNCH_CHECK();
+    if (has_y) CUDA_TRY(cudaMemcpyAsync(s->y_buf->p, y_dev, (size_t)s->B * 8, cudaMemcpyDeviceToDevice, st));
+    // graph replay works on the sampler-owned copy of x; eager steps work in place
+    float* xw = x_dev;
+    if (use_graph) {
+        xw = s->x_buf->as<float>();
+        CUDA_TRY(cudaMemcpyAsync(xw, x_dev, s->n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (!s->early_exit()) {
+        // head of the first step (every later step's head is written by its predecessor's tail kernel)
+        ddb_model* m0 = late[0] ? s->late : s->early;
+        DDB_TRY(launch_patch_gather(m0, xw, s->B, st));
+        DDB_TRY(launch_token_extras(m0, nullptr, s->t_dev->as<int>(), has_y ? s->y_buf->as<int64_t>() : nullptr, s->B, st));
+    }
     if (!use_graph) {
         for (int k = 0; k < n; ++k) {
             ddb_model* m = late[k] ? s->late : s->early;
-            DDB_TRY(sampler_step(s, m, x_dev, y_dev, z_all_dev, seed, nullptr, t_list[k],
-                                 eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
-                                 x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr,
-                                 exit_idx_trace_dev, score_mean_trace_dev, st));
+            DDB_TRY(sampler_step(s, m, xw, has_y, z_all_dev, eps_trace_dev ? eps_trace_dev + (size_t)k * s->n : nullptr,
+                                 x_trace_dev ? x_trace_dev + (size_t)k * s->n : nullptr, st));
         }
-        return DDB_OK;
-    }
-    // ---- graph replay: one captured step per backbone; t, the seed and x live in sampler-owned device memory
-    float* xb = s->x_buf->as<float>();
-    unsigned long long* sd = s->seed_dev->as<unsigned long long>();
-    CUDA_TRY(cudaMemcpyAsync(xb, x_dev, s->n * 4, cudaMemcpyDeviceToDevice, st));
-    set_u64_kernel<<<1, 1, 0, st>>>(sd, seed);
-    LAUNCH_CHECK();
-    for (int which = 0; which < 2; ++which) {
-        ddb_model* m = which == 0 ? s->early : s->late;
-        if (!m) continue;
-        const void* key[4] = {y_dev, z_all_dev, exit_idx_trace_dev, score_mean_trace_dev};
-        if (s->graph[which] && memcmp(key, s->graph_key[which], sizeof(key)) != 0) {
-            cudaGraphExecDestroy(s->graph[which]);
-            s->graph[which] = nullptr;
-        }
-        if (!s->graph[which]) {
+    } else {
+        // ---- one captured step per backbone
+        ddb_sampler::Key key;
+        key.z_all = z_all_dev, key.has_y = has_y ? 1 : 0, key.epoch = g_option_epoch.load();
+        for (int which = 0; which < 2; ++which) {
+            ddb_model* m = which == 0 ? s->early : s->late;
+            if (!m) continue;
+            if (s->graph[which] && !(key == s->graph_key[which])) {
+                cudaGraphExecDestroy(s->graph[which]);
+                s->graph[which] = nullptr;
+            }
+            if (s->graph[which]) continue;
             cudaStream_t cs;
             CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
             cudaGraph_t g = nullptr;
             CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
             const long long before = g_launches.load();
-            int r = sampler_step(s, m, xb, y_dev, z_all_dev, 0, sd, 0, nullptr, nullptr, exit_idx_trace_dev,
-                                 score_mean_trace_dev, cs);
+            int r = sampler_step(s, m, xw, has_y, z_all_dev, nullptr, nullptr, cs);
             g_launches.store(before);  // captured, not executed: replays are counted below
             cudaError_t e = cudaStreamEndCapture(cs, &g);
             if (r != DDB_OK) {
@@ -1395,15 +1562,26 @@ static int sampler_run_impl(ddb_sampler* s, float* x_dev, const int64_t* y_dev, 
             cudaGraphDestroy(g);
             cudaStreamDestroy(cs);
             if (e != cudaSuccess) return fail(DDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
-            memcpy(s->graph_key[which], key, sizeof(key));
+            s->graph_key[which] = key;
         }
+        for (int k = 0; k < n; ++k) {
+            const int which = late[k] ? 1 : 0;
+            CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
+            g_launches.fetch_add(s->graph_nodes[which], std::memory_order_relaxed);
+        }
+        CUDA_TRY(cudaMemcpyAsync(x_dev, xw, s->n * 4, cudaMemcpyDeviceToDevice, st));
     }
-    for (int k = 0; k < n; ++k) {
-        const int which = late[k] ? 1 : 0;
-        CUDA_TRY(cudaGraphLaunch(s->graph[which], st));
-        g_launches.fetch_add(s->graph_nodes[which], std::memory_order_relaxed);
+    // early-exit logs: the rows of the timesteps this call covered, from the sampler-owned buffers
+    if (log_hi >= log_lo) {
+        const size_t rows = (size_t)(log_hi - log_lo + 1);
+        if (exit_idx_trace_dev)
+            CUDA_TRY(cudaMemcpyAsync(exit_idx_trace_dev + (size_t)log_lo * s->B, s->exit_log->as<int32_t>() + (size_t)log_lo * s->B,
+                                     rows * s->B * 4, cudaMemcpyDeviceToDevice, st));
+        const int depth = s->early->cfg.depth;
+        if (score_mean_trace_dev)
+            CUDA_TRY(cudaMemcpyAsync(score_mean_trace_dev + (size_t)log_lo * depth, s->score_log->as<float>() + (size_t)log_lo * depth,
+                                     rows * depth * 4, cudaMemcpyDeviceToDevice, st));
     }
-    CUDA_TRY(cudaMemcpyAsync(x_dev, xb, s->n * 4, cudaMemcpyDeviceToDevice, st));
     return DDB_OK;
 }
 
@@ -1419,7 +1597,8 @@ int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const fl
         late.push_back((s->late && t < s->switch_t) ? 1 : 0);  // sampler.py:135-136
     }
     return sampler_run_impl(s, x_dev, y_dev, z_all_dev, seed, ts.data(), late.data(), (int)ts.size(), eps_trace_dev,
-                            x_trace_dev, exit_idx_trace_dev, score_mean_trace_dev, use_graph, (cudaStream_t)stream);
+                            x_trace_dev, exit_idx_trace_dev, score_mean_trace_dev, t_last, t_first, use_graph,
+                            (cudaStream_t)stream);
 }
 
 int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
@@ -1427,7 +1606,29 @@ int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, con
                          float* x_trace_dev, int32_t use_graph, void* stream) {
     if (!s || !x_dev || !t_list_host || !late_host) return fail(DDB_ERR_INVALID, "null argument");
     return sampler_run_impl(s, x_dev, y_dev, z_all_dev, seed, t_list_host, late_host, n_steps, eps_trace_dev,
-                            x_trace_dev, nullptr, nullptr, use_graph, (cudaStream_t)stream);
+                            x_trace_dev, nullptr, nullptr, 0, -1, use_graph, (cudaStream_t)stream);
+}
+
+int ddb_sampler_profile_step(ddb_sampler* s, float* x_dev, const int64_t* y_dev, int32_t t, int32_t late,
+                             float* ms_host, int32_t* launches_host, void* stream) {
+    if (!s || !x_dev || !ms_host || !launches_host) return fail(DDB_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t tl[1] = {t};
+    const uint8_t lf[1] = {(uint8_t)(late ? 1 : 0)};
+    g_prof.active = true, g_prof.st = st, g_prof.used = 0;
+    g_prof.cats.clear();
+    int r = sampler_run_impl(s, x_dev, y_dev, nullptr, 0, tl, lf, 1, nullptr, nullptr, nullptr, nullptr, 0, -1, 0, st);
+    g_prof.active = false;
+    if (r != DDB_OK) return r;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < PC_COUNT; ++i) ms_host[i] = 0.f, launches_host[i] = 0;
+    for (size_t i = 0; i < g_prof.cats.size(); ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, g_prof.pool[2 * i], g_prof.pool[2 * i + 1]));
+        ms_host[g_prof.cats[i]] += ms;
+        launches_host[g_prof.cats[i]] += 1;
+    }
+    return DDB_OK;
 }
 
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
@@ -1446,6 +1647,9 @@ int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const
     if (!a0_dev || !w_dev || !out_dev) return fail(DDB_ERR_INVALID, "null argument");
     if (variant == 0) variant = g_gemm_variant;
     if (variant != 1 && variant != 2) return fail(DDB_ERR_INVALID, "variant must be 0, 1 or 2");
+#ifndef DDB_EXPERIMENTAL
+    if (variant == 1) DDB_NEEDS_EXPERIMENTAL("the single-CTA GEMM for the block linears");
+#endif
     if (stats_out_dev && (variant != 2 || (epi != EPI_BIAS && epi != EPI_RES)))
         return fail(DDB_ERR_INVALID, "stats_out needs the CTA-pair kernel with a bias or residual epilogue");
     if (epi < 0 || epi > EPI_RES) return fail(DDB_ERR_INVALID, "epi must be 0..3");

@@ -48,201 +48,7 @@ __global__ void transpose_pe_kernel(const float* __restrict__ W, int D, int pd, 
     }
 }
 
-// =====================================================================================================
-// Token assembly: patch embed (models/uvit.py:221-225) + time token (:95-115, :352-360) + label (:361-364)
-// + pos_embed (:365).  One CTA per (sample, patch row); the CTA with patch row 0 also writes the extras.
-// x_img [B,C,H,W] fp32 -> tokens [B*L, D] bf16.   Requires W/p == 16 patches per row (true for every config).
-// =====================================================================================================
-constexpr int EMB_TOK = 16;
-// PD = patch_dim (compile-time so the K loop unrolls and the W loads pipeline).  Each thread owns pairs of embedding
-// dims (e, e+1) for all 16 tokens of the patch row; the math is packed fp32x2 over token pairs.  The kernel also
-// writes the LayerNorm row statistics (mean, M2) of the bf16-rounded tokens for the first block's norm1, so no
-// separate statistics pass follows (shifted single-pass sums; shift = the token's dim-0 value).
-template <int PD>
-__global__ void __launch_bounds__(256, 2) embed_tokens_kernel(
-    const float* __restrict__ x_img, const float* __restrict__ tsteps, const long long* __restrict__ y,
-    const float* __restrict__ Wt /*[pd,D]*/, const float* __restrict__ pe_bias, const float* __restrict__ pos /*[L,D]*/,
-    const float* __restrict__ label_emb /*[classes,D] or null*/, __nv_bfloat16* __restrict__ tokens,
-    float2* __restrict__ stats /*[B*L] (mean, M2) or null*/, int C, int H, int W, int P, int D, int L, int extras,
-    int normalize_t) {
-    __shared__ __align__(16) float patch[PD * EMB_TOK];  // patchT[k][16 tokens]
-    __shared__ float shift[EMB_TOK];
-    __shared__ float red[2][8][EMB_TOK + 2];
-    const int Hp = H / P;
-    const int b = blockIdx.x / Hp, hh = blockIdx.x % Hp;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pdl_launch_dependents();
-    pdl_wait();  // x_img / tsteps come from the previous step's kernels
-    // gather: k = (c*P + p1)*P + p2 ; token ww ; pixel (c, hh*P+p1, ww*P+p2)
-    {
-        // C*P*W = PD*16 elements: all global loads are issued before the first shared-memory store
-        constexpr int NLD = (PD * EMB_TOK + 255) / 256;
-        float gv[NLD];
-#pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            const int i = threadIdx.x + j * 256;
-            const int col = i % W, rp = i / W;  // rp = c*P + p1
-            const int c = rp / P, p1 = rp % P;
-            gv[j] = (i < PD * EMB_TOK) ? __ldg(x_img + (((size_t)b * C + c) * H + hh * P + p1) * W + col) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < NLD; ++j) {
-            const int i = threadIdx.x + j * 256;
-            const int col = i % W, rp = i / W;
-            const int ww = col / P, p2 = col % P;
-            if (i < PD * EMB_TOK) patch[(rp * P + p2) * EMB_TOK + ww] = gv[j];
-        }
-    }
-    __syncthreads();
-    float s1[EMB_TOK], s2[EMB_TOK];
-#pragma unroll
-    for (int t = 0; t < EMB_TOK; ++t) s1[t] = s2[t] = 0.f;
-    bool first = true;
-    for (int e2 = threadIdx.x; e2 < D / 2; e2 += blockDim.x) {  // uniform trip count per warp; D/2 is a multiple of 128
-        const int e = e2 * 2;
-        f32x2 a0[EMB_TOK / 2], a1[EMB_TOK / 2];  // dim e / dim e+1, token pairs
-        const f32x2 b0 = f2_splat(pe_bias[e]), b1 = f2_splat(pe_bias[e + 1]);
-#pragma unroll
-        for (int t = 0; t < EMB_TOK / 2; ++t) a0[t] = b0, a1[t] = b1;
-        // W rows are prefetched one batch of 4 k ahead of the FMAs that use them
-        static_assert(PD % 4 == 0, "patch_dim must be a multiple of 4");
-        float2 wn[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) wn[u] = __ldg(reinterpret_cast<const float2*>(Wt + (size_t)u * D + e));
-#pragma unroll 1
-        for (int kb = 0; kb < PD; kb += 4) {
-            float2 wc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) wc[u] = wn[u];
-            if (kb + 4 < PD) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    wn[u] = __ldg(reinterpret_cast<const float2*>(Wt + (size_t)(kb + 4 + u) * D + e));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const f32x2 w0 = f2_splat(wc[u].x), w1 = f2_splat(wc[u].y);
-                const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(patch + (kb + u) * EMB_TOK);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const ulonglong2 pv = pr[q];  // tokens 4q..4q+3 as two packed pairs
-                    a0[2 * q] = f2_fma(pv.x, w0, a0[2 * q]);
-                    a0[2 * q + 1] = f2_fma(pv.y, w0, a0[2 * q + 1]);
-                    a1[2 * q] = f2_fma(pv.x, w1, a1[2 * q]);
-                    a1[2 * q + 1] = f2_fma(pv.y, w1, a1[2 * q + 1]);
-                }
-            }
-        }
-        float v0[EMB_TOK], v1[EMB_TOK];
-#pragma unroll
-        for (int t = 0; t < EMB_TOK / 2; ++t) {
-            f2_unpack(a0[t], v0[2 * t], v0[2 * t + 1]);
-            f2_unpack(a1[t], v1[2 * t], v1[2 * t + 1]);
-        }
-#pragma unroll
-        for (int t = 0; t < EMB_TOK; ++t) {
-            const int l = extras + hh * EMB_TOK + t;
-            const float2 pp = *reinterpret_cast<const float2*>(pos + (size_t)l * D + e);
-            const uint32_t pk = pack_bf16(v0[t] + pp.x, v1[t] + pp.y);
-            *reinterpret_cast<uint32_t*>(tokens + ((size_t)b * L + l) * D + e) = pk;
-            v0[t] = bf16_lo(pk), v1[t] = bf16_hi(pk);  // statistics of what the consumer will read
-        }
-        if (stats) {
-            if (first) {
-                if (threadIdx.x == 0) {
-#pragma unroll
-                    for (int t = 0; t < EMB_TOK; ++t) shift[t] = v0[t];
-                }
-                __syncthreads();
-                first = false;
-            }
-#pragma unroll
-            for (int t = 0; t < EMB_TOK; ++t) {
-                const float c = shift[t];
-                const float d0 = v0[t] - c, d1 = v1[t] - c;
-                s1[t] += d0 + d1;
-                s2[t] = fmaf(d0, d0, fmaf(d1, d1, s2[t]));
-            }
-        }
-    }
-    if (stats) {
-#pragma unroll
-        for (int t = 0; t < EMB_TOK; ++t) {
-            float a = s1[t], q = s2[t];
-            for (int o = 16; o > 0; o >>= 1) {
-                a += __shfl_xor_sync(0xffffffffu, a, o);
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-            }
-            if (lane == 0) red[0][warp][t] = a, red[1][warp][t] = q;
-        }
-        __syncthreads();
-        if (threadIdx.x < EMB_TOK) {
-            const int t = threadIdx.x;
-            float a = 0.f, q = 0.f;
-            for (int w = 0; w < 8; ++w) a += red[0][w][t], q += red[1][w][t];
-            const float dm = a / (float)D;
-            stats[(size_t)b * L + extras + hh * EMB_TOK + t] = make_float2(shift[t] + dm, fmaf(-a, dm, q));
-        }
-    }
-    if (hh == 0) {
-        // time token: [cos(tau f_i) | sin(tau f_i)], f_i = exp(-ln(1e4) i / half); label token in front of it
-        const int half = D / 2;
-        float tau = tsteps[b];
-        if (normalize_t) tau = tau / 1000.f;
-        __syncthreads();  // red[] / shift[] are reused below
-        for (int row = 0; row < extras; ++row) {
-            const bool is_time = (row == extras - 1);
-            const float* src = is_time ? nullptr : label_emb + (size_t)y[b] * D;
-            float a = 0.f, q = 0.f, c = 0.f;
-            for (int e = threadIdx.x; e < D; e += blockDim.x) {
-                float v;
-                if (is_time) {
-                    const int i = (e < half) ? e : e - half;
-                    const float f = expf((-9.210340371976184f * (float)i) / (float)half);
-                    const float arg = tau * f;
-                    v = (e < half) ? cosf(arg) : sinf(arg);
-                } else {
-                    v = src[e];
-                }
-                const __nv_bfloat16 hv = __float2bfloat16_rn(v + pos[(size_t)row * D + e]);
-                tokens[((size_t)b * L + row) * D + e] = hv;
-                const float r = __bfloat162float(hv);
-                if (e < (int)blockDim.x) c = r;  // shift = the thread's own first value
-                const float d = r - c;
-                a += d;
-                q = fmaf(d, d, q);
-            }
-            if (stats) {
-                // per-thread shifted sums (shift c_thread, n_thread values) -> merge as (mean, M2) partials (Chan)
-                const int n_thr = (D - (int)threadIdx.x + (int)blockDim.x - 1) / (int)blockDim.x;
-                float mean = c + a / (float)n_thr, m2 = fmaf(-a, a / (float)n_thr, q), cnt = (float)n_thr;
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float mean_o = __shfl_xor_sync(0xffffffffu, mean, o);
-                    const float m2_o = __shfl_xor_sync(0xffffffffu, m2, o);
-                    const float cnt_o = __shfl_xor_sync(0xffffffffu, cnt, o);
-                    const float tot = cnt + cnt_o, dlt = mean_o - mean;
-                    m2 = m2 + m2_o + dlt * dlt * cnt * cnt_o / tot;
-                    mean = mean + dlt * cnt_o / tot;
-                    cnt = tot;
-                }
-                if (lane == 0) red[0][warp][row] = mean, red[1][warp][row] = m2, red[0][warp][EMB_TOK + row] = cnt;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    float M = red[0][0][row], Q = red[1][0][row], N = red[0][0][EMB_TOK + row];
-                    for (int w = 1; w < 8; ++w) {
-                        const float mo = red[0][w][row], qo = red[1][w][row], no = red[0][w][EMB_TOK + row];
-                        const float tot = N + no, dlt = mo - M;
-                        Q = Q + qo + dlt * dlt * N * no / tot;
-                        M = M + dlt * no / tot;
-                        N = tot;
-                    }
-                    stats[(size_t)b * L + row] = make_float2(M, Q);
-                }
-                __syncthreads();
-            }
-        }
-    }
-}
+constexpr int EMB_TOK = 16;  // patches per image row (every reference config: img_size / patch_size == 16)
 
 // =====================================================================================================
 // Tensor-core patch embed (the model path): the per-patch linear runs on the CTA-pair tcgen05 GEMM.
@@ -253,6 +59,19 @@ __global__ void __launch_bounds__(256, 2) embed_tokens_kernel(
 //   token_extras_kernel  time / label token rows (+ pos_embed) and their 64-column LayerNorm partials.
 // The GEMM epilogue adds bias + pos_embed and writes the token rows and their LayerNorm partials (GemmArgs embed_mode).
 // =====================================================================================================
+// two horizontally adjacent pixels -> bf16 hi pair at dst, lo pair (x - bf16(x)) at dst + 64
+__device__ __forceinline__ void patch_store_pair(__nv_bfloat16* dst, float v0, float v1) {
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v0 - __low2float(hi), v1 - __high2float(hi));
+    *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(dst + 64) = lo;
+}
+// address of element (c, p1, p2) of patch (hh, ww) of sample b in the patch matrix A [B * Hp * Wp, 128]
+__device__ __forceinline__ __nv_bfloat16* patch_elem(__nv_bfloat16* A, int b, int c, int yy, int xx, int P, int Hp,
+                                                      int Wp) {
+    const int hh = yy / P, p1 = yy % P, ww = xx / P, p2 = xx % P;
+    return A + ((size_t)b * (Wp * Hp) + hh * Wp + ww) * 128 + (c * P + p1) * P + p2;
+}
 __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ x_img,
                                                            __nv_bfloat16* __restrict__ A, int B, int C, int H, int W,
                                                            int P) {
@@ -267,35 +86,30 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
     const int yy = r % H;
     r /= H;
     const int c = r % C, b = r / C;
-    const int hh = yy / P, p1 = yy % P;
     const float* src = x_img + (((size_t)b * C + c) * H + yy) * W + ww * P;
-    __nv_bfloat16* dst = A + ((size_t)b * (Wp * (H / P)) + hh * Wp + ww) * 128 + (c * P + p1) * P;
+    __nv_bfloat16* dst = patch_elem(A, b, c, yy, ww * P, P, H / P, Wp);
     for (int p2 = 0; p2 < P; p2 += 2) {
         const float2 v = *reinterpret_cast<const float2*>(src + p2);
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x - __low2float(hi), v.y - __high2float(hi));
-        *reinterpret_cast<__nv_bfloat162*>(dst + p2) = hi;
-        *reinterpret_cast<__nv_bfloat162*>(dst + 64 + p2) = lo;
+        patch_store_pair(dst + p2, v.x, v.y);
     }
 }
 
-// grid = B, 256 threads; D/64 LayerNorm partials per extras row (warp w handles chunks w, w+8, ...)
-__global__ void __launch_bounds__(256) token_extras_kernel(const float* __restrict__ tsteps,
-                                                           const long long* __restrict__ y,
-                                                           const float* __restrict__ pos,
-                                                           const float* __restrict__ label_emb,
-                                                           __nv_bfloat16* __restrict__ tokens,
-                                                           float2* __restrict__ stats_p, int D, int L, int extras,
-                                                           int normalize_t) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// 256 threads write the extras rows (label token, time token; + pos_embed) of sample b and their D/64 LayerNorm
+// partials (warp w handles chunks w, w+8, ...).  tau = raw timestep (models/uvit.py:352-360).
+__device__ __forceinline__ void write_token_extras(int b, float tau, const long long* __restrict__ y,
+                                                   const float* __restrict__ pos, const float* __restrict__ label_emb,
+                                                   __nv_bfloat16* __restrict__ tokens, float2* __restrict__ stats_p,
+                                                   int D, int L, int extras, int normalize_t, int num_classes) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = D / 2;
-    float tau = tsteps[b];
     if (normalize_t) tau = tau / 1000.f;
     for (int row = 0; row < extras; ++row) {
         const bool is_time = (row == extras - 1);
-        const float* src = is_time ? nullptr : label_emb + (size_t)y[b] * D;
+        // labels are validated on the host (the reference raises IndexError); the clamp only keeps a bad label from
+        // reading outside the embedding table
+        long long cls = is_time ? 0 : y[b];
+        cls = cls < 0 ? 0 : (cls >= num_classes ? num_classes - 1 : cls);
+        const float* src = is_time ? nullptr : label_emb + (size_t)cls * D;
         for (int ch = warp; ch < D / 64; ch += 8) {
             float v[2];
 #pragma unroll
@@ -323,6 +137,22 @@ __global__ void __launch_bounds__(256) token_extras_kernel(const float* __restri
             if (lane == 0 && stats_p) stats_p[((size_t)b * L + row) * (D / 64) + ch] = make_float2(mean, q);
         }
     }
+}
+// grid = B, 256 threads.  The timestep comes from the caller's float vector (UViT.forward) or, inside the sampler, from
+// the device-side step counter.
+__global__ void __launch_bounds__(256) token_extras_kernel(const float* __restrict__ tsteps,
+                                                           const int* __restrict__ t_dev,
+                                                           const long long* __restrict__ y,
+                                                           const float* __restrict__ pos,
+                                                           const float* __restrict__ label_emb,
+                                                           __nv_bfloat16* __restrict__ tokens,
+                                                           float2* __restrict__ stats_p, int D, int L, int extras,
+                                                           int normalize_t, int num_classes) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x;
+    const float tau = t_dev ? (float)(*t_dev) : tsteps[b];
+    write_token_extras(b, tau, y, pos, label_emb, tokens, stats_p, D, L, extras, normalize_t, num_classes);
 }
 
 // W_pe [D, pd] fp32 (conv weight flattened (c, p1, p2)) -> [D, 128] bf16: [W | 0 | W | 0]
@@ -394,8 +224,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
 }
 
 // =====================================================================================================
-// final_layer: 3x3 conv, pad 1 (models/uvit.py:329-333,382).  in/out [B,C,H,W] fp32.  One CTA per
-// (sample, 16-row band).  Optional fused DDPM update (see ddpm_step_kernel) when x_io != null.
+// final_layer: 3x3 conv, pad 1 (models/uvit.py:329-333,382).  in/out [B,C,H,W] fp32.
 // =====================================================================================================
 constexpr int CONV_BAND = 16;
 // One CTA per (sample, 16-row band): the band (+1 halo row each side) of all C channels is staged in shared memory
@@ -403,6 +232,48 @@ constexpr int CONV_BAND = 16;
 // registers (a 3 x 6 window per input channel) and stores them as one float4 per channel.  Requires W % 4 == 0.
 // n_dev / slot_map (early-exit compaction): only the first *n_dev input images are live and image b is written to
 // output slot slot_map[b].
+template <int C>
+__device__ __forceinline__ void conv_stage_band(float* __restrict__ conv_smem, const float* __restrict__ in, int b,
+                                                int y0, int H, int W) {
+    const int SW = W + 8, SH = CONV_BAND + 2;
+    const int w4 = W / 4;
+    // interior: rows y0-1 .. y0+16, float4 granularity; halo columns are zero
+    for (int i = threadIdx.x; i < C * SH * (w4 + 2); i += blockDim.x) {
+        const int q = i % (w4 + 2), r = (i / (w4 + 2)) % SH, c = i / ((w4 + 2) * SH);
+        const int yy = y0 - 1 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q >= 1 && q <= w4 && yy >= 0 && yy < H)
+            v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * C + c) * H + yy) * W) + (q - 1));
+        *reinterpret_cast<float4*>(conv_smem + (c * SH + r) * SW + q * 4) = v;
+    }
+}
+// output pixels (y0 + yy, 4*xq .. 4*xq+3) of every output channel; sw = [C*C*9 weights | C biases] in shared memory
+template <int C>
+__device__ __forceinline__ void conv_pixels4(const float* __restrict__ conv_smem, const float* __restrict__ sw, int yy,
+                                             int xq, int W, float (&acc)[C][4]) {
+    const int SW = W + 8, SH = CONV_BAND + 2;
+#pragma unroll
+    for (int co = 0; co < C; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = sw[C * C * 9 + co];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            // smem column of pixel x is x + 4; the window needs x-1 .. x+4 -> columns 4*xq+3 .. 4*xq+8
+            const float* rp = conv_smem + (ci * SH + yy + dy) * SW + 4 * xq;
+            const float4 m = *reinterpret_cast<const float4*>(rp + 4);
+            const float l = rp[3], r = rp[8];
+            const float win[6] = {l, m.x, m.y, m.z, m.w, r};
+#pragma unroll
+            for (int co = 0; co < C; ++co) {
+                const float* wp = sw + (co * C + ci) * 9 + dy * 3;
+                const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    acc[co][p] = fmaf(w0, win[p], fmaf(w1, win[p + 1], fmaf(w2, win[p + 2], acc[co][p])));
+            }
+        }
+    }
+}
 template <int C>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
@@ -417,42 +288,13 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
     pdl_wait();
     if (n_dev && b >= *n_dev) return;
     const int ob = slot_map ? slot_map[b] : b;
-    const int SW = W + 8, SH = CONV_BAND + 2;
     const int w4 = W / 4;
-    // interior: rows y0-1 .. y0+16, float4 granularity; halo columns are zero
-    for (int i = threadIdx.x; i < C * SH * (w4 + 2); i += blockDim.x) {
-        const int q = i % (w4 + 2), r = (i / (w4 + 2)) % SH, c = i / ((w4 + 2) * SH);
-        const int yy = y0 - 1 + r;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (q >= 1 && q <= w4 && yy >= 0 && yy < H)
-            v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * C + c) * H + yy) * W) + (q - 1));
-        *reinterpret_cast<float4*>(conv_smem + (c * SH + r) * SW + q * 4) = v;
-    }
+    conv_stage_band<C>(conv_smem, in, b, y0, H, W);
     __syncthreads();
     for (int i = threadIdx.x; i < CONV_BAND * w4; i += blockDim.x) {
-        const int xq = i % w4, yy = i / w4;  // output pixels (y0+yy, 4*xq .. 4*xq+3)
+        const int xq = i % w4, yy = i / w4;
         float acc[C][4];
-#pragma unroll
-        for (int co = 0; co < C; ++co) acc[co][0] = acc[co][1] = acc[co][2] = acc[co][3] = sw[C * C * 9 + co];
-#pragma unroll
-        for (int ci = 0; ci < C; ++ci) {
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                // smem column of pixel x is x + 4; the window needs x-1 .. x+4 -> columns 4*xq+3 .. 4*xq+8
-                const float* rp = conv_smem + (ci * SH + yy + dy) * SW + 4 * xq;
-                const float4 m = *reinterpret_cast<const float4*>(rp + 4);
-                const float l = rp[3], r = rp[8];
-                const float win[6] = {l, m.x, m.y, m.z, m.w, r};
-#pragma unroll
-                for (int co = 0; co < C; ++co) {
-                    const float* wp = sw + (co * C + ci) * 9 + dy * 3;
-                    const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p)
-                        acc[co][p] = fmaf(w0, win[p], fmaf(w1, win[p + 1], fmaf(w2, win[p + 2], acc[co][p])));
-                }
-            }
-        }
+        conv_pixels4<C>(conv_smem, sw, yy, xq, W, acc);
 #pragma unroll
         for (int co = 0; co < C; ++co)
             *(reinterpret_cast<float4*>(out + (((size_t)ob * C + co) * H + y0 + yy) * W) + xq) =
@@ -468,7 +310,9 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 //   (mode 0) to stay within 1 ulp of the reference; mode 1 uses the generic two-term form for the other rules;
 //   mode 2 is the DDIM update (sampler.py:112-120) with a fourth coefficient d.
 // coef layout: [1000][4] = {c0, c1, sigma, d}
-// Noise: injected tensor z_all[t] (parity) or Philox4x32-10 + Box-Muller keyed by (seed, t, element).
+// Noise: injected tensor z_all[t] (parity) or Philox4x32-10 + Box-Muller keyed by (seed, t, GLOBAL float4 index): the
+// index carries the shard's offset into the global batch, so N data-parallel shards draw exactly the noise a single
+// process would draw for the whole batch.
 // =====================================================================================================
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                               uint32_t k1, uint32_t (&out)[4]) {
@@ -490,7 +334,33 @@ __device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float& n0, 
     sincosf(6.283185307179586f * b, &s, &c);
     n0 = r * c, n1 = r * s;
 }
+// the four normals of float4 number `idx4` (global index) at timestep t
+__device__ __forceinline__ float4 philox_normal4(unsigned long long idx4, int t, unsigned long long seed) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)idx4, (uint32_t)(idx4 >> 32), (uint32_t)t, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    float4 z;
+    box_muller(r[0], r[1], z.x, z.y);
+    box_muller(r[2], r[3], z.z, z.w);
+    return z;
+}
+struct StepCoef {
+    float c0, c1, sg, d;
+};
+__device__ __forceinline__ float ddpm_update1(int mode, const StepCoef& k, float x, float e, float z) {
+    if (mode == 0)  // sqrt(1/alpha) * (x - coeff*eps) + sigma*z, evaluated like the reference (no contraction)
+        return __fadd_rn(__fmul_rn(k.c0, __fsub_rn(x, __fmul_rn(k.c1, e))), __fmul_rn(k.sg, z));
+    if (mode == 2)  // DDIM (sampler.py:112-120): mean = c0*(x - c1*eps); mean += d*eps; x' = mean + sigma2*z
+        return __fadd_rn(__fadd_rn(__fmul_rn(k.c0, __fsub_rn(x, __fmul_rn(k.c1, e))), __fmul_rn(k.d, e)),
+                         __fmul_rn(k.sg, z));
+    // (c1*out + c0*x) + sigma*z   -- predict_original (sampler.py:69-72) / predict_previous (c0=0, c1=1)
+    return __fadd_rn(__fadd_rn(__fmul_rn(k.c1, e), __fmul_rn(k.c0, x)), __fmul_rn(k.sg, z));
+}
+__device__ __forceinline__ float4 ddpm_update4(int mode, const StepCoef& k, float4 x, float4 e, float4 z) {
+    return make_float4(ddpm_update1(mode, k, x.x, e.x, z.x), ddpm_update1(mode, k, x.y, e.y, z.y),
+                       ddpm_update1(mode, k, x.z, e.z, z.z), ddpm_update1(mode, k, x.w, e.w, z.w));
+}
 
+// seed_dev (graph replay / sampler): {Philox key, float4 index of this shard's first element in the global batch}
 __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, const float* __restrict__ model_out,
                                                         const float* __restrict__ z_all, size_t n, size_t z_stride,
                                                         const float* __restrict__ coef, const int* __restrict__ t_dev,
@@ -500,47 +370,110 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
     pdl_launch_dependents();
     pdl_wait();
     const int t = t_dev ? *t_dev : t_host;
-    if (seed_dev) seed = *seed_dev;  // graph replay: the Philox key lives in device memory
-    const float c0 = coef[t * 4 + 0], c1 = coef[t * 4 + 1], sg = coef[t * 4 + 2];
+    unsigned long long off4 = 0;
+    if (seed_dev) seed = seed_dev[0], off4 = seed_dev[1];
+    const StepCoef k{coef[t * 4 + 0], coef[t * 4 + 1], coef[t * 4 + 2], coef[t * 4 + 3]};
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
-    float4 xv = reinterpret_cast<const float4*>(x)[i4];
+    const float4 xv = reinterpret_cast<const float4*>(x)[i4];
     const float4 ev = reinterpret_cast<const float4*>(model_out)[i4];
     float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t > 0) {
-        if (z_all) {
-            zv = reinterpret_cast<const float4*>(z_all + (size_t)t * z_stride)[i4];
-        } else {
-            uint32_t r[4];
-            philox4x32_10((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)t, 0x5eedu, (uint32_t)seed,
-                          (uint32_t)(seed >> 32), r);
-            box_muller(r[0], r[1], zv.x, zv.y);
-            box_muller(r[2], r[3], zv.z, zv.w);
-        }
-    }
-    float4 o;
-    if (mode == 0) {
-        // sqrt(1/alpha) * (x - coeff*eps) + sigma*z, evaluated like the reference (no contraction across the adds)
-        o.x = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.x, __fmul_rn(c1, ev.x))), __fmul_rn(sg, zv.x));
-        o.y = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.y, __fmul_rn(c1, ev.y))), __fmul_rn(sg, zv.y));
-        o.z = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.z, __fmul_rn(c1, ev.z))), __fmul_rn(sg, zv.z));
-        o.w = __fadd_rn(__fmul_rn(c0, __fsub_rn(xv.w, __fmul_rn(c1, ev.w))), __fmul_rn(sg, zv.w));
-    } else if (mode == 2) {
-        // DDIM (sampler.py:112-120): mean = c0*(x - c1*eps); mean += d*eps; x' = mean + sigma2*z, in that order
-        const float d = coef[t * 4 + 3];
-        o.x = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.x, __fmul_rn(c1, ev.x))), __fmul_rn(d, ev.x)), __fmul_rn(sg, zv.x));
-        o.y = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.y, __fmul_rn(c1, ev.y))), __fmul_rn(d, ev.y)), __fmul_rn(sg, zv.y));
-        o.z = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.z, __fmul_rn(c1, ev.z))), __fmul_rn(d, ev.z)), __fmul_rn(sg, zv.z));
-        o.w = __fadd_rn(__fadd_rn(__fmul_rn(c0, __fsub_rn(xv.w, __fmul_rn(c1, ev.w))), __fmul_rn(d, ev.w)), __fmul_rn(sg, zv.w));
-    } else {
-        // (c1*out + c0*x) + sigma*z   -- predict_original (sampler.py:69-72) / predict_previous (c0=0, c1=1)
-        o.x = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.x), __fmul_rn(c0, xv.x)), __fmul_rn(sg, zv.x));
-        o.y = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.y), __fmul_rn(c0, xv.y)), __fmul_rn(sg, zv.y));
-        o.z = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.z), __fmul_rn(c0, xv.z)), __fmul_rn(sg, zv.z));
-        o.w = __fadd_rn(__fadd_rn(__fmul_rn(c1, ev.w), __fmul_rn(c0, xv.w)), __fmul_rn(sg, zv.w));
-    }
+    if (t > 0) zv = z_all ? reinterpret_cast<const float4*>(z_all + (size_t)t * z_stride)[i4] : philox_normal4(i4 + off4, t, seed);
+    const float4 o = ddpm_update4(mode, k, xv, ev, zv);
     reinterpret_cast<float4*>(x)[i4] = o;
     if (x_save) reinterpret_cast<float4*>(x_save)[i4] = o;
+}
+
+// =====================================================================================================
+// Fused tail of one sampling step (plain U-ViT path): final_layer 3x3 conv (models/uvit.py:382) -> eps, the DDPM
+// update of x (sampler.py:47-79), and the HEAD of the next step: the bf16 hi|lo patch matrix of the updated x
+// (patch_gather_kernel's output), the next step's time / label token rows (token_extras_kernel's output) and the
+// step counter t <- next_t[t].  Replaces conv3x3 + ddpm_step + next_t + fill_t + patch_gather + token_extras (six
+// launches) by one; every arithmetic expression is shared with those kernels, so the fused and the unfused step give
+// the same bits.  One CTA per (sample, 16-row band), 256 threads.
+// The next step may run on the other backbone (DuoDiff hand-off, sampler.py:135-136): next_late[t] selects which
+// model's buffers receive the prepared head.
+// =====================================================================================================
+struct TailTarget {
+    __nv_bfloat16* a_patch;  // [B * 256, 128] bf16: patch vectors hi | lo
+    __nv_bfloat16* tokens;   // x0 [B * L, D]
+    float2* stats_p;         // [B * L, D / 64]
+    const float* pos;        // [L, D]
+    const float* label_emb;  // [num_classes, D] or null
+    int P, D, L, extras, normalize_t, num_classes;
+};
+struct TailArgs {
+    const float* img_pre;  // [B,C,H,W] un-patchified decoder output (input of the 3x3 conv)
+    const float* conv_w;
+    const float* conv_b;
+    float* x;              // [B,C,H,W] in place
+    const float* z_all;    // injected noise [1000, n] or null (Philox)
+    const float* coef;     // [1000,4]
+    int* t_dev;            // step counter (read by every CTA, advanced by the last one to finish)
+    const int* next_t;     // [1000] successor table; [1000, 2000): 1 = the step after t runs on the late backbone
+    const unsigned long long* seed_dev;  // {Philox key, float4 offset of the shard in the global batch}
+    const long long* y;    // labels or null
+    float* eps_out;        // optional [B,C,H,W]: the model output of this step (parity traces)
+    float* x_save;         // optional copy of the updated x
+    unsigned* ticket;      // CTA completion counter (self-resetting)
+    size_t n;              // B*C*H*W
+    int H, W, mode;
+    TailTarget tgt[2];     // [0] early backbone, [1] late backbone
+};
+template <int C>
+__global__ void __launch_bounds__(256) step_tail_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(16) float conv_smem[];  // [C][CONV_BAND+2][W+8]
+    __shared__ float sw[C * C * 9 + C];
+    const int H = a.H, W = a.W;
+    const int bands = H / CONV_BAND;
+    const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
+        sw[i] = (i < C * C * 9) ? a.conv_w[i] : a.conv_b[i - C * C * 9];
+    pdl_wait();
+    const int t = *a.t_dev;
+    const int t_next = a.next_t[t];
+    const TailTarget& tg = a.tgt[a.next_t[1000 + t] ? 1 : 0];
+    const unsigned long long seed = a.seed_dev[0], off4 = a.seed_dev[1];
+    const StepCoef k{a.coef[t * 4 + 0], a.coef[t * 4 + 1], a.coef[t * 4 + 2], a.coef[t * 4 + 3]};
+    const int w4 = W / 4;
+    conv_stage_band<C>(conv_smem, a.img_pre, b, y0, H, W);
+    __syncthreads();
+    const int P = tg.P, Hp = H / P, Wp = W / P;
+    for (int i = threadIdx.x; i < CONV_BAND * w4; i += blockDim.x) {
+        const int xq = i % w4, yy = i / w4;
+        float acc[C][4];
+        conv_pixels4<C>(conv_smem, sw, yy, xq, W, acc);
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+            const size_t e4 = ((((size_t)b * C + co) * H + y0 + yy) * W) / 4 + xq;  // float4 index inside the shard
+            const float4 ev = make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
+            const float4 xv = reinterpret_cast<const float4*>(a.x)[e4];
+            float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t > 0)
+                zv = a.z_all ? reinterpret_cast<const float4*>(a.z_all + (size_t)t * a.n)[e4]
+                             : philox_normal4(e4 + off4, t, seed);
+            const float4 o = ddpm_update4(a.mode, k, xv, ev, zv);
+            reinterpret_cast<float4*>(a.x)[e4] = o;
+            if (a.eps_out) reinterpret_cast<float4*>(a.eps_out)[e4] = ev;
+            if (a.x_save) reinterpret_cast<float4*>(a.x_save)[e4] = o;
+            // head of the next step: the updated pixels as bf16 hi | lo patch-vector entries (P = 2: two patches)
+            patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq, P, Hp, Wp), o.x, o.y);
+            patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq + 2, P, Hp, Wp), o.z, o.w);
+        }
+    }
+    if (y0 == 0)  // one CTA per sample also writes the next step's time / label token rows
+        write_token_extras(b, (float)t_next, a.y, tg.pos, tg.label_emb, tg.tokens, tg.stats_p, tg.D, tg.L, tg.extras,
+                           tg.normalize_t, tg.num_classes);
+    // every CTA has read t above; the last one to get here advances the step counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {
+            *a.t_dev = t_next;
+            *a.ticket = 0u;
+        }
+    }
 }
 
 // step bookkeeping for graph replay: t_vec[b] = float(*t_dev) for the next forward; (*t_dev) -= 1 after a step
@@ -594,7 +527,9 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
                                                         int* __restrict__ exit_idx, const int* __restrict__ t_dev,
                                                         int* __restrict__ exit_log /*[1000,B] by t, or null*/) {
     const int b = blockIdx.y;
-    int idx = depth;
+    // eesampler.py:62-67: a row of zeros is appended to the probe outputs, so "no exit" selects index `depth` whenever
+    // 0 <= threshold; with a negative threshold the mask is all-false and argmax returns 0 (layer 0's head)
+    int idx = (0.f <= threshold) ? depth : 0;
     for (int i = 0; i < depth; ++i) {
         if (scores[(size_t)i * B + b] <= threshold) {
             idx = i;
@@ -667,7 +602,8 @@ __global__ void __launch_bounds__(1024) ee_decide_kernel(
     const bool live = b < n;
     const float myscore = live ? sc[b] : 0.f;
     const int myslot = live ? slot[b] : 0;
-    const int ex = (live && myscore <= thr) ? 1 : 0;
+    // threshold < 0: argmax over an all-false mask selects layer 0 for every sample (see ee_select_kernel)
+    const int ex = (live && (myscore <= thr || (thr < 0.f && layer == 0))) ? 1 : 0;
     const int kp = (live && !ex) ? 1 : 0;
     // block-wide exclusive scans of ex / kp and the sum of the live scores
     int ie = ex, ik = kp;
@@ -744,12 +680,15 @@ __global__ void __launch_bounds__(128) ee_gather_exit_kernel(const __nv_bfloat16
     }
 }
 
-// In-place compaction of the kept samples of up to 8 activation buffers (+ the row statistics, blockIdx.y == nbuf).
+// In-place compaction of the kept samples of up to EE_MAX_LIVE activation buffers (+ the row statistics, blockIdx.y ==
+// nbuf).  Live buffers before block i = the block input + every pending long skip: at most depth/2 + 1 (11 for the
+// depth-21 deediff_imagenet256.yaml).
 // grid = (L, nbuf + 1).  A thread owns one 16-byte column chunk of token l and walks the kept samples in increasing
 // order: keep_src[j] >= j and is increasing, so a row is always read before it can be overwritten, and the loads of
 // the next samples never alias earlier stores (dst_j <= src_j < src_{j+1}).
+constexpr int EE_MAX_LIVE = 16;
 struct EeBufList {
-    __nv_bfloat16* p[8];
+    __nv_bfloat16* p[EE_MAX_LIVE];
 };
 __global__ void __launch_bounds__(128) ee_compact_kernel(EeBufList bufs, int nbuf, float2* __restrict__ stats,
                                                          const int* __restrict__ ee_n,

@@ -16,7 +16,7 @@
 // FMA pipes makes it slower still (63 us): issue slots, not the MUFU pipe, are then short.  The one-thread-per-row kernel
 // wins because its two tiles run half a period apart and fill each other's gaps.
 #pragma once
-#include "attention.cuh"
+#include "../attention.cuh"
 
 namespace ddb {
 

@@ -17,7 +17,7 @@
 // chunk g as two 32-column sub-chunks through two 8 KB SWIZZLE_64B staging buffers), warp 16 TMA producer (both CTAs),
 // warp 17 MMA / copy issuer (leader CTA), warps 18-19 aux (per-tile row statistics, bias, colsum -> shared memory).
 #pragma once
-#include "gemm2.cuh"
+#include "../gemm2.cuh"
 
 namespace ddb {
 

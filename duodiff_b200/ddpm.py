@@ -120,58 +120,88 @@ class Sampler:
         else:
             table, mode = step_coefficients(rule, variance)
         self.coef = table
+        self.device = early.device
+        if late is not None and late.device != early.device:
+            raise _lib.DuoDiffError(f"early model on {early.device}, late model on {late.device}")
         handle = C.c_void_p()
-        _lib.check(self.lib.ddb_sampler_create(
-            early.handle, late.handle if late is not None else None, switch_step(t_switch) if late is not None else -1,
-            batch, table.data_ptr(), mode, -1.0 if ee_threshold is None else float(ee_threshold), ee_mode,
-            C.byref(handle)))
+        # early exit is switched by ee_mode (-1 = off), never by the sign of the threshold: a negative threshold is a
+        # legal value of eesampler.py's --threshold (every sample then takes layer 0's head)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_sampler_create(
+                early.handle, late.handle if late is not None else None,
+                switch_step(t_switch) if late is not None else -1, batch, table.data_ptr(), mode,
+                0.0 if ee_threshold is None else float(ee_threshold), -1 if ee_threshold is None else int(ee_mode),
+                C.byref(handle)))
         self.handle = handle
 
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
-            self.lib.ddb_sampler_destroy(h)
+            with torch.cuda.device(self.device):
+                self.lib.ddb_sampler_destroy(h)
             self.handle = None
 
-    def run(self, x, y=None, noise=None, seed: int = 0, t_first: int = 999, t_last: int = 0, eps_trace=None,
-            x_trace=None, exit_log=None, score_log=None, use_graph: bool = True):
-        """In place on x [B,C,H,W] f32 cuda.  noise: None (device Philox) or [1000, *x.shape] f32 cuda indexed by t."""
+    def set_noise_offset(self, first_row: int) -> None:
+        """This shard holds rows [first_row, first_row + batch) of a global batch: the in-kernel Philox noise is keyed
+        by the GLOBAL element index, so the shards together draw exactly the single-process noise."""
+        _lib.check(self.lib.ddb_sampler_set_noise_offset(self.handle, int(first_row)))
+
+    def _check_xy(self, x, y, noise):
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.batch
+        if x.device != self.device:
+            raise _lib.DuoDiffError(f"x is on {x.device} but the sampler's models live on {self.device}")
         if noise is not None:
             assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
             assert noise.shape[0] == 1000 and noise[0].numel() == x.numel()
         if y is not None:
-            y = y.to(device=x.device, dtype=torch.int64).contiguous()
+            y = self.early.check_labels(y, self.batch)
+            if self.late is not None:
+                y = self.late.check_labels(y, self.batch)
+        return y
+
+    def profile_step(self, x, t: int, late: bool, y=None) -> dict:
+        """Per-kernel-category device time of one eager sampling step as the sampler runs it."""
+        y = self._check_xy(x, y, None)
+        n = len(Engine.PROF_CATEGORIES)
+        ms, cnt = (C.c_float * n)(), (C.c_int32 * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_sampler_profile_step(self.handle, x.data_ptr(), _lib.ptr(y), int(t), int(bool(late)),
+                                                         ms, cnt, _lib.current_stream_ptr()))
+        return {k: dict(ms=float(ms[i]), launches=int(cnt[i])) for i, k in enumerate(Engine.PROF_CATEGORIES)}
+
+    def run(self, x, y=None, noise=None, seed: int = 0, t_first: int = 999, t_last: int = 0, eps_trace=None,
+            x_trace=None, exit_log=None, score_log=None, use_graph: bool = True):
+        """In place on x [B,C,H,W] f32 cuda.  noise: None (device Philox) or [1000, *x.shape] f32 cuda indexed by t."""
+        y = self._check_xy(x, y, noise)
         graph = bool(use_graph) and eps_trace is None and x_trace is None
-        _lib.check(self.lib.ddb_sampler_run(
-            self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), t_first, t_last,
-            _lib.ptr(eps_trace), _lib.ptr(x_trace), _lib.ptr(exit_log), _lib.ptr(score_log), int(graph),
-            _lib.current_stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_sampler_run(
+                self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), t_first, t_last,
+                _lib.ptr(eps_trace), _lib.ptr(x_trace), _lib.ptr(exit_log), _lib.ptr(score_log), int(graph),
+                _lib.current_stream_ptr()))
         return x
 
     def run_list(self, x, t_list, late_flags, y=None, noise=None, seed: int = 0, eps_trace=None, x_trace=None,
                  use_graph: bool = True):
         """The same loop over an explicit timestep list (DDIM): model at t_list[k] (late backbone if late_flags[k]),
         then the sampler's update with the coefficients of t_list[k]."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == self.batch
+        y = self._check_xy(x, y, noise)
         n = len(t_list)
         assert n == len(late_flags)
-        if noise is not None:
-            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous()
-            assert noise.shape[0] == 1000 and noise[0].numel() == x.numel()
-        if y is not None:
-            y = y.to(device=x.device, dtype=torch.int64).contiguous()
         ts = (C.c_int32 * n)(*[int(t) for t in t_list])
         lf = (C.c_uint8 * n)(*[1 if f else 0 for f in late_flags])
         graph = bool(use_graph) and eps_trace is None and x_trace is None
-        _lib.check(self.lib.ddb_sampler_run_list(
-            self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), ts, lf, n,
-            _lib.ptr(eps_trace), _lib.ptr(x_trace), int(graph), _lib.current_stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ddb_sampler_run_list(
+                self.handle, x.data_ptr(), _lib.ptr(y), _lib.ptr(noise), int(seed) & (2**64 - 1), ts, lf, n,
+                _lib.ptr(eps_trace), _lib.ptr(x_trace), int(graph), _lib.current_stream_ptr()))
         return x
 
     def finalize(self, x):
         """(x + 1) / 2, 'b c h w -> b h w c' (sampler.py:145-146)."""
         B, Cc, H, W = x.shape
         out = torch.empty(B, H, W, Cc, device=x.device, dtype=torch.float32)
-        _lib.check(self.lib.ddb_finalize_nhwc(x.data_ptr(), out.data_ptr(), B, Cc, H, W, _lib.current_stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(self.lib.ddb_finalize_nhwc(x.data_ptr(), out.data_ptr(), B, Cc, H, W,
+                                                  _lib.current_stream_ptr()))
         return out

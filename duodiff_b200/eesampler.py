@@ -16,22 +16,37 @@ import torch
 from . import _io
 from .autoencoder import get_autoencoder
 from .ddpm import cached_sampler
+from .sampler import _pick_device, draw_labels
 from .early_exit import EarlyExitUViT
 from .uvit import UViT
 
 
 def get_samples(model, batch_size: int, seed: int, num_channels: int, sample_height: int, sample_width: int,
                 threshold: float, depth: int, y=None, autoencoder=None, *, noise=None, mode: int = 0,
-                use_graph: bool = True, device=None):
+                use_graph: bool = True, device=None, x_T=None, noise_row_offset: int = 0):
     """eesampler.py:40-89 -> (samples [B,H,W,C] numpy, error_prediction_by_timestep [1000,depth],
-    indices_by_timestep [1000,B]) with both logs as CPU float32 tensors indexed by t like the reference's."""
-    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    indices_by_timestep [1000,B]) with both logs as CPU float32 tensors indexed by t like the reference's.
+
+    ``mode`` 0 evaluates every probe and head like the reference ("simulate"); ``mode`` 1 really skips the layers after
+    a sample's exit ("compact"): samples and ``indices_by_timestep`` are bit-identical to mode 0, but row t of
+    ``error_prediction_by_timestep`` then holds, per layer, the mean probe output over the samples STILL IN THE BATCH at
+    that layer (NaN once the batch is empty) -- the reference's mean over the whole batch (eesampler.py:71) would need
+    the skipped layers.  Any ``threshold`` is legal; a negative one selects layer 0's head for every sample, as the
+    reference's argmax over an all-false mask does.  ``x_T`` / ``noise_row_offset``: see sampler.get_samples."""
+    dev = _pick_device(model, device)
     _io.seed_everything(seed)
-    x = torch.randn(batch_size, num_channels, sample_height, sample_width).pin_memory().to(dev, non_blocking=True)
+    if x_T is None:
+        x = torch.randn(batch_size, num_channels, sample_height, sample_width)
+    else:
+        x = torch.as_tensor(x_T, dtype=torch.float32).detach().cpu().contiguous()
+        if tuple(x.shape) != (batch_size, num_channels, sample_height, sample_width):
+            raise ValueError(f"x_T has shape {tuple(x.shape)}")
+    x = x.pin_memory().to(dev, non_blocking=True)
     with torch.cuda.device(dev):
         eng = model.engine(batch_size)
         sampler = cached_sampler(eng, None, np.inf, batch_size, rule="predict_noise", ee_threshold=threshold,
                                  ee_mode=mode)
+        sampler.set_noise_offset(noise_row_offset)
         exit_log = torch.zeros(1000, batch_size, device=dev, dtype=torch.int32)
         score_log = torch.zeros(1000, depth, device=dev, dtype=torch.float32)
         if noise is not None:
@@ -86,10 +101,7 @@ def main(argv=None):
     _io.seed_everything(args.seed)
     y = None
     if args.class_id is not None:
-        y = torch.randint(1, 1001, (args.batch_size,))
-        if mp.get("num_classes", -1) > 0:
-            y = y % mp["num_classes"]
-        y = y.to(device)
+        y = draw_labels(args.batch_size, mp.get("num_classes", -1)).to(device)
     autoencoder = None
     if "autoencoder" in cfg:  # eesampler.py:184-189
         autoencoder = get_autoencoder(cfg["autoencoder"]["autoencoder_checkpoint_path"])

@@ -52,6 +52,17 @@ def _rule_name(postprocessing) -> str:
     raise ValueError(f"unsupported postprocessing {postprocessing!r}; expected one of {RULES}")
 
 
+def _pick_device(model, device=None) -> torch.device:
+    """The reference samples on its module-level `device` (sampler.py:37); here: the explicit argument, else the device
+    the model's parameters live on, else the current CUDA device."""
+    if device is not None:
+        return torch.device(device)
+    mdev = getattr(model, "device", None)
+    if isinstance(mdev, torch.device) and mdev.type == "cuda":
+        return mdev
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _ddim_plan(ddim_steps: int, late_available: bool, t_switch):
     """(timesteps, late flags) of the DDIM loop, sampler.py:103-123: pairs (t, s) of the strided schedule; the
     hand-off `if t < 1000 - t_switch: model = late_model` happens AFTER the step at t."""
@@ -67,7 +78,7 @@ def _ddim_plan(ddim_steps: int, late_available: bool, t_switch):
 def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels: int, sample_height: int,
                 sample_width: int, use_ddim: bool = False, ddim_steps: int = 50, ddim_eta: float = 0.0,
                 timesteps_save: List[int] = (), y=None, autoencoder=None, late_model=None, t_switch=np.inf, *,
-                noise=None, use_graph: bool = True, device=None):
+                noise=None, use_graph: bool = True, device=None, x_T=None, noise_row_offset: int = 0):
     """sampler.py:82-155.  Returns (samples [B,H,W,C] f32 numpy un-clipped, [intermediate samples]).
 
     x_T is drawn on the CPU generator after ``seed_everything(seed)`` exactly like the reference (sampler.py:99-100);
@@ -75,11 +86,21 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
     by t) is injected (parity tests).  ``use_ddim`` runs the strided DDIM branch (sampler.py:103-126, including the
     reference's sigma_t^2 * z noise term).  ``autoencoder`` (duodiff_b200.autoencoder.get_autoencoder, or any object
     with the reference's ``decode``) maps the final and the saved intermediate latents to images (sampler.py:141-143,
-    149-150)."""
-    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    149-150).
+
+    Sharded (data-parallel) use, see duodiff_b200.distributed: ``x_T`` [B,C,H,W] replaces the draw of the initial
+    noise (this rank's rows of the global draw) and ``noise_row_offset`` is the global index of its first row, which
+    keys the Philox stream -- the shards of a global batch then reproduce the single-process result row for row."""
+    dev = _pick_device(model, device)
     _io.seed_everything(seed)
-    x = torch.randn(batch_size, num_channels, sample_height, sample_width)
-    x = x.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else x.to(dev)
+    if x_T is None:
+        x = torch.randn(batch_size, num_channels, sample_height, sample_width)
+    else:
+        x = torch.as_tensor(x_T, dtype=torch.float32).detach().cpu().contiguous()
+        if tuple(x.shape) != (batch_size, num_channels, sample_height, sample_width):
+            raise ValueError(f"x_T has shape {tuple(x.shape)}, expected "
+                             f"{(batch_size, num_channels, sample_height, sample_width)}")
+    x = x.pin_memory().to(dev, non_blocking=True)
     with torch.cuda.device(dev):
         early = model.engine(batch_size)
         late = late_model.engine(batch_size) if late_model is not None else None
@@ -96,6 +117,7 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
             return sampler.finalize(lat)
         if use_ddim:
             sampler = cached_sampler(early, late, t_switch, batch_size, rule=("ddim", int(ddim_steps), float(ddim_eta)))
+            sampler.set_noise_offset(noise_row_offset)
             steps, flags = _ddim_plan(int(ddim_steps), late is not None, t_switch)
             k0 = 0
             for k, t in enumerate(steps):
@@ -107,6 +129,7 @@ def get_samples(model, batch_size: int, postprocessing, seed: int, num_channels:
                     k0 = k + 1
         else:
             sampler = cached_sampler(early, late, t_switch, batch_size, rule=_rule_name(postprocessing))
+            sampler.set_noise_offset(noise_row_offset)
             t_first = 999
             for t_stop in sorted((t for t in save_at if 0 <= t <= 999), reverse=True) + [0]:
                 if t_stop > t_first:
@@ -156,6 +179,15 @@ def get_args(argv=None):
     return p.parse_args(argv)
 
 
+def draw_labels(batch_size: int, num_classes: int):
+    """sampler.py:314-318 / eesampler.py:176-180: with --class_id the reference draws a RANDOM label per sample,
+    ``torch.randint(1, 1001, (batch_size,))`` (Q14; the flag's value is ignored).  Deviation, stated: that range
+    overflows a 1000-row embedding table (label 1000 -> IndexError in the reference, 1 time in 1000 per sample), so the
+    labels are taken modulo ``num_classes`` here; for every label the reference can embed the value is unchanged."""
+    y = torch.randint(1, 1001, (batch_size,))
+    return y % num_classes if num_classes > 0 else y
+
+
 def _build(config_path, checkpoint_path, batch_size, device):
     cfg = _io.load_config(config_path)
     net = UViT(**_io.uvit_kwargs(cfg), max_batch=batch_size)
@@ -177,14 +209,9 @@ def main(argv=None):
         late, cfg = _build(args.config_path_late, args.checkpoint_path_late, args.batch_size, device)
     mp = cfg["model_params"]
     _io.seed_everything(args.seed)
-    # sampler.py:314-318 draws a *random* label per sample whenever --class_id is given (Q14); labels are taken
-    # modulo num_classes here because the reference's randint(1, 1001) overflows a 1000-row embedding.
     y = None
     if args.class_id is not None:
-        y = torch.randint(1, 1001, (args.batch_size,))
-        if mp.get("num_classes", -1) > 0:
-            y = y % mp["num_classes"]
-        y = y.to(device)
+        y = draw_labels(args.batch_size, mp.get("num_classes", -1)).to(device)
     autoencoder = None
     if "autoencoder" in cfg:  # sampler.py:320-325
         autoencoder = get_autoencoder(cfg["autoencoder"]["autoencoder_checkpoint_path"])

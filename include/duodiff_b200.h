@@ -8,7 +8,10 @@
  * Conventions: every function returns 0 on success or a negative ddb_status; ddb_last_error() returns a
  * thread-local message for the last failure.  All pointers named *_dev are CUDA device pointers owned by the
  * caller; the library never allocates caller-visible memory.  `stream` is a cudaStream_t passed as void*.
- * One handle = one device = one stream at a time (handles are not re-entrant; distinct handles are independent).
+ * One handle = one device = one stream at a time (handles are not re-entrant; distinct handles are independent and
+ * may be used from different threads and on different devices: the CUDA device that is current when a handle is
+ * created must be current for every call on it -- the Python shims guarantee that).  The only process-wide state is
+ * the set of measurement switches of ddb_set_option() (atomics, read at launch / graph-capture time).
  * There is no CPU fallback: on a machine without an sm_100 device every compute call fails with DDB_ERR_CUDA.
  */
 #ifndef DUODIFF_B200_H
@@ -70,9 +73,10 @@ int ddb_uvit_forward(ddb_model* m, const float* x_dev, const float* t_dev, const
 
 /* Same forward with a CUDA-event pair recorded on `stream` around every kernel launch; per-category device time
  * (ms) and launch counts are returned in host arrays of DDB_PROF_CATEGORIES entries, in the order
- * embed, ln_stats, gemm_qkv, attention, gemm_proj, gemm_fc1, gemm_fc2, gemm_skip, gemm_decode, conv, ee_other, ddpm.
+ * embed, ln_stats, gemm_qkv, attention, gemm_proj, gemm_fc1, gemm_fc2, gemm_skip, gemm_decode, conv, ee_other, ddpm,
+ * tail (the sampler's fused conv + DDPM update + next-step head kernel; ddb_sampler_profile_step only).
  * ee != 0 also evaluates probes and heads (early-exit model).  Used by bench.py for the roofline figures. */
-#define DDB_PROF_CATEGORIES 12
+#define DDB_PROF_CATEGORIES 13
 int ddb_profile_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
                         float* eps_dev, int32_t ee, float* ms_host, int32_t* launches_host, void* stream);
 
@@ -101,16 +105,30 @@ int ddb_ddpm_step(float* x_dev, const float* model_out_dev, const float* z_dev, 
 /* get_samples() DDPM loop (sampler.py:128-139 incl. the model hand-off :135-136; eesampler.py:57-82).
  *   late may be NULL.  switch_t = 1000 - t_switch when the hand-off can trigger (1 <= t_switch <= 1000), else -1:
  *   `early` runs the steps with t >= switch_t, `late` the rest.
- *   ee_threshold < 0: plain U-ViT forward; otherwise `early` is an early-exit model (ee_mode as above). */
+ *   ee_mode -1: plain U-ViT forward; 0 / 1: `early` is an early-exit model (simulate / compact, see ddb_ee_forward)
+ *   and ee_threshold is eesampler.py's --threshold.  Any threshold is meaningful: a negative one selects layer 0's
+ *   head for every sample, exactly like the reference's argmax over an all-false mask (eesampler.py:62-67). */
 int ddb_sampler_create(ddb_model* early, ddb_model* late, int32_t switch_t, int32_t B, const float* coef_host,
                        int32_t step_mode, float ee_threshold, int32_t ee_mode, ddb_sampler** out);
 void ddb_sampler_destroy(ddb_sampler* s);
+/* Data-parallel sharding: `first_row` = index of this shard's first sample in the global batch (default 0).  The
+ * in-kernel Philox noise is keyed by (seed, t, GLOBAL element index), so the shards of a global batch draw exactly the
+ * z_t a single-GPU run of the whole batch draws: N-GPU sampling == 1-GPU sampling row for row. */
+int ddb_sampler_set_noise_offset(ddb_sampler* s, uint64_t first_row);
+/* One eager step at timestep t on the early (late = 0) or late backbone with a CUDA-event pair around every kernel:
+ * per-category device ms / launch counts like ddb_profile_forward, but of the step as the sampler runs it (fused
+ * tail, early-exit kernels, DDPM update).  x_dev is updated in place. */
+int ddb_sampler_profile_step(ddb_sampler* s, float* x_dev, const int64_t* y_dev, int32_t t, int32_t late,
+                             float* ms_host, int32_t* launches_host, void* stream);
 /* Runs steps t = t_first, t_first-1, ..., t_last in place on x_dev.
  *   z_all_dev: injected noise [1000, n] indexed by t, or NULL (Philox, `seed`).
  *   eps_trace_dev / x_trace_dev: optional [n_steps, n] per-step model output / x_{t-1} (parity tests).
  *   exit_idx_trace_dev [1000, B] i32 and score_mean_trace_dev [1000, depth] f32 are indexed by t like the
- *   reference's indices_by_timestep / error_prediction_by_timestep logs (eesampler.py:54-55,71-72).
- *   use_graph != 0 replays one captured CUDA graph per backbone (eps/x traces must then be NULL). */
+ *   reference's indices_by_timestep / error_prediction_by_timestep logs (eesampler.py:54-55,71-72); only the rows
+ *   t_last..t_first are written.  In compact mode (ee_mode 1) row t of the score log holds, per layer, the mean over
+ *   the samples STILL IN THE BATCH at that layer (the reference's batch mean needs the dead layers evaluated).
+ *   use_graph != 0 replays one captured CUDA graph per backbone (eps/x traces must then be NULL).  The captured step
+ *   only touches sampler-owned memory (x, labels and logs are staged), so caller pointers may change between calls. */
 int ddb_sampler_run(ddb_sampler* s, float* x_dev, const int64_t* y_dev, const float* z_all_dev, uint64_t seed,
                     int32_t t_first, int32_t t_last, float* eps_trace_dev, float* x_trace_dev,
                     int32_t* exit_idx_trace_dev, float* score_mean_trace_dev, int32_t use_graph, void* stream);
@@ -122,7 +140,11 @@ int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, con
                          float* x_trace_dev, int32_t use_graph, void* stream);
 /* samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146). */
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
-/* Runtime switches for A/B measurements: "gemm_variant" = 2 (CTA-pair kernel, default) or 1 (single-CTA kernel). */
+/* Process-wide runtime switches for A/B measurements (DESIGN.md lists them): "alt_dir", "attn_discard", "pdl",
+ * "mlp_split", "l2_hints", ...; the measured-and-rejected kernel variants ("gemm_variant" = 1, "gemm_ts", "attn_x2",
+ * "gemm_bn128", "gemm_ln_cfg") exist only in libraries built with DDB_EXPERIMENTAL=1 (ddb_version() then ends in
+ * "+experimental"); selecting one in a product build fails with DDB_ERR_INVALID.  Captured step graphs are
+ * re-captured after any change. */
 int ddb_set_option(const char* name, int32_t value);
 /* Bench-only instrumentation hooks (tools/): "attn_trace" = device buffer [items][2][8] of clock64() stamps. */
 int ddb_debug_set_ptr(const char* name, void* dev_ptr);
@@ -168,14 +190,15 @@ int ddb_ae_decode_debug(ddb_ae* ae, const float* z_dev, int32_t B, float* img_de
 /* ---- single-operator entry points (used by the parity tests; same kernels as the model path) ---- */
 /* out[M,N] = epi([A0|A1] W^T); bf16 row-major operands.  epi: 0 bias, 1 LN-fold, 2 LN-fold+GELU, 3 bias+residual.
  * stats_out_dev (optional, [M, N/64, 2] f32): per-row (mean, M2) of every 64-column output chunk.
- * variant 0: the model path's kernel; 1: single-CTA 128x256 tiles; 2: CTA-pair (cta_group::2) 256x256 tiles. */
+ * variant 0: the model path's kernel; 2: CTA-pair (cta_group::2) 256x256 tiles; 1: single-CTA 128x256 tiles
+ * (DDB_EXPERIMENTAL builds only). */
 int ddb_op_gemm(const void* a0_dev, const void* a1_dev, const void* w_dev, const float* bias_dev,
                 const float* colsum_dev, const float* stats_dev, int32_t nparts, int32_t ln_dim,
                 const void* residual_dev, void* out_dev, float* stats_out_dev, int32_t M, int32_t N, int32_t K0,
                 int32_t K1, int32_t epi, int32_t variant, void* stream);
 /* softmax(q k^T / 8) v over qkv [B*L, 3*H*64] bf16 -> out [B*L, H*64] bf16 (models/uvit.py:159-164).
- * variant 0: the model path's choice (tcgen05/TMEM kernel when L = 256 + {1,2}, else the mma.sync kernel);
- * 1: force the generic mma.sync kernel; 2: force the tcgen05 kernel. */
+ * variant 0 / 2: the tcgen05/TMEM kernel of the model path (needs L = 256 + {1,2}, true for every reference config);
+ * 1: generic-L mma.sync kernel, 3: two softmax threads per row (both DDB_EXPERIMENTAL builds only). */
 int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, int32_t H, int32_t variant,
                      void* stream);
 /* per-row (mean, M2) of x [M, D] bf16 -> stats [M,2] f32 */

@@ -304,8 +304,9 @@ def to_samples_nhwc(x: torch.Tensor) -> torch.Tensor:
 
 
 def ee_sample(ee_model, threshold: float, depth: int, x_T: torch.Tensor, noise, y=None, t_first: int = 999,
-              t_last: int = 0):
-    """eesampler.py:57-82 — returns (x_0, error_prediction_by_timestep [1000, depth], indices_by_timestep [1000, B])."""
+              t_last: int = 0, trace: dict | None = None):
+    """eesampler.py:57-82 — returns (x_0, error_prediction_by_timestep [1000, depth], indices_by_timestep [1000, B]).
+    ``trace`` (tests): per step the input x_t and the per-sample probe outputs [depth+1, B], keyed by t."""
     sch = ddpm_schedule(x_T.device)
     B = x_T.shape[0]
     err_log = torch.zeros(1000, depth)
@@ -318,6 +319,9 @@ def ee_sample(ee_model, threshold: float, depth: int, x_T: torch.Tensor, noise, 
         eps, indices, scores = ee_select(eps_full, cls, outs, threshold)
         err_log[t] = scores.mean(axis=1)[:depth]
         idx_log[t, :] = indices
+        if trace is not None:
+            trace.setdefault("x_in", {})[t] = x
+            trace.setdefault("scores", {})[t] = scores
         z = None
         if t > 0:
             z = noise(t) if callable(noise) else noise[t]

@@ -45,14 +45,21 @@ def _lib():
     return _lib, _lib.load()
 
 
+def _need_experimental():
+    """Measured-and-rejected kernel variants are only compiled with DDB_EXPERIMENTAL=1 (duodiff_b200/_build.py)."""
+    lib, L = _lib()
+    if b"+experimental" not in L.ddb_version():
+        pytest.skip("kernel variant only exists in DDB_EXPERIMENTAL builds")
+
+
 def _model(name, seed, hot, dev, ee=False):
     import duodiff_b200 as ddb
     torch.manual_seed(seed)
     net = ddb.UViT(**CONFIGS[name])
     if ee:
         net = ddb.EarlyExitUViT(net, "mlp_probe_per_layer")
-    if hot:
-        heat_(net, seed + 100)
+    if hot:  # True: heat_()'s default x4 Linear scale; a float: that scale (the 17- and 21-block backbones use x2)
+        heat_(net, seed + 100, scale=4.0 if hot is True else float(hot))
     net = net.eval().to(dev)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     return net, sd, O.UViTSpec.from_params(CONFIGS[name])
@@ -68,8 +75,10 @@ def _model(name, seed, hot, dev, ee=False):
     (257 * 128, 512, 2048, 0, 3), (257 * 128, 512, 512, 512, 0), (257 * 128, 1536, 512, 0, 1),
 ])
 def test_op_gemm(dev, M, N, K0, K1, epi, variant):
-    """variant 2 = CTA-pair (cta_group::2) kernel of the model path, 1 = single-CTA kernel."""
+    """variant 2 = CTA-pair (cta_group::2) kernel of the model path, 1 = single-CTA kernel (experimental builds)."""
     lib, L = _lib()
+    if variant == 1:
+        _need_experimental()
     g = torch.Generator().manual_seed(M + N + epi)
     a0 = (torch.randn(M, K0, generator=g) + 0.3).to(dev).bfloat16()
     a1 = torch.randn(M, K1, generator=g).to(dev).bfloat16() if K1 else None
@@ -113,8 +122,10 @@ def test_op_gemm(dev, M, N, K0, K1, epi, variant):
                                               (1, 257, 1, 3), (2, 257, 8, 3), (3, 258, 12, 3), (40, 258, 16, 3)])
 def test_op_attention(dev, B, L, H, variant):
     """variant 2 = tcgen05/TMEM kernel (the model path), 3 = the same with two softmax threads per query row,
-    1 = generic mma.sync kernel, 0 = dispatcher."""
+    1 = generic mma.sync kernel, 0 = dispatcher.  Variants 1 and 3 (and L != 256 + extras) need an experimental build."""
     lib, Lb = _lib()
+    if variant in (1, 3) or L not in (257, 258):
+        _need_experimental()
     g = torch.Generator().manual_seed(B * 31 + H)
     D = H * 64
     qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.5).to(dev).bfloat16()
@@ -191,6 +202,9 @@ def _forward_case(dev, name, B, hot, seed, ts):
 @pytest.mark.parametrize("name,B,hot", [
     ("celeba_3", 4, False), ("celeba_3", 4, True), ("celeba", 3, False), ("celeba", 3, True),
     ("cifar10", 2, True), ("imagenet64_3", 2, True), ("imagenet256_3", 2, True), ("celeba_3", 1, True),
+    # the full-depth backbones of BASELINE configs 4 and 5 (D = 768 depth 17, D = 1024 depth 21) and the CIFAR shallow one
+    ("imagenet64", 2, 2.0), ("imagenet256", 2, 2.0), ("cifar10_3", 2, True), ("imagenet64", 2, False),
+    ("imagenet256", 3, False),
 ])
 def test_uvit_forward_matches_oracle(dev, name, B, hot):
     _forward_case(dev, name, B, hot, seed=7, ts=[999.0, 431.0, 0.0, 17.0])
@@ -209,6 +223,7 @@ def test_uvit_forward_golden_dims_rejected(dev):
 def test_gemm_variants_agree_on_the_forward(dev):
     """The single-CTA kernel + standalone LN statistics and the CTA-pair kernel + fused statistics are two
     implementations of the same forward."""
+    _need_experimental()
     lib, L = _lib()
     net, sd, spec = _model("celeba", 5, True, dev)
     g = torch.Generator().manual_seed(5)
@@ -235,11 +250,15 @@ def test_scheduling_options_do_not_change_a_bit(dev):
     x = torch.randn(21, 3, 64, 64, generator=g).to(dev)  # 21 x 257 rows: 22 row blocks, odd split 10 / 11 samples
     t = torch.full((21,), 321.0, device=dev)
     base = net(x, t)
-    defaults = {b"alt_dir": 1, b"attn_discard": 1, b"mlp_split": 0, b"gemm_ts": 0}
-    try:
+    defaults = {b"alt_dir": 1, b"attn_discard": 1, b"mlp_split": 0, b"pdl": 1}
+    combos = [{b"alt_dir": 0}, {b"attn_discard": 0}, {b"alt_dir": 0, b"attn_discard": 0}, {b"mlp_split": 1},
+              {b"mlp_split": 1, b"alt_dir": 0}, {b"pdl": 0}]
+    if b"+experimental" in L.ddb_version():
         # (gemm_ts: the K <= 512 GEMMs with the A panel resident in TMEM accumulate in the same order -> same bits)
-        for opts in ({b"alt_dir": 0}, {b"attn_discard": 0}, {b"alt_dir": 0, b"attn_discard": 0}, {b"mlp_split": 1},
-                     {b"mlp_split": 1, b"alt_dir": 0}, {b"gemm_ts": 1}, {b"gemm_ts": 1, b"alt_dir": 0}):
+        defaults[b"gemm_ts"] = 0
+        combos += [{b"gemm_ts": 1}, {b"gemm_ts": 1, b"alt_dir": 0}]
+    try:
+        for opts in combos:
             for k, v in {**defaults, **opts}.items():
                 lib.check(L.ddb_set_option(k, v))
             assert torch.equal(net(x, t), base), opts
@@ -347,15 +366,21 @@ def test_ee_forward_matches_oracle(dev, hot):
     assert net.engine(B).ee_forward(x, t, None, threshold=0.0)[1].eq(13).all()
 
 
-@pytest.mark.parametrize("name,B", [("celeba", 9), ("imagenet64_3", 5)])
-def test_ee_compaction_equals_simulation(dev, name, B):
+@pytest.mark.parametrize("name,B,scale", [("celeba", 9, 4.0), ("imagenet64_3", 5, 4.0),
+                                          # deediff_imagenet64.yaml (depth 17: 9 live buffers before block 8) and
+                                          # deediff_imagenet256.yaml (depth 21: 11 live buffers) -- EE_MAX_LIVE = 16
+                                          ("imagenet64", 4, 2.0), ("imagenet256", 3, 2.0),
+                                          # BASELINE batch: ee_decide's single 1024-thread CTA and the in-place
+                                          # compaction at 128 samples
+                                          ("celeba", 128, 4.0)])
+def test_ee_compaction_equals_simulation(dev, name, B, scale):
     """mode 1 (leavers are squeezed out of the batch, later kernels run on fewer rows) must give every sample the
     same eps and exit index as mode 0 (the reference's evaluate-everything semantics) -- bit for bit, because every
     kernel is batch-invariant -- and both must agree with the oracle's selection."""
     import duodiff_b200 as ddb
     torch.manual_seed(15)
     net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS[name]), "mlp_probe_per_layer")
-    heat_(net, 16)
+    heat_(net, 16, scale=scale)
     depth = CONFIGS[name]["depth"]
     _spread_probes(net, depth)
     net = net.eval().to(dev)
@@ -368,8 +393,12 @@ def test_ee_compaction_equals_simulation(dev, name, B):
     eng = net.engine(B)
     with torch.no_grad():
         r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t, y)
+    dev_max = max((a - b).abs().max().item()
+                  for a, b in zip(eng.ee_forward(x, t, y, threshold=0.0, mode=0)[2], r_cls))
+    print(f"{name} B={B}: probe max deviation {dev_max:.2e}")
+    assert dev_max <= PROBE_MARGIN_HOT
     seen = set()
-    for thr in (0.0, 0.2, 0.35, 0.5, 0.65, 0.8, 1.0):
+    for thr in (-1.0, 0.0, 0.2, 0.35, 0.5, 0.65, 0.8, 1.0):
         e0, i0, s0, _ = eng.ee_forward(x, t, y, threshold=thr, mode=0)
         e1, i1, s1, o1 = eng.ee_forward(x, t, y, threshold=thr, mode=1)
         torch.cuda.synchronize()
@@ -389,6 +418,10 @@ def test_ee_compaction_equals_simulation(dev, name, B):
         assert rel_l2(e1[ok], r_sel[ok]) <= EPS_REL_L2
         seen.update(i1.tolist())
     assert len(seen) >= 4, f"exit layers exercised: {sorted(seen)}"  # compaction happened at several depths
+    # eesampler.py:62-67 with a negative threshold: argmax over an all-false mask -> layer 0's head for every sample
+    for mode in (0, 1):
+        e, i, _, _ = eng.ee_forward(x, t, y, threshold=-1.0, mode=mode)
+        assert i.eq(0).all() and rel_l2(e, r_outs[0]) <= EPS_REL_L2
 
 
 def test_ee_sampler_compact_mode_matches_simulate(dev):
@@ -527,10 +560,15 @@ def test_ddim_step_kernel_matches_reference_expression(dev):
             assert rel_l2(xd.cpu(), ref) <= 1e-6, (steps, eta, t)
 
 
-def test_ee_sampler_logs(dev):
-    """eesampler.get_samples: indices log and batch-mean probe log, indexed by t (eesampler.py:54-55,71-72)."""
+def test_ee_sampler_logs_teacher_forced(dev):
+    """eesampler logs under the margin rule: every step of the oracle's trajectory is replayed on
+    the oracle's own x_t, so one flipped exit cannot cascade, and EVERY index mismatch must be explained by a probe
+    within the margin of the threshold.  Also: only the rows of the steps a call covered are written, the batch-mean
+    probe log matches (eesampler.py:71), graph replay and eager steps agree, and get_samples() returns the logs in the
+    reference's shapes / dtypes."""
     import duodiff_b200 as ddb
     from duodiff_b200 import eesampler as ES
+    from duodiff_b200.ddpm import Sampler
     torch.manual_seed(8)
     net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["cifar10"]), "mlp_probe_per_layer")
     heat_(net, 9)
@@ -538,19 +576,126 @@ def test_ee_sampler_logs(dev):
     net = net.eval().to(dev)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     spec = O.UViTSpec.from_params(CONFIGS["cifar10"])
-    B, thr = 3, 0.4
+    B, thr = 4, 0.4
     g = torch.Generator().manual_seed(6)
     noise = torch.randn(1000, B, 3, 32, 32, generator=g)
-    samples, err_log, idx_log = ES.get_samples(net, B, seed=1, num_channels=3, sample_height=32, sample_width=32,
-                                               threshold=thr, depth=13, noise=noise)
-    assert samples.shape == (B, 32, 32, 3) and err_log.shape == (1000, 13) and idx_log.shape == (1000, B)
+    nz = noise.to(dev)
     torch.manual_seed(1)
     x_T = torch.randn(B, 3, 32, 32).to(dev)
     model = lambda x, t, y: O.ee_forward(sd, spec, x, t, y)  # noqa: E731
-    nz = noise.to(dev)
-    # teacher-free comparison over the first 40 steps (before one flipped exit can cascade)
-    x0, r_err, r_idx = O.ee_sample(model, thr, 13, x_T, nz, t_first=999, t_last=960)
-    sl = slice(960, 1000)
-    assert (idx_log[sl] != r_idx[sl]).float().mean().item() <= 0.05
-    assert (err_log[sl] - r_err[sl]).abs().max().item() <= PROBE_MARGIN_HOT
-    assert np.isfinite(samples).all()
+    trace = {}
+    _x0, r_err, r_idx = O.ee_sample(model, thr, 13, x_T, nz, t_first=999, t_last=960, trace=trace)
+    smp = Sampler(net.engine(B), None, np.inf, B, ee_threshold=thr, ee_mode=0)
+    n_diff = n_exits = 0
+    for t in range(999, 959, -1):
+        x = trace["x_in"][t].clone()
+        exit_log = torch.full((1000, B), -7, device=dev, dtype=torch.int32)
+        score_log = torch.full((1000, 13), -7.0, device=dev)
+        smp.run(x, noise=nz, t_first=t, t_last=t, exit_log=exit_log, score_log=score_log, use_graph=(t % 2 == 0))
+        scores = trace["scores"][t]  # [depth + 1, B] probe outputs of the oracle on the same x_t
+        near = ((scores[:-1] - thr).abs() < PROBE_MARGIN_HOT).any(0)
+        same = exit_log[t].long() == r_idx[t].long().to(dev)
+        assert bool((same | near).all()), (t, exit_log[t].tolist(), r_idx[t].tolist())
+        n_diff += int((~same).sum())
+        n_exits += int((r_idx[t] < 13).sum())
+        assert (score_log[t].cpu() - r_err[t]).abs().max().item() <= PROBE_MARGIN_HOT
+        mask = torch.ones(1000, dtype=torch.bool, device=dev)
+        mask[t] = False
+        assert exit_log[mask].eq(-7).all() and score_log[mask].eq(-7.0).all()  # other rows are the caller's
+        if t > 960 and bool(same.all()):  # the step itself, on the samples that took the same exit
+            assert rel_l2(x, trace["x_in"][t - 1]) <= 5e-3
+    print(f"teacher-forced: {n_diff} index mismatches (all within the margin) over 40 steps x {B} samples; "
+          f"{n_exits} early exits in the oracle's log")
+    assert n_exits > 0, "no early exits: the test would not exercise the selection"
+    # the public API: shapes / dtypes of eesampler.py:88-89, and its first step (same x_T) under the margin rule
+    samples, err_log, idx_log = ES.get_samples(net, B, seed=1, num_channels=3, sample_height=32, sample_width=32,
+                                               threshold=thr, depth=13, noise=noise)
+    assert samples.shape == (B, 32, 32, 3) and err_log.shape == (1000, 13) and idx_log.shape == (1000, B)
+    assert idx_log.dtype == torch.float32 and err_log.dtype == torch.float32 and np.isfinite(samples).all()
+    near = ((trace["scores"][999][:-1] - thr).abs() < PROBE_MARGIN_HOT).any(0).cpu()
+    assert bool(((idx_log[999] == r_idx[999]) | near).all())
+    assert (err_log[999] - r_err[999]).abs().max().item() <= PROBE_MARGIN_HOT
+
+
+def test_fused_step_equals_unfused_kernels(dev):
+    """The sampler's step ends in step_tail_kernel (3x3 conv + DDPM update + patch matrix / time token of the NEXT
+    step) and skips patch_gather / token_extras at its head.  It must give, bit for bit, what the stand-alone entry
+    points give: UViT.forward (patch_gather, token_extras, conv3x3) followed by ddb_ddpm_step -- across the DuoDiff
+    hand-off, for graph replay and eager launches, with injected noise and with the Philox stream."""
+    lib, L = _lib()
+    from duodiff_b200.ddpm import Sampler, step_coefficients
+    for pair, B in ((("celeba_3", "celeba"), 5), (("imagenet256_3", "imagenet256_3"), 3)):
+        early, _, spec = _model(pair[0], 51, True, dev)
+        late, _, _ = _model(pair[1], 52, True, dev)
+        C, H = spec.in_chans, spec.img_size
+        g = torch.Generator(device=dev).manual_seed(3)
+        x_T = torch.randn(B, C, H, H, device=dev, generator=g)
+        y = torch.randint(0, spec.num_classes, (B,), device=dev, generator=g) if spec.num_classes > 0 else None
+        noise = torch.zeros(1000, B, C, H, H, device=dev)
+        noise[695:705] = torch.randn(10, B, C, H, H, device=dev, generator=g)
+        table, mode = step_coefficients("predict_noise")
+        coef = table.to(dev)
+        for injected in (True, False):
+            ref = x_T.clone()
+            for t in range(702, 696, -1):
+                net = early if t >= 700 else late
+                eps = net(ref, torch.full((B,), float(t), device=dev), y)
+                lib.check(L.ddb_ddpm_step(ref.data_ptr(), eps.data_ptr(), noise[t].data_ptr() if injected else None,
+                                          coef.data_ptr(), t, mode, 77, ref.numel(), lib.current_stream_ptr()))
+            smp = Sampler(early.engine(B), late.engine(B), 300, B)
+            for use_graph in (True, False):
+                x = x_T.clone()
+                smp.run(x, y=y, noise=noise if injected else None, seed=77, t_first=702, t_last=697,
+                        use_graph=use_graph)
+                assert torch.equal(x, ref), (pair, injected, use_graph)
+            # eps / x traces of the eager path are the per-step model outputs and updated x
+            x = x_T.clone()
+            eps_tr, x_tr = torch.zeros(6, B, C, H, H, device=dev), torch.zeros(6, B, C, H, H, device=dev)
+            smp.run(x, y=y, noise=noise if injected else None, seed=77, t_first=702, t_last=697, eps_trace=eps_tr,
+                    x_trace=x_tr)
+            assert torch.equal(x, ref) and torch.equal(x_tr[-1], ref)
+            assert torch.equal(eps_tr[0], early(x_T, torch.full((B,), 702.0, device=dev), y))
+
+
+def test_philox_shards_draw_the_global_noise(dev):
+    """The in-kernel noise is keyed by (seed, t, GLOBAL element index): two shards with set_noise_offset() reproduce the
+    whole-batch run bit for bit, and consecutive seeds are different streams (seed + rank collided)."""
+    from duodiff_b200.ddpm import Sampler
+    net, _, _ = _model("cifar10_3", 61, False, dev)
+    g = torch.Generator(device=dev).manual_seed(8)
+    x_T = torch.randn(8, 3, 32, 32, device=dev, generator=g)
+    whole = x_T.clone()
+    Sampler(net.engine(8), None, np.inf, 8).run(whole, seed=5, t_first=999, t_last=990)
+    for lo, hi in ((0, 3), (3, 8)):
+        part = x_T[lo:hi].clone()
+        smp = Sampler(net.engine(8), None, np.inf, hi - lo)
+        smp.set_noise_offset(lo)
+        smp.run(part, seed=5, t_first=999, t_last=990)
+        assert torch.equal(part, whole[lo:hi]), (lo, hi)
+    other = x_T.clone()
+    Sampler(net.engine(8), None, np.inf, 8).run(other, seed=6, t_first=999, t_last=990)
+    assert (other - whole).abs().max().item() > 1e-2
+    # rank r of a (seed, rank) grid must not replay rank r-1 of seed + 1
+    a = x_T[:4].clone()
+    s1 = Sampler(net.engine(8), None, np.inf, 4)
+    s1.set_noise_offset(4)
+    s1.run(a, seed=5, t_first=999, t_last=990)
+    b = x_T[:4].clone()
+    s2 = Sampler(net.engine(8), None, np.inf, 4)
+    s2.run(b, seed=6, t_first=999, t_last=990)
+    assert (a - b).abs().max().item() > 1e-2
+
+
+def test_labels_are_range_checked(dev):
+    """nn.Embedding raises IndexError for a label outside [0, num_classes) (models/uvit.py:361-363); so do the shims --
+    the kernels never read outside the table."""
+    from duodiff_b200.ddpm import Sampler
+    net, _, spec = _model("imagenet64_3", 71, False, dev)
+    x = torch.zeros(2, 3, 64, 64, device=dev)
+    t = torch.zeros(2, device=dev)
+    for bad in (torch.tensor([0, 1000]), torch.tensor([-1, 5])):
+        with pytest.raises(IndexError):
+            net(x, t, bad.to(dev))
+        with pytest.raises(IndexError):
+            Sampler(net.engine(2), None, np.inf, 2).run(x.clone(), y=bad.to(dev), t_first=999, t_last=999)
+    assert torch.isfinite(net(x, t, torch.tensor([0, 999], device=dev))).all()

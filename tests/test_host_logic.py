@@ -244,3 +244,42 @@ def test_bench_reference_arm_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["value"] > 0 and d["gpu_launches"] == 0
+
+
+def test_cli_labels_follow_the_reference_draw_modulo_num_classes():
+    """sampler.py:314-318: `--class_id` draws torch.randint(1, 1001, (B,)) after seed_everything(seed).  The shims keep
+    that draw and take it modulo num_classes (documented deviation: label 1000 cannot index a 1000-row table)."""
+    torch.manual_seed(11)
+    ref = torch.randint(1, 1001, (4096,))
+    torch.manual_seed(11)
+    y = sampler.draw_labels(4096, 1000)
+    assert y.dtype == torch.int64 and int(y.min()) >= 0 and int(y.max()) <= 999
+    ok = ref < 1000
+    assert torch.equal(y[ok], ref[ok]) and y[~ok].eq(0).all()  # only the reference's out-of-range label changes
+    torch.manual_seed(11)
+    assert torch.equal(sampler.draw_labels(4096, 1001), ref)  # ImageNet-256 configs: 1001 classes, nothing changes
+    assert eesampler.draw_labels is sampler.draw_labels
+
+
+def test_top_level_cli_shims_reexport_the_reference_names():
+    """`python sampler.py ...` / `python eesampler.py ...` work from the repository root like in the reference."""
+    import importlib.util
+    for name, mod, names in (("sampler.py", sampler, ("main", "get_samples", "get_args", "dump_samples",
+                                                      "dump_statistics", "predict_noise_postprocessing",
+                                                      "predict_original_postprocessing",
+                                                      "predict_previous_postprocessing")),
+                             ("eesampler.py", eesampler, ("main", "get_samples", "get_args", "dump_samples",
+                                                          "dump_statistics"))):
+        spec = importlib.util.spec_from_file_location("_shim_" + name[:-3], ROOT / name)
+        shim = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(shim)
+        for n in names:
+            assert getattr(shim, n) is getattr(mod, n), (name, n)
+
+
+def test_engine_rejects_threshold_free_early_exit_flag_confusion():
+    """Early exit is switched by ee_mode, not by the sign of the threshold: the Sampler passes ee_mode = -1
+    exactly when no threshold is given."""
+    import inspect
+    src = inspect.getsource(ddpm.Sampler.__init__)
+    assert "-1 if ee_threshold is None" in src
