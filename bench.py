@@ -2,20 +2,27 @@
 """bench.py — DuoDiff sampling throughput (images/sec, 1000 DDPM steps, t_switch=300) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config celeba] [--batch 128]
+                    [--ee [--threshold 0.08] [--slope 0.5]] [--decode] [--verify-shards]
 
 A "step" is one pass of the hot path over one batch: a full 1000-step DuoDiff sampling of `batch` images per GPU
 (300 shallow-U-ViT steps, 700 full-U-ViT steps, 1000 DDPM updates).  One JSON line on stdout (rank 0):
   value  = whole-job images/sec with x_T already resident in HBM, CUDA-event timed, max over ranks
   e2e    = the same through the public API duodiff_b200.sampler.get_samples(): x_T drawn on the host, pinned
            H2D copy, 1000 steps, (x+1)/2 NHWC, D2H to numpy — all inside the timed region
-  roofline / kernels = per-kernel CUDA-event timings of one shallow + one full forward (ddb_profile_forward)
-  cpu_baseline = the oracle (or baseline/_ref when present) on the host cores, bounded sample, rank 0, N=1 only
-`--impl reference` times the reference's own CPU implementation of the path instead (see DESIGN.md §Measurement).
+  roofline / kernels = per-kernel CUDA-event timings of one shallow + one full sampling STEP as the sampler runs it
+           (ddb_sampler_profile_step, eager), tensor-bound categories as TFLOP/s vs the sustained bf16 peak,
+           memory-bound ones as GB/s vs the measured HBM copy bandwidth; `step_ms_in_graph` = the same steps timed as
+           CUDA-graph replays, which is what `ms_per_step` is made of (eager event pairs lose the PDL overlap)
+  cpu_baseline = the UNMODIFIED reference (baseline/_ref) on the host cores, bounded sample, rank 0, N=1 only
+`--impl reference` times the reference's own CPU implementation of the path instead (see DESIGN.md §5).
+`--ee` measures BASELINE config 3 (DeeDiff early exit, compaction mode) instead of the DuoDiff pair.
+`--verify-shards` is a correctness run, not a benchmark: N-rank sharded sampling == single-GPU sampling row for row.
 """
 from __future__ import annotations
 
 import argparse
 import contextlib
+import io
 import json
 import os
 import statistics
@@ -40,6 +47,7 @@ PAIRS = {  # BASELINE.json configs -> (shallow, full, default batch per GPU)
 }
 T_SWITCH = 300
 METRIC = "images/sec (DuoDiff sampling, 1000 steps)"
+METRIC_EE = "images/sec (DeeDiff early-exit sampling, 1000 steps)"
 
 
 def forward_flops(p: dict) -> dict:
@@ -57,6 +65,33 @@ def forward_flops(p: dict) -> dict:
     return per
 
 
+def block_flops(p: dict, i: int) -> int:
+    """FLOPs per image of block i alone (long-skip GEMM included for the out-blocks)."""
+    D, d = p["embed_dim"], p["depth"]
+    L = (p["img_size"] // p["patch_size"]) ** 2 + (2 if p["num_classes"] > 0 else 1)
+    f = 24 * L * D * D + 4 * L * L * D
+    return f + (4 * L * D * D if i > d // 2 else 0)
+
+
+def launch_bytes(p: dict, B: int) -> dict:
+    """ALGORITHMIC HBM bytes per launch of the memory-bound categories: every tensor the kernel must
+    read or write once, nothing for re-reads, weights or L2 hits."""
+    D = p["embed_dim"]
+    N = (p["img_size"] // p["patch_size"]) ** 2
+    L = N + (2 if p["num_classes"] > 0 else 1)
+    n = B * p["in_chans"] * p["img_size"] ** 2
+    M = B * L
+    return dict(
+        embed=B * N * 256 + M * D * 2,         # inside the sampler: read the bf16 hi|lo patch matrix, write the tokens
+        attention=M * 3 * D * 2 + M * D * 2,   # q|k|v in, o out (bf16)
+        gemm_decode=M * D * 2 + n * 4,         # tokens in (bf16), un-patchified image out (fp32)
+        conv=2 * n * 4,                        # stand-alone 3x3 conv (early-exit heads)
+        ddpm=3 * n * 4,                        # stand-alone update with in-kernel Philox: x, eps in; x out
+        tail=3 * n * 4 + B * N * 256,          # fused: decoder image in, x in/out, next step's patch matrix out
+        ln_stats=M * D * 2,                    # early exit: probe + LayerNorm statistics pass over the block input
+    )
+
+
 def peaks() -> dict:
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -64,6 +99,14 @@ def peaks() -> dict:
         return dict(tflops=d.get("bf16_tflops_sustained", d.get("bf16_tflops")), tflops_burst=d.get("bf16_tflops"),
                     hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def workload_config(name: str, B: int, world: int, extra: str = "") -> dict:
+    """The `config` object of the JSON line: identical for the GPU arm and the reference arm of the same workload."""
+    shallow, full, _ = PAIRS[name]
+    return dict(workload=f"DuoDiff {name} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}" + extra,
+                batch_per_gpu=B, global_batch=B * world, t_switch=T_SWITCH, parallelism=f"dp{world}",
+                l2="no flush: one DDPM step touches ~1 GB of activations+weights (> 126 MB L2)")
 
 
 class ClockSampler:
@@ -114,105 +157,183 @@ class ClockSampler:
                     reasons=sorted(reasons), power_w_max=power or None, samples=len(sm))
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline
-def _ref_modules():
-    """The unmodified reference under baseline/_ref (staged in the build container; travels with gpurun)."""
+# ------------------------------------------------------------------------------------------------ reference (CPU) arm
+def _load_reference():
+    """The UNMODIFIED reference modules staged under baseline/_ref (git-ignored; travels with gpurun): its `sampler`
+    module (get_samples, predict_noise_postprocessing, the module-level schedule) and `models.uvit.UViT`.  matplotlib
+    (only used by dump_samples) is stubbed.  Returns None when the copy is absent -> the oracle port is timed."""
+    import importlib.util
+    import types
     ref = ROOT / "baseline" / "_ref"
-    if not (ref / "models" / "uvit.py").exists():
+    if not (ref / "sampler.py").exists() or not (ref / "models" / "uvit.py").exists():
         return None
-    sys.path.insert(0, str(ref))
+    mpl, pp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = pp
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", pp)
+    sys.path.insert(0, str(ref))  # the reference imports `models.*` / `utils.*` as top-level packages
     try:
-        import contextlib
-        import io
         with contextlib.redirect_stdout(io.StringIO()):
-            from models.uvit import UViT as RefUViT  # type: ignore
-        return RefUViT
-    except Exception:  # noqa: BLE001
+            spec = importlib.util.spec_from_file_location("_duodiff_reference_sampler", ref / "sampler.py")
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        return mod
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] reference import failed ({e!r}); timing the oracle port instead", file=sys.stderr)
         return None
     finally:
         sys.path.remove(str(ref))
 
 
-def cpu_sample(pair: str, batch: int, reps: int, use_reference: bool) -> dict:
-    """Bounded CPU sample of the same workload: `reps` x (one shallow forward + one full forward + 2 DDPM updates)
-    at `batch` images on the host cores, extrapolated to 300 shallow + 700 full steps."""
-    import contextlib
-    import io
-
-    from oracle import uvit_oracle as O
-    shallow, full, _ = PAIRS[pair]
-    torch.manual_seed(1234)
-    RefUViT = _ref_modules() if use_reference else None
-    fwd, kind = {}, "port"
-    for name in (shallow, full):
-        p = CONFIGS[name]
-        if RefUViT is not None:
-            with contextlib.redirect_stdout(io.StringIO()):
-                m = RefUViT(**p).eval()
-            fwd[name] = (lambda mm: (lambda x, t, y: mm(x, t, y)))(m)
-            kind = "reference"
-        else:
-            import duodiff_b200 as ddb
-            sd = ddb.UViT(**p).state_dict()
-            spec = O.UViTSpec.from_params(p)
-            fwd[name] = (lambda s, sp: (lambda x, t, y: O.uvit_forward(s, sp, x, t, y)))(sd, spec)
-    p = CONFIGS[full]
-    sch = O.ddpm_schedule()
-    x = torch.randn(batch, p["in_chans"], p["img_size"], p["img_size"])
-    y = torch.randint(0, p["num_classes"], (batch,)) if p["num_classes"] > 0 else None
-    times = {shallow: [], full: [], "update": []}
-    with torch.no_grad():
-        for rep in range(reps + 1):  # first rep is warm-up
-            for name, t in ((shallow, 800), (full, 400)):
-                tt = t * torch.ones(batch)
-                t0 = time.perf_counter()
-                eps = fwd[name](x, tt, y)
-                t1 = time.perf_counter()
-                x = O.predict_noise_step(sch, eps, x, t, torch.randn_like(x))
-                t2 = time.perf_counter()
-                if rep:
-                    times[name].append(t1 - t0)
-                    times["update"].append(t2 - t1)
-    ts, tf, tu = (statistics.mean(times[k]) for k in (shallow, full, "update"))
-    total = T_SWITCH * ts + (1000 - T_SWITCH) * tf + 1000 * tu
-    return dict(value=batch / total, unit="images/sec", cores=torch.get_num_threads(), kind=kind,
-                sample=f"{reps}x(1 {shallow} fwd + 1 {full} fwd + 2 DDPM updates) at batch {batch}, fp32, "
-                       f"extrapolated to {T_SWITCH}+{1000 - T_SWITCH} steps "
-                       f"(t_shallow={ts:.3f}s t_full={tf:.3f}s t_update={tu:.4f}s)",
-                host_cpus=os.cpu_count())
-
-
 def run_reference(args, rank: int, world: int) -> None:
+    """The reference's CPU implementation of the path on this box's host cores (all threads).  One `step` = a bounded
+    sample of the workload AT THE CONFIGURED BATCH: 1 shallow-backbone forward + 1 full-backbone forward + 2 DDPM
+    updates through the reference's own predict_noise_postprocessing (sampler.py:47-56); value = batch / (300 t_shallow
+    + 700 t_full + 1000 t_update) from the medians over the timed steps.  --full-run executes the unmodified
+    sampler.get_samples for all 1000 steps instead (BASELINE config 1: CIFAR-10, batch 8)."""
     if rank != 0:
         return
     steps, warm = max(args.steps, 1), max(args.warmup, 0)
-    batch = 8
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is entitled to every host thread
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    vals, info = [], None
-    t_begin = time.perf_counter()
-    for i in range(warm + steps):
-        info = cpu_sample(args.config, batch, 1, use_reference=True)
-        if i >= warm:
-            vals.append(info["value"])
-    ms = (time.perf_counter() - t_begin) * 1e3 / (warm + steps)
-    v = statistics.mean(vals)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))  # torchrun exports OMP_NUM_THREADS=1
     shallow, full, default_b = PAIRS[args.config]
     B = args.batch or default_b
-    info["value"] = v
-    # same metric / unit / config as the GPU arm; what was actually timed is described in cpu_baseline.sample
+    ps, pf = CONFIGS[shallow], CONFIGS[full]
+    ref = _load_reference()
+    kind = "reference" if ref is not None else "port"
+    torch.manual_seed(1234)
+    if ref is not None:
+        with contextlib.redirect_stdout(io.StringIO()):
+            nets = {shallow: ref.UViT(**ps).eval(), full: ref.UViT(**pf).eval()}
+        fwd = {k: (lambda mm: (lambda x, t, y: mm(x, t, y)))(m) for k, m in nets.items()}
+        update = ref.predict_noise_postprocessing  # draws z with torch.randn_like like the reference does
+    else:
+        import duodiff_b200 as ddb
+        from oracle import uvit_oracle as O
+        fwd = {}
+        for name, p in ((shallow, ps), (full, pf)):
+            sd, spec = ddb.UViT(**p).state_dict(), O.UViTSpec.from_params(p)
+            fwd[name] = (lambda s, sp: (lambda x, t, y: O.uvit_forward(s, sp, x, t, y)))(sd, spec)
+        sch = O.ddpm_schedule()
+        update = lambda eps, x, t: O.predict_noise_step(sch, eps, x, t, torch.randn_like(x))  # noqa: E731
+    C, H = pf["in_chans"], pf["img_size"]
+    y = torch.randint(0, min(ps["num_classes"], pf["num_classes"]), (B,)) if pf["num_classes"] > 0 else None
+    t_begin = time.perf_counter()
+    if args.full_run:
+        if ref is None:
+            raise SystemExit("--full-run needs the reference copy under baseline/_ref")
+        vals = []
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                out, _ = ref.get_samples(model=nets[shallow], batch_size=B, postprocessing=update, seed=i,
+                                         num_channels=C, sample_height=H, sample_width=H, use_ddim=False,
+                                         ddim_steps=50, ddim_eta=0.0, timesteps_save=[], y=y, autoencoder=None,
+                                         late_model=nets[full], t_switch=T_SWITCH)
+            dt = time.perf_counter() - t0
+            assert out.shape == (B, H, H, C)
+            if i >= warm:
+                vals.append(B / dt)
+        v, sample = statistics.median(vals), (f"{len(vals)} x the unmodified sampler.get_samples, all 1000 steps "
+                                              f"({T_SWITCH} {shallow} + {1000 - T_SWITCH} {full}) at batch {B}, fp32")
+        extra = dict(values=vals)
+    else:
+        x = torch.randn(B, C, H, H)
+        times = {shallow: [], full: [], "update": []}
+        with torch.no_grad():
+            for i in range(warm + steps):
+                for name, t in ((shallow, 800), (full, 400)):
+                    tt = t * torch.ones(B)
+                    t0 = time.perf_counter()
+                    eps = fwd[name](x, tt, y)
+                    t1 = time.perf_counter()
+                    x = update(eps, x, t)
+                    t2 = time.perf_counter()
+                    if i >= warm:
+                        times[name].append(t1 - t0)
+                        times["update"].append(t2 - t1)
+                x = x.clamp(-3, 3)  # the bounded sample repeats two timesteps: keep x in the range of real iterates
+        med = {k: statistics.median(v) for k, v in times.items()}
+        mn = {k: min(v) for k, v in times.items()}
+        total = lambda d: T_SWITCH * d[shallow] + (1000 - T_SWITCH) * d[full] + 1000 * d["update"]  # noqa: E731
+        v = B / total(med)
+        sample = (f"{steps} x (1 {shallow} fwd + 1 {full} fwd + 2 DDPM updates via the reference's "
+                  f"predict_noise_postprocessing) at batch {B}, fp32; medians t_shallow={med[shallow]:.3f}s "
+                  f"t_full={med[full]:.3f}s t_update={med['update']:.4f}s extrapolated to {T_SWITCH}+{1000 - T_SWITCH} steps")
+        extra = dict(value_from_min=B / total(mn), value_from_median=v, reps=steps)
+    ms = (time.perf_counter() - t_begin) * 1e3 / (warm + steps)
+    info = dict(value=v, unit="images/sec", cores=torch.get_num_threads(), kind=kind, sample=sample,
+                host_cpus=os.cpu_count(), **extra)
     line = dict(impl="reference", metric=METRIC, value=v, unit="images/sec", n_gpus=args.gpus, steps=steps,
                 warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic (random-init weights, N(0,1) x_T)",
-                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}",
-                            batch_per_gpu=B, global_batch=B * args.gpus, t_switch=T_SWITCH,
-                            parallelism=f"dp{args.gpus}", l2="n/a (host cores)"),
+                data="synthetic (random-init weights, N(0,1) x_T)", config=workload_config(args.config, B, args.gpus),
                 cpu_baseline=info, e2e=dict(value=v, unit="images/sec", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
+                gpu_launches=0,
+                note=("N > 1: one CPU process on rank 0 only; dividing an N-GPU value by it multiplies the 1-GPU "
+                      "ratio by N" if args.gpus > 1 else None))
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess(args, B: int) -> dict | None:
+    """The reference arm as a child process with the GPU hidden (this process has CUDA initialised; the reference's
+    module-level `device = get_device()` must resolve to the CPU)."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--config", args.config, "--batch", str(B),
+           "--steps", "3", "--warmup", "1"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return dict(error=(r.stderr or r.stdout)[-400:])
+    except Exception as e:  # noqa: BLE001
+        return dict(error=repr(e))
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _kernel_table(prof_fn, fl: dict | None, nbytes: dict, B: int, pk: dict, reps: int = 5) -> dict:
+    """Average `reps` eager profiled steps; per category: ms, launches, share, TFLOP/s (tensor-bound categories) or
+    GB/s + fraction of the measured HBM bandwidth (memory-bound categories, algorithmic bytes)."""
+    for _ in range(2):
+        prof = prof_fn()
+    acc = {k: 0.0 for k in prof}
+    for _ in range(reps):
+        prof = prof_fn()
+        for k, v in prof.items():
+            acc[k] += v["ms"] / reps
+    tot = sum(acc.values())
+    table = {}
+    for k in acc:
+        n = prof[k]["launches"]
+        if not n:
+            continue
+        row = dict(ms=round(acc[k], 4), launches=n, share=round(acc[k] / tot, 4))
+        if fl and k in fl and k.startswith(("gemm_q", "gemm_p", "gemm_f", "gemm_s", "attention")):
+            row["tflops"] = round(fl[k] * B / (acc[k] * 1e-3) / 1e12, 1)
+            row["frac_tensor"] = round(row["tflops"] / pk["tflops"], 4)
+        if k in nbytes:
+            gbps = nbytes[k] * n / (acc[k] * 1e-3) / 1e9
+            row["gbps"] = round(gbps, 1)
+            row["frac_hbm"] = round(gbps / pk["hbm"], 4)
+            row["bytes_per_launch"] = nbytes[k]
+        table[k] = row
+    table["_step_ms_sum_eager"] = round(tot, 4)
+    return table
+
+
+def _time_steps(smp, x, y, t_first: int, n: int) -> float:
+    """ms per step of `n` graph-replayed sampling steps starting at t_first (CUDA events on the launching stream)."""
+    smp.run(x, y=y, seed=1, t_first=t_first, t_last=t_first - n + 1, use_graph=True)  # capture / warm
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    smp.run(x, y=y, seed=1, t_first=t_first, t_last=t_first - n + 1, use_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch.distributed as dist
 
@@ -244,6 +365,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
             ae = AE.FrozenAutoencoderKL(AE.DEFAULT_DDCONFIG, 4, state_dict=AE.random_init_state_dict(seed=4321),
                                         max_batch=min(B, 32))
     smp = Sampler(early.engine(B), late.engine(B), T_SWITCH, B)
+    smp.set_noise_offset(rank * B)  # rows [rank*B, (rank+1)*B) of the global batch
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     n_total = args.warmup + args.steps
     x_all = [torch.randn(B, C, H, H, device=dev, generator=gen) for _ in range(min(n_total, 4))]
@@ -252,7 +374,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
 
     def one_pass(i: int):
         x = x_all[i % len(x_all)].clone()
-        smp.run(x, y=y, seed=rank * 7919 + i, use_graph=True)
+        smp.run(x, y=y, seed=i, use_graph=True)
         out = smp.finalize(ae.decode(x) if ae is not None else x)
         if world > 1:
             dist.all_gather(gathered, out)  # the path's only collective: finished samples
@@ -282,13 +404,10 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     # ---- end-to-end through the public API (host x_T -> H2D -> 1000 steps -> NHWC -> D2H numpy)
     def e2e_pass(i: int):
         with contextlib.redirect_stdout(sys.stderr):
-            return _e2e_pass(i)
-
-    def _e2e_pass(i: int):
-        return S.get_samples(early, B, S.predict_noise_postprocessing, seed=rank * 104729 + i, num_channels=C,
-                             sample_height=H, sample_width=H, use_ddim=False, ddim_steps=50, ddim_eta=0.0,
-                             timesteps_save=[], y=y, autoencoder=ae, late_model=late, t_switch=T_SWITCH,
-                             device=dev)[0]
+            return S.get_samples(early, B, S.predict_noise_postprocessing, seed=i, num_channels=C, sample_height=H,
+                                 sample_width=H, use_ddim=False, ddim_steps=50, ddim_eta=0.0, timesteps_save=[], y=y,
+                                 autoencoder=ae, late_model=late, t_switch=T_SWITCH, device=dev,
+                                 noise_row_offset=rank * B)[0]
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for i in range(min(args.warmup, 1)):
@@ -317,51 +436,51 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     fl_s, fl_f = forward_flops(ps), forward_flops(pf)
     flops_per_image = T_SWITCH * fl_s["total"] + (1000 - T_SWITCH) * fl_f["total"]
 
-    # ---- per-kernel roofline (CUDA events around every launch of one forward, eager)
-    kernels = {}
-    xs = x_all[0]
-    tvec = torch.full((B,), 500.0, device=dev)
-    for name, net, fl in ((shallow, early, fl_s), (full, late, fl_f)):
-        eng = net.engine(B)
-        for _ in range(2):
-            prof = eng.profile_forward(xs, tvec, y)
-        reps = 5
-        acc = {k: 0.0 for k in prof}
-        for _ in range(reps):
-            prof = eng.profile_forward(xs, tvec, y)
-            for k, v in prof.items():
-                acc[k] += v["ms"] / reps
-        tot = sum(acc.values())
-        kernels[name] = {
-            k: dict(ms=round(acc[k], 4), launches=prof[k]["launches"], share=round(acc[k] / tot, 4),
-                    tflops=round(fl[k] * B / (acc[k] * 1e-3) / 1e12, 1) if k in fl and acc[k] > 0 else None)
-            for k in acc if prof[k]["launches"]}
-        kernels[name]["_forward_ms_sum"] = round(tot, 4)
+    # ---- per-kernel roofline: one eager sampling step per backbone with a CUDA-event pair around every launch
+    xs = x_all[0].clone()
+    kernels = {
+        shallow: _kernel_table(lambda: smp.profile_step(xs, 800, False, y), fl_s, launch_bytes(ps, B), B, pk),
+        full: _kernel_table(lambda: smp.profile_step(xs, 400, True, y), fl_f, launch_bytes(pf, B), B, pk),
+    }
+    # the same steps as CUDA-graph replays (PDL overlap kept): what ms_per_step is made of
+    g_s = _time_steps(smp, x_all[0].clone(), y, 999, 50)
+    g_f = _time_steps(smp, x_all[0].clone(), y, 500, 50)
+    step_in_graph = dict(shallow_ms=round(g_s, 4), full_ms=round(g_f, 4),
+                         pass_ms_from_steps=round(T_SWITCH * g_s + (1000 - T_SWITCH) * g_f, 1),
+                         pass_ms_measured=round(ms_max / args.steps, 1),
+                         eager_event_sum_ms=round(T_SWITCH * kernels[shallow]["_step_ms_sum_eager"]
+                                                  + (1000 - T_SWITCH) * kernels[full]["_step_ms_sum_eager"], 1),
+                         note="eager event pairs serialise the kernels (no programmatic-dependent-launch overlap): the "
+                              "per-kernel TFLOP/s and GB/s below are pessimistic by eager_event_sum / pass_ms_from_steps")
     kf = kernels[full]
     # the north star's "fraction of bf16 tensor-core peak on the U-ViT GEMMs": GEMM FLOPs / summed GEMM-kernel time
     gk = [k for k in kf if k.startswith("gemm_") and k != "gemm_decode"]
     gemm_tf = sum(fl_f[k] for k in gk) * B / (sum(kf[k]["ms"] for k in gk) * 1e-3) / 1e12
+    scale = step_in_graph["eager_event_sum_ms"] / step_in_graph["pass_ms_from_steps"]
     gemm_only = dict(tflops=round(gemm_tf, 1), frac_of_sustained_peak=round(gemm_tf / pk["tflops"], 4),
                      frac_of_burst_peak=round(gemm_tf / pk["tflops_burst"], 4) if pk.get("tflops_burst") else None,
-                     kernels=gk)
+                     in_graph_estimate_tflops=round(gemm_tf * scale, 1),
+                     in_graph_estimate_frac_of_sustained=round(gemm_tf * scale / pk["tflops"], 4), kernels=gk)
     dom = max((k for k in kf if not k.startswith("_")), key=lambda k: kf[k]["ms"])
     dom_ms = kf[dom]["ms"] / kf[dom]["launches"]
     dom_flops = fl_f[dom] * B / kf[dom]["launches"]
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text()).get(dom)
+        tj = json.loads(tf.read_text())
+        traffic, traffic_src = tj.get(dom), tj.get("_source")
     roofline = dict(bound="tensor", kernel=f"{dom} (gemm2_tcgen05_kernel, CTA pair)" if dom.startswith("gemm") else dom,
                     achieved=round(achieved, 1), peak=pk["tflops"], unit="TFLOP/s", frac=round(achieved / pk["tflops"], 4),
-                    traffic=traffic, peak_source=pk["source"] + ", sustained bf16",
+                    traffic=traffic, traffic_provenance=("NOT measured in this run: " + traffic_src) if traffic_src else None,
+                    peak_source=pk["source"] + ", sustained bf16; memory-bound kernels vs hbm_gbs copy bandwidth",
                     flops_per_launch=dom_flops, avg_launch_ms=round(dom_ms, 4),
-                    gemm_only=gemm_only,
+                    gemm_only=gemm_only, hbm_peak_gbs=pk["hbm"],
                     whole_path=dict(tflops=round(value * flops_per_image / 1e12, 1),
                                     frac=round(value * flops_per_image / 1e12 / (pk["tflops"] * world), 4),
                                     flops_per_image=flops_per_image))
 
-    cpu = cpu_sample(args.config, 8, 1, use_reference=True) if world == 1 and not args.no_cpu else None
+    cpu = cpu_baseline_subprocess(args, B) if world == 1 and not args.no_cpu else None
     nbytes = B * C * H * H * 4
     out_bytes = B * 256 * 256 * 3 * 4 if ae is not None else nbytes
     ae_info = None
@@ -373,19 +492,239 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     line = dict(metric=METRIC, value=round(value, 3), unit="images/sec", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(ms_max / args.steps, 2), higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16", data="synthetic (random-init weights, N(0,1) x_T, Philox z_t)",
-                config=dict(workload=f"DuoDiff {args.config} ({shallow}+{full}) 1000 DDPM steps, t_switch={T_SWITCH}"
-                            + (" + KL-autoencoder decode to 3x256x256" if ae is not None else ""),
-                            batch_per_gpu=B, global_batch=B * world, t_switch=T_SWITCH, parallelism=f"dp{world}",
-                            l2="no flush: one DDPM step touches ~1 GB of activations+weights (> 126 MB L2)"),
+                config=workload_config(args.config, B, world,
+                                       " + KL-autoencoder decode to 3x256x256" if ae is not None else ""),
                 clocks=clocks.summary(),
                 e2e=dict(value=round(e2e_val, 3), unit="images/sec", h2d_bytes_per_step=nbytes,
                          d2h_bytes_per_step=out_bytes, steps=e2e_steps, api="duodiff_b200.sampler.get_samples"),
-                gpu_launches=int(tt[2].item()), roofline=roofline, kernels=kernels, cpu_baseline=cpu)
+                gpu_launches=int(tt[2].item()), roofline=roofline, step_ms_in_graph=step_in_graph, kernels=kernels,
+                cpu_baseline=cpu)
     if ae_info is not None:
         line["autoencoder"] = ae_info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ early exit (config 3)
+def synthetic_probes_(net, depth: int, slope: float) -> None:
+    """Random-init probes sit at 0.47..0.55 and never cross 0.08: scale the probe weights x4
+    (per-sample spread) and set bias_i = -slope * i so that the probe outputs fall with depth like a trained
+    uncertainty estimator's; `slope` positions the mean exit layer."""
+    with torch.no_grad():
+        for i in range(depth):
+            net.matrix[f"{i}"].classifier[0].weight.mul_(4.0)
+            net.matrix[f"{i}"].classifier[0].bias.fill_(-slope * i)
+
+
+def run_ee(args, rank: int, world: int, local_rank: int) -> None:
+    """BASELINE config 3: DeeDiff / AdaDiff early-exit sampling (deediff_<config>.yaml: the full backbone + one MLP
+    probe and one output head per layer, threshold 0.08), exited samples compacted out of the batch."""
+    import torch.distributed as dist
+
+    import duodiff_b200 as ddb
+    from duodiff_b200 import _lib
+    from duodiff_b200 import eesampler as ES
+    from duodiff_b200.ddpm import Sampler
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _, full, default_b = PAIRS[args.config]
+    B = args.batch or default_b
+    pf = CONFIGS[full]
+    depth, C, H = pf["depth"], pf["in_chans"], pf["img_size"]
+    torch.manual_seed(1234)
+    net = ddb.EarlyExitUViT(ddb.UViT(**pf, max_batch=B), "mlp_probe_per_layer")
+    synthetic_probes_(net, depth, args.slope)
+    net = net.eval().to(dev)
+    eng = net.engine(B)
+    y = torch.randint(0, pf["num_classes"], (B,), device=dev) if pf["num_classes"] > 0 else None
+    lib = _lib.load()
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    x0 = [torch.randn(B, C, H, H, device=dev, generator=gen) for _ in range(2)]
+    exit_log = torch.zeros(1000, B, device=dev, dtype=torch.int32)
+    score_log = torch.zeros(1000, depth, device=dev)
+    samplers = {m: Sampler(eng, None, float("inf"), B, ee_threshold=thr, ee_mode=mode)
+                for m, (thr, mode) in dict(compact=(args.threshold, 1), simulate=(args.threshold, 0),
+                                           never_exit=(0.0, 1)).items()}
+    plain = Sampler(eng, None, float("inf"), B)  # the same backbone without probes / heads
+    for s in list(samplers.values()) + [plain]:
+        s.set_noise_offset(rank * B)
+
+    def one_pass(i: int, smp=samplers["compact"], t_last=0):
+        x = x0[i % 2].clone()
+        smp.run(x, y=y, seed=i, t_first=999, t_last=t_last, exit_log=exit_log if smp is not plain else None,
+                score_log=score_log if smp is not plain else None, use_graph=True)
+        return smp.finalize(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_pass(i)
+    barrier()
+    l0 = lib.ddb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record()
+        for i in range(args.steps):
+            out = one_pass(args.warmup + i)
+        e1.record()
+        barrier()
+    launches = lib.ddb_launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    assert torch.isfinite(out).all()
+    idx = exit_log.float()  # [1000, B] of the last pass
+    mean_exit = idx.mean().item()
+    # FLOPs actually needed: blocks executed per sample = its exit index (depth = never left), + token assembly
+    blocks = torch.tensor([block_flops(pf, i) for i in range(depth)], dtype=torch.float64)
+    cum = torch.cat([torch.zeros(1, dtype=torch.float64), blocks.cumsum(0)]).to(dev)
+    flops_pass = cum[exit_log.long()].sum().item()  # sum over (t, sample)
+
+    # side measurements on 100 steps: simulate (reference semantics), never-exit (threshold 0) and the plain backbone
+    side = {}
+    for name, smp in list(samplers.items()) + [("plain_backbone", plain)]:
+        one_pass(0, smp, 950)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one_pass(1, smp, 900)
+        b.record()
+        barrier()
+        side[name + "_ms_per_step"] = round(a.elapsed_time(b) / 100, 4)
+    side["compact_speedup_over_simulate"] = round(side["simulate_ms_per_step"] / side["compact_ms_per_step"], 3)
+    side["never_exit_overhead_vs_plain"] = round(side["never_exit_ms_per_step"] / side["plain_backbone_ms_per_step"] - 1, 4)
+
+    def e2e_pass(i: int):
+        with contextlib.redirect_stdout(sys.stderr):
+            return ES.get_samples(net, B, seed=i, num_channels=C, sample_height=H, sample_width=H,
+                                  threshold=args.threshold, depth=depth, y=y, mode=1, device=dev,
+                                  noise_row_offset=rank * B)[0]
+
+    e2e_pass(0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for i in range(e2e_steps):
+        host = e2e_pass(100 + i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert host.shape == (B, H, H, C)
+    tt = torch.tensor([ms, e2e_s * 1e3, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * B * args.steps / (tt[0].item() / 1e3)
+    achieved = flops_pass * args.steps / (ms / 1e3) / 1e12  # this rank's executed-block FLOPs
+    prof = _kernel_table(lambda: samplers["compact"].profile_step(x0[0].clone(), 500, False, y), None,
+                         launch_bytes(pf, B), B, pk)
+    line = dict(metric=METRIC_EE, value=round(value, 3), unit="images/sec", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(tt[0].item() / args.steps, 2), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic (random-init weights; probe weights x4, bias_i = -slope*i so that exits occur)",
+                config=dict(workload=f"DeeDiff {args.config} (deediff_{args.config}.yaml, mlp_probe_per_layer) 1000 DDPM "
+                                     f"steps, threshold {args.threshold}, per-sample exit compaction",
+                            batch_per_gpu=B, global_batch=B * world, threshold=args.threshold, probe_slope=args.slope,
+                            parallelism=f"dp{world}",
+                            l2="no flush: one DDPM step touches ~1 GB of activations+weights (> 126 MB L2)"),
+                clocks=clocks.summary(),
+                e2e=dict(value=round(world * B * e2e_steps / (tt[1].item() / 1e3), 3), unit="images/sec",
+                         h2d_bytes_per_step=B * C * H * H * 4, d2h_bytes_per_step=B * C * H * H * 4, steps=e2e_steps,
+                         api="duodiff_b200.eesampler.get_samples(mode=1)"),
+                gpu_launches=int(tt[2].item()),
+                early_exit=dict(mean_exit_layer=round(mean_exit, 3), depth=depth,
+                                exit_histogram=torch.bincount(exit_log.flatten().long().cpu(), minlength=depth + 1).tolist(),
+                                flops_executed_per_image=flops_pass / B, **side),
+                roofline=dict(bound="tensor", kernel="executed blocks (sum of exit indices) of the compacted step",
+                              achieved=round(achieved, 1), peak=pk["tflops"], unit="TFLOP/s",
+                              frac=round(achieved / pk["tflops"], 4), traffic=None,
+                              peak_source=pk["source"] + ", sustained bf16", hbm_peak_gbs=pk["hbm"]),
+                kernels={"compact_step_t500": prof}, cpu_baseline=None)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ N-GPU correctness
+def run_verify(args, rank: int, world: int, local_rank: int) -> None:
+    """NCCL correctness, not speed: the all-gathered result of N sharded ranks must equal rank 0's own
+    single-GPU run of the GLOBAL batch, row for row -- DuoDiff with the hand-off inside the run (39 DDIM steps through
+    the public get_samples API), once with injected noise and once with the seed-keyed Philox stream, plus the
+    eesampler index / probe logs through duodiff_b200.distributed."""
+    import numpy as np
+    import torch.distributed as dist
+
+    import duodiff_b200 as ddb
+    from duodiff_b200 import distributed as D
+    from duodiff_b200 import eesampler as ES
+    from duodiff_b200 import sampler as S
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shallow, full, _ = PAIRS[args.config]
+    ps, pf = CONFIGS[shallow], CONFIGS[full]
+    per = args.batch or 8
+    G = per * world + (1 if world > 1 else 0)  # uneven shards
+    C, H = pf["in_chans"], pf["img_size"]
+    torch.manual_seed(1234)
+    early = ddb.UViT(**ps, max_batch=G).eval().to(dev)
+    late = ddb.UViT(**pf, max_batch=G).eval().to(dev)
+    g = torch.Generator().manual_seed(99)
+    noise = torch.randn(1000, G, C, H, H, generator=g)
+    y = torch.randint(0, min(ps["num_classes"], pf["num_classes"]), (G,), generator=g) if pf["num_classes"] > 0 else None
+    res = {}
+
+    def gs(**kw):
+        with contextlib.redirect_stdout(sys.stderr):
+            return S.get_samples(early, postprocessing=S.predict_noise_postprocessing, num_channels=C, sample_height=H,
+                                 sample_width=H, use_ddim=True, ddim_steps=40, ddim_eta=0.5, late_model=late,
+                                 t_switch=T_SWITCH, device=dev, **kw)
+    for label, nz in (("injected_noise", noise), ("philox", None)):
+        got = D.get_samples_sharded(gs, G, shape=(C, H, H), noise=nz, y=y, seed=11)
+        if rank == 0:
+            ref = gs(batch_size=G, seed=11, x_T=D.global_x_T(11, G, (C, H, H)), noise=nz,
+                     y=y.to(dev) if y is not None else None)[0]
+            res[label] = dict(equal=bool(np.array_equal(got.cpu().numpy(), ref)),
+                              max_abs_diff=float(np.abs(got.cpu().numpy() - ref).max()), rows=G)
+    # early exit: samples + both logs
+    pe = CONFIGS["cifar10"]
+    torch.manual_seed(4321)
+    ee = ddb.EarlyExitUViT(ddb.UViT(**pe, max_batch=G), "mlp_probe_per_layer")
+    synthetic_probes_(ee, pe["depth"], 0.5)
+    ee = ee.eval().to(dev)
+    lo, hi = D.shard_bounds(G, rank, world)
+    kw = dict(num_channels=3, sample_height=32, sample_width=32, threshold=0.08, depth=pe["depth"], device=dev)
+    xT = D.global_x_T(5, G, (3, 32, 32))
+    with contextlib.redirect_stdout(sys.stderr):
+        s_loc, err_loc, idx_loc = ES.get_samples(ee, hi - lo, seed=5, x_T=xT[lo:hi], noise_row_offset=lo, **kw)
+    s_all = D.all_gather_rows(torch.from_numpy(s_loc).to(dev), G)
+    err_all, idx_all = D.gather_ee_logs(err_loc.to(dev), idx_loc.to(dev), G)
+    if rank == 0:
+        with contextlib.redirect_stdout(sys.stderr):
+            s_ref, err_ref, idx_ref = ES.get_samples(ee, G, seed=5, x_T=xT, **kw)
+        res["early_exit"] = dict(samples_equal=bool(np.array_equal(s_all.cpu().numpy(), s_ref)),
+                                 indices_equal=bool(torch.equal(idx_all.cpu(), idx_ref)),
+                                 probe_log_max_abs_diff=float((err_all.cpu() - err_ref).abs().max()),
+                                 mean_exit_layer=float(idx_ref.mean()), rows=G)
+        ok = (all(v["equal"] for k, v in res.items() if k != "early_exit") and res["early_exit"]["samples_equal"]
+              and res["early_exit"]["indices_equal"] and res["early_exit"]["probe_log_max_abs_diff"] < 1e-5)
+        print(json.dumps(dict(verify_shards=res, n_gpus=world, backend="nccl" if world > 1 else "none",
+                              config=args.config, ok=ok)), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and not ok:
+        raise SystemExit(1)
 
 
 def main():
@@ -400,11 +739,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--decode", action="store_true",
                     help="latent configs: decode the samples with the KL autoencoder inside the timed regions")
+    ap.add_argument("--ee", action="store_true", help="BASELINE config 3: early-exit sampling with exit compaction")
+    ap.add_argument("--threshold", type=float, default=0.08)
+    ap.add_argument("--slope", type=float, default=0.5, help="--ee: synthetic probe bias slope (sets the mean exit layer)")
+    ap.add_argument("--full-run", action="store_true",
+                    help="--impl reference: run the unmodified get_samples for all 1000 steps (config 1: --config cifar10 --batch 8)")
+    ap.add_argument("--verify-shards", action="store_true", help="N-rank sharded == single-GPU, row for row (not a benchmark)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the CPU arm: the reference's get_device() must pick the host
         run_reference(args, rank, world)
         return
     if world == 1 and args.gpus > 1:
@@ -413,7 +759,12 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__,
                *sys.argv[1:]]
         sys.exit(subprocess.call(cmd))
-    run_ours(args, rank, world, local_rank)
+    if args.verify_shards:
+        run_verify(args, rank, world, local_rank)
+    elif args.ee:
+        run_ee(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -92,7 +92,7 @@ def test_sampler_cli_ddim_class_conditional(tmp_path):
     ck, cfg = _write(tmp_path, "in64", CONFIGS["imagenet64_3"], 5, wrap=True, extra={"classifier_type": "attention_probe"})
     out = tmp_path / "ddim"
     S.main(["--checkpoint_path", ck, "--config_path", cfg, "--batch_size", "2", "--parametrization", "predict_noise",
-            "--output_folder", str(out), "--use_ddim", "--ddim_steps", "20", "--ddim_eta", "0.1", "--class_id", "7",
+            "--output_folder", str(out), "--use_ddim", "--ddim_steps", "20", "--ddim_eta", "0.02", "--class_id", "7",
             "--seed", "1"])
     assert sorted(p.name for p in out.iterdir()) == ["0.png", "1.png", "grid_image.png", "statistics.txt"]
     assert _png(out / "1.png").shape == (64, 64, 4)
