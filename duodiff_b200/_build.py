@@ -9,8 +9,9 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libduodiff_b200.so"
 SOURCES = ["duodiff_b200.cu", "autoencoder.cu"]
-HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "gemm3.cuh", "attention.cuh", "attention2.cuh", "elementwise.cuh", "conv_gemm.cuh",
-           "host_common.h"]
+HEADERS = ["ptx.cuh", "gemm.cuh", "gemm2.cuh", "attention.cuh", "elementwise.cuh", "conv_gemm.cuh", "host_common.h",
+           "experimental/gemm3.cuh", "experimental/attention2.cuh", "experimental/attention_mma.cuh",
+           "experimental/embed_tokens.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -31,11 +32,18 @@ def needs_rebuild() -> bool:
     return any(d.stat().st_mtime > built for d in deps if d.exists())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA library for sm_100a. Cross-compiles without a GPU."""
-    if not force and not needs_rebuild():
+def build(force: bool = False, verbose: bool = False, experimental: bool | None = None) -> Path:
+    """Compile the CUDA library for sm_100a. Cross-compiles without a GPU.
+
+    DDB_EXPERIMENTAL=1 (or experimental=True) also compiles the measured-and-rejected kernel variants under
+    csrc/experimental/ (A-in-TMEM GEMM, two-threads-per-row attention, generic mma.sync attention, fp32-FMA token assembly,
+    single-CTA GEMM for the block linears); the product library does not contain them."""
+    if experimental is None:
+        experimental = os.environ.get("DDB_EXPERIMENTAL", "0") not in ("", "0")
+    if not force and not needs_rebuild() and not experimental:
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-DDDB_EXPERIMENTAL"] if experimental else []), "-o", str(LIB_PATH),
+           *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -186,10 +186,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 struct AttnArgs {
-    CUtensorMap tmQKV;  // [B, L, 3D] bf16, box {64, 128, 1}
-    CUtensorMap tmKV;   // [B, L, 3D] bf16, box {64, 256, 1}
-    CUtensorMap tmX;    // [B, L, 3D] bf16, box {64, 16, 1}
-    CUtensorMap tmOut;  // [B, L, D]  bf16, box {64, 128, 1}
+    CUtensorMap tmQKV;    // [B, L, 3D] bf16, box {64, 128, 1}
+    CUtensorMap tmKV;     // [B, L, 3D] bf16, box {64, 256, 1}
+    CUtensorMap tmX;      // [B, L, 3D] bf16, box {64, 16, 1}
+    CUtensorMap tmOut;    // [B, L, D]  bf16, box {64, 128, 1}
+    CUtensorMap tmOut32;  // [B, L, D]  bf16, box {64, 32, 1}: one epilogue warp's rows
     const __nv_bfloat16* qkv;
     __nv_bfloat16* out;
     int L, H, extras, B;
@@ -197,6 +198,7 @@ struct AttnArgs {
     const int* b_dev;  // optional live batch size (early-exit compaction)
     int reverse;       // walk the (sample, head) items from the last to the first (see GemmArgs::reverse)
     int discard;       // drop the consumed q|k|v lines from L2 instead of letting them be written back (model path only)
+    int token;         // the two query tiles take turns in the exp pass (one MUFU pipe per SM: see the kernel header)
     long long* trace;  // bench-only: CTA 0 records clock64() at the phase boundaries of every item ([it][tile][8])
 };
 
@@ -206,20 +208,36 @@ constexpr int ATT3_OFF_K = 32768, ATT3_OFF_V = 65536, ATT3_OFF_VX = 98304, ATT3_
 constexpr int ATT3_STAGE = 104448;
 constexpr int ATT3_OFF_BAR = 2 * ATT3_STAGE;
 constexpr int ATT3_SMEM = ATT3_OFF_BAR + 256;
-constexpr uint32_t ATT3_QK_BYTES = 16384 + 16384 + 32768 + 2048 + 2048, ATT3_V_BYTES = 32768 + 2048;
+constexpr uint32_t ATT3_Q_BYTES = 16384, ATT3_K_BYTES = 32768 + 2048 + 2048, ATT3_V_BYTES = 32768 + 2048;
 
+// Round-2 pipeline notes (profiles/r02_attention_trace_before.txt -> _after.txt).  With ONE "stage free" barrier per
+// operand stage (round 1) the two query tiles ran in lock-step: a tile that finished an item early still had to wait
+// for the other tile (and the extras warp) before the NEXT-BUT-ONE item's operands could even be requested, and then
+// for the ~3 000 clk the 102 KB TMA refill takes; both tiles then entered the exp pass together and shared the SM's
+// single MUFU pipe (pass 2: ~3 900 clk each instead of ~2 100), while the pipe idled during everything else.  Now
+//   * every operand has its own full / empty barrier pair (K+Kx+Qx, V+Vx, Q0, Q1): K is re-requested as soon as both
+//     S MMAs have retired (early in the item), each tile's Q slot as soon as that tile's own output stores have read it;
+//     the producer polls the four "empty" barriers and issues whichever refill is possible;
+//   * each epilogue warp stores its own 32 rows with its own TMA store (no warpgroup barrier in the epilogue);
+//   * optionally (AttnArgs::token) the tiles alternate in the exp pass through a pair of token barriers, so that one
+//     tile's MMA waits / row max / epilogue always run under the other tile's exponentials.
 __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT3_OFF_BAR);
-    uint64_t* qk_full = bars + 0;      // [2] per operand stage
-    uint64_t* v_full = bars + 2;       // [2]
-    uint64_t* stage_empty = bars + 4;  // [2] 5 arrivals: each tile's MMAs retired + its TMA store read, extras warp
-    uint64_t* s_full = bars + 6;       // [2] per query tile
-    uint64_t* p_full = bars + 8;       // [2]
-    uint64_t* o_full = bars + 10;      // [2]
-    uint64_t* tmem_free = bars + 12;   // [2]
-    uint64_t* p_half = bars + 14;      // [2] P of keys [0, 128) written
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* k_full = bars + 0;      // [2] per operand stage: K, Kx, Qx landed
+    uint64_t* v_full = bars + 2;      // [2] V, Vx landed
+    uint64_t* q_full = bars + 4;      // [2 tiles][2 stages] Q_t landed
+    uint64_t* k_empty = bars + 8;     // [2] 11 arrivals: both tiles' S MMAs retired, extras warp done, and the eight
+                                      //     softmax warps have read Kx (extras_scores)
+    uint64_t* v_empty = bars + 10;    // [2] 3 arrivals: both tiles' PV MMAs retired, extras warp done
+    uint64_t* q_empty = bars + 12;    // [2][2] 4 arrivals: the tile's four epilogue warps (their TMA stores have read it)
+    uint64_t* s_full = bars + 16;     // [2] per query tile
+    uint64_t* p_full = bars + 18;     // [2]
+    uint64_t* o_full = bars + 20;     // [2]
+    uint64_t* tmem_free = bars + 22;  // [2]
+    uint64_t* p_half = bars + 24;     // [2] P of keys [0, 128) written
+    uint64_t* tok = bars + 26;        // [2] tok[t]: tile t may enter its exp pass (4 arrivals from the other tile)
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.H * 64;
@@ -234,16 +252,22 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         tma_prefetch_desc(&a.tmQKV);
         tma_prefetch_desc(&a.tmKV);
         tma_prefetch_desc(&a.tmX);
-        tma_prefetch_desc(&a.tmOut);
+        tma_prefetch_desc(&a.tmOut32);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&qk_full[i], 1);
+            mbar_init(&k_full[i], 1);
             mbar_init(&v_full[i], 1);
-            mbar_init(&stage_empty[i], 5);
+            mbar_init(&k_empty[i], 11);
+            mbar_init(&v_empty[i], 3);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
             mbar_init(&tmem_free[i], 4);
             mbar_init(&p_half[i], 4);
+            mbar_init(&tok[i], 4);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 4);
         }
         fence_mbar_init();
     }
@@ -254,15 +278,16 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     const uint32_t tmem = *tmem_holder;
     pdl_wait();  // qkv is the predecessor's output
 
+    auto item_of = [&](int it) {
+        return a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
+    };
+
     if (warp == 8) {
         // ================================================================= TMA producer (+ L2 discard of consumed q|k|v)
         // a.discard: the q|k|v slice of a finished item is dead (the next block's qkv GEMM rewrites the whole buffer),
-        // but its lines sit dirty in L2 and would be written back to HBM on eviction -- 101 MB per launch.  Once the
-        // stage of item it-2 is released (all MMAs retired, extras warp done, stores read) its 3 x L lines of 128 bytes
-        // (one head's slice of one token: exclusively this item's) are dropped with discard.global.L2.
-        auto item_of = [&](int it) {
-            return a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
-        };
+        // but its lines sit dirty in L2 and would be written back to HBM on eviction -- 101 MB per launch.  Once every
+        // operand slot of item it-2 has been released its 3 x L lines of 128 bytes (one head's slice of one token:
+        // exclusively this item's) are dropped with discard.global.L2.
         auto discard_item = [&](int it) {
             const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
@@ -275,23 +300,53 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         };
         for (int it = 0; it < my_items + (a.discard ? 2 : 0); ++it) {
             const int s = it & 1;
-            if (lane == 0) mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
-            __syncwarp();
-            if (a.discard && it >= 2) discard_item(it - 2);
-            if (it < my_items && lane == 0) {
-                const int item = item_of(it);
+            if (lane == 0) {
+                // the four operand slots of stage s are released at different times (K early, the Q slots when their
+                // tile finishes, V last): poll, and refill whichever is free
+                const uint32_t par = ((it >> 1) & 1) ^ 1;
+                const bool load = it < my_items;
+                const int item = load ? item_of(it) : 0;
                 const int b = item / a.H, h = item % a.H;
                 uint8_t* st = smem + s * ATT3_STAGE;
-                mbar_expect_tx(&qk_full[s], ATT3_QK_BYTES);
-                tma_load_3d(st + ATT3_OFF_K, &a.tmKV, &qk_full[s], D + h * 64, a.extras, b);
-                tma_load_3d(st, &a.tmQKV, &qk_full[s], h * 64, a.extras, b);
-                tma_load_3d(st + 16384, &a.tmQKV, &qk_full[s], h * 64, a.extras + 128, b);
-                tma_load_3d(st + ATT3_OFF_KX, &a.tmX, &qk_full[s], D + h * 64, 0, b);
-                tma_load_3d(st + ATT3_OFF_QX, &a.tmX, &qk_full[s], h * 64, 0, b);
-                mbar_expect_tx(&v_full[s], ATT3_V_BYTES);
-                tma_load_3d(st + ATT3_OFF_V, &a.tmKV, &v_full[s], 2 * D + h * 64, a.extras, b);
-                tma_load_3d(st + ATT3_OFF_VX, &a.tmX, &v_full[s], 2 * D + h * 64, 0, b);
+                uint32_t pend = 0xF, spins = 0;
+                while (pend) {
+                    if ((pend & 1) && mbar_test(&k_empty[s], par)) {
+                        pend &= ~1u;
+                        if (load) {
+                            mbar_expect_tx(&k_full[s], ATT3_K_BYTES);
+                            tma_load_3d(st + ATT3_OFF_K, &a.tmKV, &k_full[s], D + h * 64, a.extras, b);
+                            tma_load_3d(st + ATT3_OFF_KX, &a.tmX, &k_full[s], D + h * 64, 0, b);
+                            tma_load_3d(st + ATT3_OFF_QX, &a.tmX, &k_full[s], h * 64, 0, b);
+                        }
+                    }
+                    if ((pend & 2) && mbar_test(&q_empty[0 * 2 + s], par)) {
+                        pend &= ~2u;
+                        if (load) {
+                            mbar_expect_tx(&q_full[0 * 2 + s], ATT3_Q_BYTES);
+                            tma_load_3d(st, &a.tmQKV, &q_full[0 * 2 + s], h * 64, a.extras, b);
+                        }
+                    }
+                    if ((pend & 4) && mbar_test(&q_empty[1 * 2 + s], par)) {
+                        pend &= ~4u;
+                        if (load) {
+                            mbar_expect_tx(&q_full[1 * 2 + s], ATT3_Q_BYTES);
+                            tma_load_3d(st + 16384, &a.tmQKV, &q_full[1 * 2 + s], h * 64, a.extras + 128, b);
+                        }
+                    }
+                    if ((pend & 8) && mbar_test(&v_empty[s], par)) {
+                        pend &= ~8u;
+                        if (load) {
+                            mbar_expect_tx(&v_full[s], ATT3_V_BYTES);
+                            tma_load_3d(st + ATT3_OFF_V, &a.tmKV, &v_full[s], 2 * D + h * 64, a.extras, b);
+                            tma_load_3d(st + ATT3_OFF_VX, &a.tmX, &v_full[s], 2 * D + h * 64, 0, b);
+                        }
+                    }
+                    if (++spins > DDB_SPIN_LIMIT) __trap();
+                    if (pend && (a.token & 2)) __nanosleep(64);  // nothing else to do: leave the issue slots to the softmax warps
+                }
             }
+            __syncwarp();
+            if (a.discard && it >= 2) discard_item(it - 2);  // every consumer of item it-2 has released its slot
             __syncwarp();
         }
     } else if (warp == 9 || warp == 11) {
@@ -303,23 +358,26 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
             for (int it = 0; it < my_items; ++it) {
                 const int s = it & 1;
+                const uint32_t sph = (it >> 1) & 1;
                 const uint8_t* st = smem + s * ATT3_STAGE;
-                // S_t(it): needs the operands of the item and the tile's TMEM columns (O_t(it-1) drained)
-                mbar_wait(&qk_full[s], (it >> 1) & 1);
+                // S_t(it): needs K and Q_t of the item and the tile's TMEM columns (O_t(it-1) drained)
+                mbar_wait(&k_full[s], sph);
+                mbar_wait(&q_full[t * 2 + s], sph);
                 mbar_wait(&tmem_free[t], (it & 1) ^ 1);
                 // start tile 1 half a period late so the two softmax warpgroups do not fight over the MUFU pipe
-                if (t == 1 && it == 0) mbar_wait(&p_full[0], 0);
+                if (t == 1 && it == 0 && !(a.token & 1)) mbar_wait(&p_full[0], 0);
                 tc_fence_after();
                 const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(st + t * 16384));
                 const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(st + ATT3_OFF_K));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_f16_ss(tmem + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                 umma_commit(&s_full[t]);
+                umma_commit(&k_empty[s]);  // this tile's S MMAs no longer read K once retired
                 // O_t(it) = P_t [V; V_x]: 16 keys per k-step (P columns +8, V rows +16 = 2048 B); the first 8
                 // k-steps start as soon as the first half of P is written
                 long long* tr = (a.trace && blockIdx.x == 0) ? a.trace + (it * 2 + t) * 16 + 8 : nullptr;
                 if (tr) tr[0] = clock64();
-                mbar_wait(&v_full[s], (it >> 1) & 1);
+                mbar_wait(&v_full[s], sph);
                 const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(st + ATT3_OFF_V));
                 mbar_wait(&p_half[t], it & 1);
                 tc_fence_after();
@@ -337,7 +395,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     umma_f16_ts(tmem + t * 256 + 64, tmem + t * 256 + 64 + 8 * k, dv + (uint64_t)(k * (2048 >> 4)),
                                 idesc_o, 1u);
                 umma_commit(&o_full[t]);
-                umma_commit(&stage_empty[s]);  // this tile's MMAs no longer read the operand stage once retired
+                umma_commit(&v_empty[s]);  // this tile's PV MMAs no longer read V once retired
                 if (tr) {
                     tr[4] = clock64();
                     mbar_wait(&o_full[t], it & 1);
@@ -349,11 +407,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         // ================================================================= extras query rows on mma.sync
         const int g = lane >> 2, t = lane & 3;
         for (int it = 0; it < my_items; ++it) {
-            const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
+            const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
             const int s = it & 1;
             const uint8_t* st = smem + s * ATT3_STAGE;
-            mbar_wait(&qk_full[s], (it >> 1) & 1);
+            mbar_wait(&k_full[s], (it >> 1) & 1);
             // A fragments: rows g (token g of the sample; only g < extras is kept), rows g+8 are zero
             uint32_t qf[4][4];
 #pragma unroll
@@ -369,11 +427,16 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             att_mma_block<true>(smem_u32(st + ATT3_OFF_KX), smem_u32(st + ATT3_OFF_VX), 0, 1, a.extras, qf, rs,
                                 a.scale_log2e, lane);
             const uint32_t sK_u = smem_u32(st + ATT3_OFF_K), sV_u = smem_u32(st + ATT3_OFF_V);
+            if (!(a.token & 4)) {
 #pragma unroll 1
-            for (int kb0 = 0; kb0 < 256; kb0 += 64)
-                att_mma_block<true>(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
+                for (int kb0 = 0; kb0 < 256; kb0 += 64)
+                    att_mma_block<true>(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&stage_empty[s]);  // this warp no longer reads the stage
+            if (lane == 0) {  // this warp no longer reads the stage
+                mbar_arrive(&k_empty[s]);
+                mbar_arrive(&v_empty[s]);
+            }
             float l0 = rs.l0;
             l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
             l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -390,7 +453,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         const int t = warp >> 2;  // query tile == warpgroup
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
-        const int et = threadIdx.x & 127;
         const uint32_t t_row = tmem + (uint32_t(quarter * 32) << 16) + t * 256;
         const float c = a.scale_log2e;
         const int q0 = a.extras + t * 128;
@@ -400,7 +462,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             const int s = it & 1;
             const uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;
             const uint8_t* sKx = smem + s * ATT3_STAGE + ATT3_OFF_KX;
-            mbar_wait(&qk_full[s], (it >> 1) & 1);
+            mbar_wait(&k_full[s], (it >> 1) & 1);
+            mbar_wait(&q_full[t * 2 + s], (it >> 1) & 1);
             se0 = 0.f, se1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -421,12 +484,14 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 }
             }
             if (a.extras != 2) se1 = -INFINITY;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&k_empty[s]);  // this warp has read Kx of the item
         };
 
         float se0 = 0.f, se1 = 0.f;
         if (my_items > 0) extras_scores(0, se0, se1);
         for (int it = 0; it < my_items; ++it) {
-            const int item = a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
+            const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
             const int s = it & 1;
             const uint32_t ph = it & 1;
@@ -437,11 +502,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             mbar_wait(&s_full[t], ph);
             tc_fence_after();
             if (tr) tr[1] = clock64();
-            // the previous item's TMA store was issued ~1000 clk ago: once it has read its staging tile (the Q_t
-            // buffer of the other stage) that stage may be refilled
-            if (et == 0 && it > 0) {
+            // this warp's store of the previous item was issued ~1000 clk ago: once it has read its 32 staging rows
+            // (in the Q_t buffer of the other stage) that Q slot may be refilled
+            if (lane == 0 && it > 0) {
                 tma_store_wait_read<0>();
-                mbar_arrive(&stage_empty[s ^ 1]);
+                mbar_arrive(&q_empty[t * 2 + (s ^ 1)]);
             }
             if (tr) tr[2] = clock64();
             uint32_t va[32], vb[32];
@@ -450,7 +515,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int jj = 0; jj < 8; jj += 2) {
+            for (int jj = 0; jj < ((a.token & 32) ? 2 : 8); jj += 2) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     uint32_t(&cur)[32] = u ? vb : va;
@@ -469,6 +534,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             }
             const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
             if (tr) tr[3] = clock64();
+            // the tiles take turns in the exp pass: tile t waits for its token (the other tile's previous exp pass has
+            // ended), so that tile's MMA waits, row max and epilogue always run under this tile's exponentials
+            if ((a.token & 1) && (t == 1 || it > 0)) mbar_wait(&tok[t], (t == 1 ? it : it - 1) & 1);
             const float pe0 = ex2_approx(fmaf(se0, c, -mc));
             const float pe1 = (a.extras == 2) ? ex2_approx(fmaf(se1, c, -mc)) : 0.f;
             // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
@@ -489,7 +557,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     for (int e = 0; e < 16; ++e) {
                         float x0, x1;
                         f2_unpack(f2_fma(f2_pack_u(cur[2 * e], cur[2 * e + 1]), c2, nmc2), x0, x1);
-                        const f32x2 p = f2_pack(ex2_approx(x0), ex2_approx(x1));
+                        const f32x2 p = (a.token & 8) ? f2_pack(x0 * 0.001f, x1 * 0.001f)
+                                                      : f2_pack(ex2_approx(x0), ex2_approx(x1));
                         if (e & 1)
                             sum2b = f2_add(sum2b, p);
                         else
@@ -499,7 +568,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     if (j < 7) tmem_ld_wait();
                     // P chunk j < 4 -> columns [16j, 16j+16) (inside S chunk j/2), j >= 4 -> [128 + 16(j-4), ..)
                     // (inside S chunks 4, 5): always columns whose scores are already in registers
-                    tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);
+                    if (!(a.token & 16)) tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);
+                    else if (pk[0] == 0x12345u && pk[7] == 0x77u) m2 += 1.f;
                 }
                 if (jj == 2) {
                     // keys [0, 128) are done: the first 8 k-steps of O = P V run under the rest of pass 2
@@ -509,6 +579,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     if (lane == 0) mbar_arrive(&p_half[t]);
                 }
             }
+            if ((a.token & 1) && lane == 0) mbar_arrive(&tok[t ^ 1]);  // exp pass over: the other tile's turn
             {
                 // 17th k-step: keys = tokens 0..15 of the sample, non-zero weight only for the extras tokens
                 const uint32_t px[8] = {pack_bf16(pe0, pe1), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -524,7 +595,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             f2_unpack(sum2b, sc, sd);
             const float inv = 1.f / ((sa + sb) + (sc + sd));
             // while the tensor core finishes O: the next item's extras-key scores (its operands landed long ago)
-            if (it + 1 < my_items) extras_scores(it + 1, se0, se1);
+            if (it + 1 < my_items && !(a.token & 64)) extras_scores(it + 1, se0, se1);
+            if (a.token & 64) {
+                __syncwarp();
+                if (lane == 0 && it + 1 < my_items) mbar_arrive(&k_empty[(it + 1) & 1]);
+            }
             if (tr) tr[5] = clock64();
 
             // ---- epilogue: O row (fp32) out of TMEM, then release the tile's columns for S_t of the next item
@@ -550,17 +625,18 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 w.w = f2_to_bf16x2(f2_mul(f2_pack_u(o[6], o[7]), inv2));
                 *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
             }
+            // each warp stores its own 32 rows (4 KB, a whole number of 1 KB swizzle atoms): no warpgroup barrier
             fence_proxy_async_smem();
-            named_bar_sync(1 + t, 128);
-            if (et == 0) {
-                tma_store_3d(&a.tmOut, sQ, h * 64, q0, b);
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_3d(&a.tmOut32, sQ + quarter * 4096, h * 64, q0 + quarter * 32, b);
                 tma_store_commit();
             }
             if (tr) tr[7] = clock64();
         }
-        if (et == 0 && my_items > 0) {
+        if (lane == 0 && my_items > 0) {
             tma_store_wait_read<0>();
-            mbar_arrive(&stage_empty[(my_items - 1) & 1]);
+            mbar_arrive(&q_empty[t * 2 + ((my_items - 1) & 1)]);
             tma_store_wait_all<0>();
         }
     }

@@ -421,11 +421,13 @@ static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* 
     DDB_TRY(make_tmap_bf16_3d(&a.tmKV, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 256));
     DDB_TRY(make_tmap_bf16_3d(&a.tmX, qkv, 3 * D, L, Bcap, 3 * D * 2, (uint64_t)L * 3 * D * 2, 16));
     DDB_TRY(make_tmap_bf16_3d(&a.tmOut, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 128));
+    DDB_TRY(make_tmap_bf16_3d(&a.tmOut32, out, D, L, Bcap, D * 2, (uint64_t)L * D * 2, 32));
     return DDB_OK;
 }
 static std::atomic<long long*> g_attn_trace{nullptr};  // bench-only (ddb_debug_set_ptr "attn_trace")
 // persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
-static std::atomic<int> g_attn_x2{0};  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
+static std::atomic<int> g_attn_x2{0};
+static std::atomic<int> g_attn_token{1};  // ddb_set_option "attn_token": the two query tiles alternate in the exp pass  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
 static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, int force_x2 = -1) {
     static ddb_host::DeviceOnce configured;
     if (!configured.done()) {
@@ -440,6 +442,7 @@ static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, 
     if (B <= 0) return DDB_OK;
     a.B = B;
     a.trace = g_attn_trace;
+    a.token = g_attn_token;
     const int items = B * a.H;
     const dim3 grid(items < num_sms ? items : num_sms);
     if (force_x2 >= 0 ? force_x2 != 0 : g_attn_x2 != 0) {
@@ -913,14 +916,19 @@ static int launch_token_extras(const ddb_model* m, const float* t_vec, const int
 }
 static int launch_step_tail(const ddb_model* m, const TailArgs& ta, int B, cudaStream_t st) {
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
-    const size_t smem = (size_t)C * (CONV_BAND + 2) * (W + 8) * 4;
     const dim3 grid(B * (H / CONV_BAND));
     ProfScope ps(PC_TAIL);
-    switch (C) {
-        case 3: CUDA_TRY(launch_pdl(step_tail_kernel<3>, grid, dim3(256), smem, st, ta)); break;
-        case 4: CUDA_TRY(launch_pdl(step_tail_kernel<4>, grid, dim3(256), smem, st, ta)); break;
-        default: return fail(DDB_ERR_INVALID, "in_chans %d unsupported by the final 3x3 conv (3 or 4)", C);
-    }
+    if (C == 3 && W == 64)
+        CUDA_TRY(launch_pdl(step_tail_kernel<3, 64>, grid, dim3(256), 0, st, ta));
+    else if (C == 3 && W == 32)
+        CUDA_TRY(launch_pdl(step_tail_kernel<3, 32>, grid, dim3(256), 0, st, ta));
+    else if (C == 4 && W == 32)
+        CUDA_TRY(launch_pdl(step_tail_kernel<4, 32>, grid, dim3(256), 0, st, ta));
+    else if (C == 4 && W == 64)
+        CUDA_TRY(launch_pdl(step_tail_kernel<4, 64>, grid, dim3(256), 0, st, ta));
+    else
+        return fail(DDB_ERR_INVALID, "sample shape [%d,%d,%d] unsupported by the fused step tail (C in {3,4}, size in "
+                                     "{32,64}: every reference config)", C, H, W);
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -1317,6 +1325,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "attn_x2")) {
         g_attn_x2 = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "attn_token")) {
+        g_attn_token = value;  // bit 0: token; bits 1-3: bench-only experiments (attention.cuh)
         return DDB_OK;
     }
     if (!strcmp(name, "attn_discard")) {

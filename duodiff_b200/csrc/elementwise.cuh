@@ -274,6 +274,28 @@ __device__ __forceinline__ void conv_pixels4(const float* __restrict__ conv_smem
         }
     }
 }
+// the same four pixels of ONE output channel: per accumulator the FMA order over (ci, dy) is that of conv_pixels4, so
+// both give the same bits; one channel per work item keeps the register count low enough for 3-4 CTAs per SM
+template <int C>
+__device__ __forceinline__ void conv_pixels4_one(const float* __restrict__ conv_smem, const float* __restrict__ sw,
+                                                 int co, int yy, int xq, int W, float (&acc)[4]) {
+    const int SW = W + 8, SH = CONV_BAND + 2;
+    acc[0] = acc[1] = acc[2] = acc[3] = sw[C * C * 9 + co];
+#pragma unroll
+    for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const float* rp = conv_smem + (ci * SH + yy + dy) * SW + 4 * xq;
+            const float4 m = *reinterpret_cast<const float4*>(rp + 4);
+            const float l = rp[3], r = rp[8];
+            const float win[6] = {l, m.x, m.y, m.z, m.w, r};
+            const float* wp = sw + (co * C + ci) * 9 + dy * 3;
+            const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[p] = fmaf(w0, win[p], fmaf(w1, win[p + 1], fmaf(w2, win[p + 2], acc[p])));
+        }
+    }
+}
 template <int C>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
@@ -291,14 +313,12 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
     const int w4 = W / 4;
     conv_stage_band<C>(conv_smem, in, b, y0, H, W);
     __syncthreads();
-    for (int i = threadIdx.x; i < CONV_BAND * w4; i += blockDim.x) {
-        const int xq = i % w4, yy = i / w4;
-        float acc[C][4];
-        conv_pixels4<C>(conv_smem, sw, yy, xq, W, acc);
-#pragma unroll
-        for (int co = 0; co < C; ++co)
-            *(reinterpret_cast<float4*>(out + (((size_t)ob * C + co) * H + y0 + yy) * W) + xq) =
-                make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
+    for (int i = threadIdx.x; i < C * CONV_BAND * w4; i += blockDim.x) {
+        const int xq = i % w4, yy = (i / w4) % CONV_BAND, co = i / (w4 * CONV_BAND);
+        float acc[4];
+        conv_pixels4_one<C>(conv_smem, sw, co, yy, xq, W, acc);
+        *(reinterpret_cast<float4*>(out + (((size_t)ob * C + co) * H + y0 + yy) * W) + xq) =
+            make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
 }
 
@@ -390,7 +410,7 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
 // (patch_gather_kernel's output), the next step's time / label token rows (token_extras_kernel's output) and the
 // step counter t <- next_t[t].  Replaces conv3x3 + ddpm_step + next_t + fill_t + patch_gather + token_extras (six
 // launches) by one; every arithmetic expression is shared with those kernels, so the fused and the unfused step give
-// the same bits.  One CTA per (sample, 16-row band), 256 threads.
+// the same bits.  One CTA per (sample, 16-row band), 256 threads, one work item = 4 pixels of one output channel.
 // The next step may run on the other backbone (DuoDiff hand-off, sampler.py:135-136): next_late[t] selects which
 // model's buffers receive the prepared head.
 // =====================================================================================================
@@ -420,11 +440,14 @@ struct TailArgs {
     int H, W, mode;
     TailTarget tgt[2];     // [0] early backbone, [1] late backbone
 };
-template <int C>
-__global__ void __launch_bounds__(256) step_tail_kernel(const __grid_constant__ TailArgs a) {
-    extern __shared__ __align__(16) float conv_smem[];  // [C][CONV_BAND+2][W+8]
+template <int C, int W>
+__global__ void __launch_bounds__(256, 4) step_tail_kernel(const __grid_constant__ TailArgs a) {
+    constexpr int SW = W + 8, SH = CONV_BAND + 2, w4 = W / 4;
+    constexpr int N_STAGE = C * SH * (w4 + 2);          // float4 slots of the staged band (halo columns included)
+    constexpr int N_ITEMS = C * CONV_BAND * w4;          // (output channel, row, 4-pixel group) work items
+    __shared__ __align__(16) float conv_smem[C * SH * SW];
     __shared__ float sw[C * C * 9 + C];
-    const int H = a.H, W = a.W;
+    const int H = a.H;
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
     pdl_launch_dependents();
@@ -432,35 +455,53 @@ __global__ void __launch_bounds__(256) step_tail_kernel(const __grid_constant__ 
         sw[i] = (i < C * C * 9) ? a.conv_w[i] : a.conv_b[i - C * C * 9];
     pdl_wait();
     const int t = *a.t_dev;
-    const int t_next = a.next_t[t];
-    const TailTarget& tg = a.tgt[a.next_t[1000 + t] ? 1 : 0];
+    // everything that depends on t is requested at once (one further round trip, not three)
+    const int t_next = a.next_t[t], late_next = a.next_t[1000 + t];
+    const float4 kc = *reinterpret_cast<const float4*>(a.coef + t * 4);
     const unsigned long long seed = a.seed_dev[0], off4 = a.seed_dev[1];
-    const StepCoef k{a.coef[t * 4 + 0], a.coef[t * 4 + 1], a.coef[t * 4 + 2], a.coef[t * 4 + 3]};
-    const int w4 = W / 4;
-    conv_stage_band<C>(conv_smem, a.img_pre, b, y0, H, W);
-    __syncthreads();
-    const int P = tg.P, Hp = H / P, Wp = W / P;
-    for (int i = threadIdx.x; i < CONV_BAND * w4; i += blockDim.x) {
-        const int xq = i % w4, yy = i / w4;
-        float acc[C][4];
-        conv_pixels4<C>(conv_smem, sw, yy, xq, W, acc);
+    // band of the decoder image: all loads of a thread are in flight before its first shared-memory store
+    {
+        constexpr int PER = (N_STAGE + 255) / 256;
+        float4 v[PER];
 #pragma unroll
-        for (int co = 0; co < C; ++co) {
-            const size_t e4 = ((((size_t)b * C + co) * H + y0 + yy) * W) / 4 + xq;  // float4 index inside the shard
-            const float4 ev = make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
-            const float4 xv = reinterpret_cast<const float4*>(a.x)[e4];
-            float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t > 0)
-                zv = a.z_all ? reinterpret_cast<const float4*>(a.z_all + (size_t)t * a.n)[e4]
-                             : philox_normal4(e4 + off4, t, seed);
-            const float4 o = ddpm_update4(a.mode, k, xv, ev, zv);
-            reinterpret_cast<float4*>(a.x)[e4] = o;
-            if (a.eps_out) reinterpret_cast<float4*>(a.eps_out)[e4] = ev;
-            if (a.x_save) reinterpret_cast<float4*>(a.x_save)[e4] = o;
-            // head of the next step: the updated pixels as bf16 hi | lo patch-vector entries (P = 2: two patches)
-            patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq, P, Hp, Wp), o.x, o.y);
-            patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq + 2, P, Hp, Wp), o.z, o.w);
+        for (int j = 0; j < PER; ++j) {
+            const int i = threadIdx.x + j * 256;
+            const int q = i % (w4 + 2), r = (i / (w4 + 2)) % SH, c = i / ((w4 + 2) * SH);
+            const int yy = y0 - 1 + r;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < N_STAGE && q >= 1 && q <= w4 && yy >= 0 && yy < H)
+                v[j] = __ldg(reinterpret_cast<const float4*>(a.img_pre + (((size_t)b * C + c) * H + yy) * W) + (q - 1));
         }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = threadIdx.x + j * 256;
+            const int q = i % (w4 + 2), r = (i / (w4 + 2)) % SH, c = i / ((w4 + 2) * SH);
+            if (i < N_STAGE) *reinterpret_cast<float4*>(conv_smem + (c * SH + r) * SW + q * 4) = v[j];
+        }
+    }
+    const StepCoef k{kc.x, kc.y, kc.z, kc.w};
+    const TailTarget& tg = a.tgt[late_next ? 1 : 0];
+    const int P = tg.P, Hp = H / P, Wp = W / P;
+    __syncthreads();
+#pragma unroll 1
+    for (int i = threadIdx.x; i < N_ITEMS; i += 256) {
+        const int xq = i % w4, yy = (i / w4) % CONV_BAND, co = i / (w4 * CONV_BAND);
+        const size_t e4 = ((((size_t)b * C + co) * H + y0 + yy) * W) / 4 + xq;  // float4 index inside the shard
+        // x (and the injected noise) do not depend on the conv: their loads are in flight while it is computed
+        const float4 xv = reinterpret_cast<const float4*>(a.x)[e4];
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t > 0 && a.z_all) zv = reinterpret_cast<const float4*>(a.z_all + (size_t)t * a.n)[e4];
+        float acc[4];
+        conv_pixels4_one<C>(conv_smem, sw, co, yy, xq, W, acc);
+        const float4 ev = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (t > 0 && !a.z_all) zv = philox_normal4(e4 + off4, t, seed);
+        const float4 o = ddpm_update4(a.mode, k, xv, ev, zv);
+        reinterpret_cast<float4*>(a.x)[e4] = o;
+        if (a.eps_out) reinterpret_cast<float4*>(a.eps_out)[e4] = ev;
+        if (a.x_save) reinterpret_cast<float4*>(a.x_save)[e4] = o;
+        // head of the next step: the updated pixels as bf16 hi | lo patch-vector entries (P = 2: two patches)
+        patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq, P, Hp, Wp), o.x, o.y);
+        patch_store_pair(patch_elem(tg.a_patch, b, co, y0 + yy, 4 * xq + 2, P, Hp, Wp), o.z, o.w);
     }
     if (y0 == 0)  // one CTA per sample also writes the next step's time / label token rows
         write_token_extras(b, (float)t_next, a.y, tg.pos, tg.label_emb, tg.tokens, tg.stats_p, tg.D, tg.L, tg.extras,

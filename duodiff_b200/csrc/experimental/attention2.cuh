@@ -20,6 +20,9 @@
 
 namespace ddb {
 
+constexpr uint32_t ATT4_QK_BYTES = 16384 + 16384 + 32768 + 2048 + 2048;  // Q0, Q1, K, Kx, Qx on one barrier
+
+
 constexpr int ATT4_THREADS = 640;  // 16 softmax warps + producer, 2 MMA issuers, extras warp
 constexpr int ATT4_SMEM = ATT3_SMEM + 4096;
 
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(ATT4_THREADS, 1) attention_tcgen05_x2_kernel(c
                 const int s = it & 1;
                 uint8_t* st = smem + s * ATT3_STAGE;
                 mbar_wait(&stage_empty[s], ((it >> 1) & 1) ^ 1);
-                mbar_expect_tx(&qk_full[s], ATT3_QK_BYTES);
+                mbar_expect_tx(&qk_full[s], ATT4_QK_BYTES);
                 tma_load_3d(st + ATT3_OFF_K, &a.tmKV, &qk_full[s], D + h * 64, a.extras, b);
                 tma_load_3d(st, &a.tmQKV, &qk_full[s], h * 64, a.extras, b);
                 tma_load_3d(st + 16384, &a.tmQKV, &qk_full[s], h * 64, a.extras + 128, b);

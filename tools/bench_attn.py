@@ -18,8 +18,12 @@ ap.add_argument("--n", type=int, default=50)
 ap.add_argument("--check", action="store_true")
 ap.add_argument("--debug", default="0")
 ap.add_argument("--lib", default=None, help="alternative libduodiff_b200.so (A/B builds)")
+ap.add_argument("--opt", action="append", default=[], help="ddb_set_option name=value (repeatable), e.g. attn_token=0")
 a = ap.parse_args()
 Lb = _lib.load(a.lib)
+for o in a.opt:
+    k, v = o.split("=")
+    _lib.check(Lb.ddb_set_option(k.encode(), int(v)))
 dev = torch.device("cuda:0")
 B, L, H = a.B, a.L, a.H
 D = H * 64
