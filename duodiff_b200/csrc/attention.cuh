@@ -36,6 +36,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 constexpr int ATT_THREADS = 256;
 
 // smem row = one key (64 bf16 = 128 B), 16-byte chunks XOR-swizzled by (row & 7): the TMA SWIZZLE_128B pattern
@@ -174,15 +185,65 @@ __device__ __forceinline__ void att_mma_block(uint32_t sK_u, uint32_t sV_u, int 
 //                          k-steps are issued as soon as keys [0,128) are done and run under the rest of pass 2
 //   epilogue               O row / sum -> bf16 -> the tile's own (dead) Q buffer -> TMA store
 // =====================================================================================================
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
+
+// The extras QUERY rows (A rows g < 2 of the Qx fragments; rows g+8 are zero) against 32 consecutive, all-valid patch
+// keys starting at kb0: ONE softmax block with the fragment traffic of att_mma_block<true>, without masks or running
+// state.  Returns the block's row max (raw score units), row sum (reduced over the quad) and un-normalised output
+// (lane (g, t): dims 8i + 2t, 8i + 2t + 1 of row g).
+__device__ __forceinline__ void att_extras_slice32(uint32_t sK_u, uint32_t sV_u, int kb0, const uint32_t (&qf)[4][4],
+                                                   float scale_log2e, int lane, float& m_out, float& l_out,
+                                                   float (&o)[8][2]) {
+    const int t = lane & 3;
+    (void)t;
+    float s[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const int key = kb0 + j * 8 + (lane & 7);
+        const int cs = lane >> 3;
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(sK_u + att_swz(key, cs), b0, b1, b2, b3);  // dims 0..31
+        mma_bf16_16816(s[j], qf[0], b0, b1);
+        mma_bf16_16816(s[j], qf[1], b2, b3);
+        ldmatrix_x4(sK_u + att_swz(key, cs + 4), b0, b1, b2, b3);  // dims 32..63
+        mma_bf16_16816(s[j], qf[2], b0, b1);
+        mma_bf16_16816(s[j], qf[3], b2, b3);
+    }
+    float m = fmaxf(fmax3(s[0][0], s[0][1], s[1][0]), fmax3(s[1][1], s[2][0], s[2][1]));
+    m = fmax3(m, s[3][0], s[3][1]);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    const float ms = m * scale_log2e;
+    float l = 0.f;
+    uint32_t pf[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -ms));
+        const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -ms));
+        l += p0 + p1;
+        pf[j] = pack_bf16(p0, p1);
+    }
+    float oacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t pa[4] = {pf[2 * kk], 0u, pf[2 * kk + 1], 0u};
+        const int key = kb0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int dsel = lane >> 4;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+            uint32_t v0, v1, v2, v3;
+            ldmatrix_x4_trans(sV_u + att_swz(key, dn * 2 + dsel), v0, v1, v2, v3);
+            mma_bf16_16816(oacc[dn * 2], pa, v0, v1);
+            mma_bf16_16816(oacc[dn * 2 + 1], pa, v2, v3);
+        }
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    m_out = m, l_out = l;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = oacc[i][0], o[i][1] = oacc[i][1];
 }
 
 struct AttnArgs {
@@ -207,7 +268,10 @@ constexpr int ATT3_THREADS = 384;
 constexpr int ATT3_OFF_K = 32768, ATT3_OFF_V = 65536, ATT3_OFF_VX = 98304, ATT3_OFF_KX = 100352, ATT3_OFF_QX = 102400;
 constexpr int ATT3_STAGE = 104448;
 constexpr int ATT3_OFF_BAR = 2 * ATT3_STAGE;
-constexpr int ATT3_SMEM = ATT3_OFF_BAR + 256;
+// extras-QUERY partials: per stage, one record per softmax warp = 2 query rows x (64 output dims + row max + row sum)
+constexpr int ATT3_PX_ROW = 66, ATT3_PX_REC = 2 * ATT3_PX_ROW;  // floats
+constexpr int ATT3_OFF_PX = ATT3_OFF_BAR + 512;
+constexpr int ATT3_SMEM = ATT3_OFF_PX + 2 * 8 * ATT3_PX_REC * 4;
 constexpr uint32_t ATT3_Q_BYTES = 16384, ATT3_K_BYTES = 32768 + 2048 + 2048, ATT3_V_BYTES = 32768 + 2048;
 
 // Round-2 pipeline notes (profiles/r02_attention_trace_before.txt -> _after.txt).  With ONE "stage free" barrier per
@@ -220,7 +284,13 @@ constexpr uint32_t ATT3_Q_BYTES = 16384, ATT3_K_BYTES = 32768 + 2048 + 2048, ATT
 //     the producer polls the four "empty" barriers and issues whichever refill is possible;
 //   * each epilogue warp stores its own 32 rows with its own TMA store (no warpgroup barrier in the epilogue);
 //   * optionally (AttnArgs::token) the tiles alternate in the exp pass through a pair of token barriers, so that one
-//     tile's MMA waits / row max / epilogue always run under the other tile's exponentials.
+//     tile's MMA waits / row max / epilogue always run under the other tile's exponentials;
+//   * the extras QUERY rows (1-2 rows x 257 keys) used to be one warp's job (five serial mma.sync blocks per item,
+//     ~5 000 clk on a scheduler it shares with two softmax warps) and every operand slot waited for it: with its key loop
+//     switched off the launch was 13 % faster.  Now each of the eight softmax warps computes the partial attention of
+//     the extras rows over ITS OWN 32 patch keys (one mma.sync block, in the slot where it used to compute the
+//     extras-KEY scores with fp32 FMAs -- those now come from 8 mma.sync as well), and the extras warp only handles the
+//     extras keys and merges the nine partials (max-rescaled sums).
 __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(const __grid_constant__ AttnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT3_OFF_BAR);
@@ -229,7 +299,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     uint64_t* q_full = bars + 4;      // [2 tiles][2 stages] Q_t landed
     uint64_t* k_empty = bars + 8;     // [2] 11 arrivals: both tiles' S MMAs retired, extras warp done, and the eight
                                       //     softmax warps have read Kx (extras_scores)
-    uint64_t* v_empty = bars + 10;    // [2] 3 arrivals: both tiles' PV MMAs retired, extras warp done
+    uint64_t* v_empty = bars + 10;    // [2] 11 arrivals: both tiles' PV MMAs retired, extras warp done, eight softmax warps
     uint64_t* q_empty = bars + 12;    // [2][2] 4 arrivals: the tile's four epilogue warps (their TMA stores have read it)
     uint64_t* s_full = bars + 16;     // [2] per query tile
     uint64_t* p_full = bars + 18;     // [2]
@@ -237,7 +307,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     uint64_t* tmem_free = bars + 22;  // [2]
     uint64_t* p_half = bars + 24;     // [2] P of keys [0, 128) written
     uint64_t* tok = bars + 26;        // [2] tok[t]: tile t may enter its exp pass (4 arrivals from the other tile)
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
+    uint64_t* px_full = bars + 28;    // [2] 8 arrivals: the softmax warps' extras-query partials of the item are written
+    uint64_t* px_empty = bars + 30;   // [2] 1 arrival: the extras warp has merged them
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
+    float* px_buf = reinterpret_cast<float*>(smem + ATT3_OFF_PX);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.H * 64;
@@ -257,7 +330,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             mbar_init(&k_full[i], 1);
             mbar_init(&v_full[i], 1);
             mbar_init(&k_empty[i], 11);
-            mbar_init(&v_empty[i], 3);
+            mbar_init(&v_empty[i], 11);
+            mbar_init(&px_full[i], 8);
+            mbar_init(&px_empty[i], 1);
             mbar_init(&s_full[i], 1);
             mbar_init(&p_full[i], 4);
             mbar_init(&o_full[i], 1);
@@ -278,6 +353,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     const uint32_t tmem = *tmem_holder;
     pdl_wait();  // qkv is the predecessor's output
 
+    auto wait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
     auto item_of = [&](int it) {
         return a.reverse ? n_items - 1 - (int)(blockIdx.x + it * gridDim.x) : (int)(blockIdx.x + it * gridDim.x);
     };
@@ -342,7 +418,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                         }
                     }
                     if (++spins > DDB_SPIN_LIMIT) __trap();
-                    if (pend && (a.token & 2)) __nanosleep(64);  // nothing else to do: leave the issue slots to the softmax warps
+                    if (pend) __nanosleep(64);  // nothing else to do: leave the issue slots to the softmax warps
                 }
             }
             __syncwarp();
@@ -361,11 +437,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 const uint32_t sph = (it >> 1) & 1;
                 const uint8_t* st = smem + s * ATT3_STAGE;
                 // S_t(it): needs K and Q_t of the item and the tile's TMEM columns (O_t(it-1) drained)
-                mbar_wait(&k_full[s], sph);
-                mbar_wait(&q_full[t * 2 + s], sph);
-                mbar_wait(&tmem_free[t], (it & 1) ^ 1);
+                wait(&k_full[s], sph);
+                wait(&q_full[t * 2 + s], sph);
+                wait(&tmem_free[t], (it & 1) ^ 1);
                 // start tile 1 half a period late so the two softmax warpgroups do not fight over the MUFU pipe
-                if (t == 1 && it == 0 && !(a.token & 1)) mbar_wait(&p_full[0], 0);
+                if (t == 1 && it == 0 && !(a.token & 1)) wait(&p_full[0], 0);
                 tc_fence_after();
                 const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(st + t * 16384));
                 const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(st + ATT3_OFF_K));
@@ -377,9 +453,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 // k-steps start as soon as the first half of P is written
                 long long* tr = (a.trace && blockIdx.x == 0) ? a.trace + (it * 2 + t) * 16 + 8 : nullptr;
                 if (tr) tr[0] = clock64();
-                mbar_wait(&v_full[s], sph);
+                wait(&v_full[s], sph);
                 const uint64_t dv = umma_desc_mnmajor_sw128(smem_u32(st + ATT3_OFF_V));
-                mbar_wait(&p_half[t], it & 1);
+                wait(&p_half[t], it & 1);
                 tc_fence_after();
                 if (tr) tr[1] = clock64();
 #pragma unroll
@@ -387,7 +463,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     umma_f16_ts(tmem + t * 256 + 64, tmem + t * 256 + 8 * k, dv + (uint64_t)(k * (2048 >> 4)),
                                 idesc_o, k != 0);
                 if (tr) tr[2] = clock64();
-                mbar_wait(&p_full[t], it & 1);
+                wait(&p_full[t], it & 1);
                 tc_fence_after();
                 if (tr) tr[3] = clock64();
 #pragma unroll
@@ -398,20 +474,20 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                 umma_commit(&v_empty[s]);  // this tile's PV MMAs no longer read V once retired
                 if (tr) {
                     tr[4] = clock64();
-                    mbar_wait(&o_full[t], it & 1);
+                    wait(&o_full[t], it & 1);
                     tr[5] = clock64();
                 }
             }
         }
     } else if (warp == 10) {
-        // ================================================================= extras query rows on mma.sync
+        // ================================================================= extras query rows: extras keys + merge
         const int g = lane >> 2, t = lane & 3;
         for (int it = 0; it < my_items; ++it) {
             const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
             const int s = it & 1;
             const uint8_t* st = smem + s * ATT3_STAGE;
-            mbar_wait(&k_full[s], (it >> 1) & 1);
+            wait(&k_full[s], (it >> 1) & 1);
             // A fragments: rows g (token g of the sample; only g < extras is kept), rows g+8 are zero
             uint32_t qf[4][4];
 #pragma unroll
@@ -422,16 +498,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             }
             AttRowState rs;
             rs.init();
-            mbar_wait(&v_full[s], (it >> 1) & 1);
+            wait(&v_full[s], (it >> 1) & 1);
             // extras keys: the first 8 tokens of the X tile, of which [0, extras) are valid
             att_mma_block<true>(smem_u32(st + ATT3_OFF_KX), smem_u32(st + ATT3_OFF_VX), 0, 1, a.extras, qf, rs,
                                 a.scale_log2e, lane);
-            const uint32_t sK_u = smem_u32(st + ATT3_OFF_K), sV_u = smem_u32(st + ATT3_OFF_V);
-            if (!(a.token & 4)) {
-#pragma unroll 1
-                for (int kb0 = 0; kb0 < 256; kb0 += 64)
-                    att_mma_block<true>(sK_u, sV_u, kb0, 8, 256, qf, rs, a.scale_log2e, lane);
-            }
             __syncwarp();
             if (lane == 0) {  // this warp no longer reads the stage
                 mbar_arrive(&k_empty[s]);
@@ -440,13 +510,38 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             float l0 = rs.l0;
             l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
             l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            // merge with the eight partials over the patch keys (fixed order: deterministic)
+            wait(&px_full[s], (it >> 1) & 1);
             if (g < a.extras) {
-                const float inv0 = 1.f / l0;
+                const float* rec = px_buf + (size_t)s * 8 * ATT3_PX_REC + g * ATT3_PX_ROW;
+                float M = rs.m0;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) M = fmaxf(M, rec[p * ATT3_PX_REC + 64]);
+                float sc = exp2f((rs.m0 - M) * a.scale_log2e);
+                float Lsum = l0 * sc;
+                float o[8][2];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i][0] = rs.o[i][0] * sc, o[i][1] = rs.o[i][1] * sc;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const float* r = rec + p * ATT3_PX_REC;
+                    sc = exp2f((r[64] - M) * a.scale_log2e);
+                    Lsum = fmaf(r[65], sc, Lsum);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 v = *reinterpret_cast<const float2*>(r + i * 8 + 2 * t);
+                        o[i][0] = fmaf(v.x, sc, o[i][0]);
+                        o[i][1] = fmaf(v.y, sc, o[i][1]);
+                    }
+                }
+                const float inv0 = 1.f / Lsum;
                 __nv_bfloat16* o0 = a.out + ((size_t)b * a.L + g) * D + h * 64 + 2 * t;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(rs.o[i][0] * inv0, rs.o[i][1] * inv0);
+                    *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(o[i][0] * inv0, o[i][1] * inv0);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&px_empty[s]);
         }
     } else {
         // ================================================================= softmax + epilogue: one thread per query row
@@ -457,39 +552,86 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         const float c = a.scale_log2e;
         const int q0 = a.extras + t * 128;
 
-        // scores of query row r against the extras keys (tokens [0, extras)) of item `it`, on the CUDA cores
+        // Per-item side work of a softmax warp on mma.sync, done for item it+1 while the tensor core finishes O of item it
+        // (measured alternatives, profiles/r02_attention_experiments.txt: after the epilogue -- the K / V slots are then
+        // released too late and the refill latency is exposed -- and at the start of the item under its S MMA: both slower):
+        //  extras_scores(it)  scores of this warp's 32 query rows against the extras KEYS (tokens [0, extras)):
+        //                     S = Q_rows Kx^T, 8 HMMA;
+        //  extras_slice(it)   the extras QUERY rows' partial attention over this warp's own 32 patch keys (one softmax
+        //                     block); the record (row max, row sum, 64 output dims per extras row) goes to shared memory
+        //                     for the extras warp.  Last reader of K / V of the item in this warp.
+        const int w8 = t * 4 + quarter;
         auto extras_scores = [&](int it, float& se0, float& se1) {
             const int s = it & 1;
-            const uint8_t* sQ = smem + s * ATT3_STAGE + t * 16384;
-            const uint8_t* sKx = smem + s * ATT3_STAGE + ATT3_OFF_KX;
-            mbar_wait(&k_full[s], (it >> 1) & 1);
-            mbar_wait(&q_full[t * 2 + s], (it >> 1) & 1);
-            se0 = 0.f, se1 = 0.f;
+            const uint32_t sph = (it >> 1) & 1;
+            const uint8_t* st = smem + s * ATT3_STAGE;
+            wait(&k_full[s], sph);
+            wait(&q_full[t * 2 + s], sph);
+            const uint32_t sQ_u = smem_u32(st + t * 16384), sKx_u = smem_u32(st + ATT3_OFF_KX);
+            uint32_t bk[4][2];  // B fragments of Kx: k-step ks -> (dims 16ks..+7, +8..+15) x keys 0..7
+            ldmatrix_x4(sKx_u + att_swz(lane & 7, lane >> 3), bk[0][0], bk[0][1], bk[1][0], bk[1][1]);
+            ldmatrix_x4(sKx_u + att_swz(lane & 7, (lane >> 3) + 4), bk[2][0], bk[2][1], bk[3][0], bk[3][1]);
+            float cacc[2][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(sQ + r * 128 + ((j ^ (r & 7)) << 4));
-                const float qf[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
-                                     bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-                const uint4 k0 = *reinterpret_cast<const uint4*>(sKx + att_swz(0, j));
-                const float kf[8] = {bf16_lo(k0.x), bf16_hi(k0.x), bf16_lo(k0.y), bf16_hi(k0.y),
-                                     bf16_lo(k0.z), bf16_hi(k0.z), bf16_lo(k0.w), bf16_hi(k0.w)};
+            for (int mt = 0; mt < 2; ++mt) {
+                cacc[mt][0] = cacc[mt][1] = cacc[mt][2] = cacc[mt][3] = 0.f;
+                const int row = quarter * 32 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) se0 = fmaf(qf[e], kf[e], se0);
-                if (a.extras == 2) {
-                    const uint4 k1 = *reinterpret_cast<const uint4*>(sKx + att_swz(1, j));
-                    const float kg[8] = {bf16_lo(k1.x), bf16_hi(k1.x), bf16_lo(k1.y), bf16_hi(k1.y),
-                                         bf16_lo(k1.z), bf16_hi(k1.z), bf16_lo(k1.w), bf16_hi(k1.w)};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) se1 = fmaf(qf[e], kg[e], se1);
+                for (int ks = 0; ks < 4; ++ks) {
+                    uint32_t af[4];
+                    ldmatrix_x4(sQ_u + att_swz(row, ks * 2 + (lane >> 4)), af[0], af[1], af[2], af[3]);
+                    mma_bf16_16816(cacc[mt], af, bk[ks][0], bk[ks][1]);
                 }
             }
+            // row (lane) of this warp = m-tile lane/16, fragment row (lane & 15): held by lane 4 * (lane & 7)
+            const int src = 4 * (lane & 7);
+            float v[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[mt][k] = __shfl_sync(0xffffffffu, cacc[mt][k], src);
+            const int mt = lane >> 4, up = (lane >> 3) & 1;
+            se0 = mt ? (up ? v[1][2] : v[1][0]) : (up ? v[0][2] : v[0][0]);
+            se1 = mt ? (up ? v[1][3] : v[1][1]) : (up ? v[0][3] : v[0][1]);
             if (a.extras != 2) se1 = -INFINITY;
+        };
+        auto extras_slice = [&](int it) {
+            const int s = it & 1;
+            const uint32_t sph = (it >> 1) & 1;
+            const uint8_t* st = smem + s * ATT3_STAGE;
+            const int g = lane >> 2, tt = lane & 3;
+            uint32_t qf[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qf[ks][0] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2) + 4 * tt);
+                qf[ks][2] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2 + 1) + 4 * tt);
+                qf[ks][1] = qf[ks][3] = 0u;
+            }
+            wait(&v_full[s], sph);
+            float m0, l0, o[8][2];
+            att_extras_slice32(smem_u32(st + ATT3_OFF_K), smem_u32(st + ATT3_OFF_V), w8 * 32, qf, a.scale_log2e, lane,
+                               m0, l0, o);
+            wait(&px_empty[s], sph ^ 1);  // the extras warp has merged the record of item it-2
+            if (g < 2) {
+                float* rec = px_buf + ((size_t)s * 8 + w8) * ATT3_PX_REC + g * ATT3_PX_ROW;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float2*>(rec + i * 8 + 2 * tt) = make_float2(o[i][0], o[i][1]);
+                if (tt == 0) rec[64] = m0, rec[65] = l0;
+            }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&k_empty[s]);  // this warp has read Kx of the item
+            if (lane == 0) {  // this warp has read K / Kx / Qx / V of the item; its record is written
+                mbar_arrive(&px_full[s]);
+                mbar_arrive(&k_empty[s]);
+                mbar_arrive(&v_empty[s]);
+            }
         };
 
         float se0 = 0.f, se1 = 0.f;
-        if (my_items > 0) extras_scores(0, se0, se1);
+        if (my_items > 0) {
+            extras_scores(0, se0, se1);
+            extras_slice(0);
+        }
         for (int it = 0; it < my_items; ++it) {
             const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
@@ -499,7 +641,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
 
             long long* tr = (a.trace && blockIdx.x == 0 && r == 0) ? a.trace + (it * 2 + t) * 16 : nullptr;
             if (tr) tr[0] = clock64();
-            mbar_wait(&s_full[t], ph);
+            wait(&s_full[t], ph);
             tc_fence_after();
             if (tr) tr[1] = clock64();
             // this warp's store of the previous item was issued ~1000 clk ago: once it has read its 32 staging rows
@@ -515,7 +657,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
 #pragma unroll 1
-            for (int jj = 0; jj < ((a.token & 32) ? 2 : 8); jj += 2) {
+            for (int jj = 0; jj < 8; jj += 2) {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     uint32_t(&cur)[32] = u ? vb : va;
@@ -536,7 +678,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             if (tr) tr[3] = clock64();
             // the tiles take turns in the exp pass: tile t waits for its token (the other tile's previous exp pass has
             // ended), so that tile's MMA waits, row max and epilogue always run under this tile's exponentials
-            if ((a.token & 1) && (t == 1 || it > 0)) mbar_wait(&tok[t], (t == 1 ? it : it - 1) & 1);
+            if ((a.token & 1) && (t == 1 || it > 0)) wait(&tok[t], (t == 1 ? it : it - 1) & 1);
             const float pe0 = ex2_approx(fmaf(se0, c, -mc));
             const float pe1 = (a.extras == 2) ? ex2_approx(fmaf(se1, c, -mc)) : 0.f;
             // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
@@ -544,6 +686,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             f32x2 sum2 = f2_pack(pe0, pe1), sum2b = f2_splat(0.f);
             tmem_ld_32x32b_x32(t_row, va);
             tmem_ld_wait();
+            // (fully unrolled, one basic block: the scheduler can run chunk j's exponentials on the MUFU pipe under the
+            // conversions / row sums of chunk j-1 and the scaling of chunk j+1)
 #pragma unroll 1
             for (int jj = 0; jj < 8; jj += 2) {
 #pragma unroll
@@ -557,8 +701,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     for (int e = 0; e < 16; ++e) {
                         float x0, x1;
                         f2_unpack(f2_fma(f2_pack_u(cur[2 * e], cur[2 * e + 1]), c2, nmc2), x0, x1);
-                        const f32x2 p = (a.token & 8) ? f2_pack(x0 * 0.001f, x1 * 0.001f)
-                                                      : f2_pack(ex2_approx(x0), ex2_approx(x1));
+                        const f32x2 p = f2_pack(ex2_approx(x0), ex2_approx(x1));
                         if (e & 1)
                             sum2b = f2_add(sum2b, p);
                         else
@@ -568,8 +711,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     if (j < 7) tmem_ld_wait();
                     // P chunk j < 4 -> columns [16j, 16j+16) (inside S chunk j/2), j >= 4 -> [128 + 16(j-4), ..)
                     // (inside S chunks 4, 5): always columns whose scores are already in registers
-                    if (!(a.token & 16)) tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);
-                    else if (pk[0] == 0x12345u && pk[7] == 0x77u) m2 += 1.f;
+                    tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);
                 }
                 if (jj == 2) {
                     // keys [0, 128) are done: the first 8 k-steps of O = P V run under the rest of pass 2
@@ -594,16 +736,15 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             f2_unpack(sum2, sa, sb);
             f2_unpack(sum2b, sc, sd);
             const float inv = 1.f / ((sa + sb) + (sc + sd));
-            // while the tensor core finishes O: the next item's extras-key scores (its operands landed long ago)
-            if (it + 1 < my_items && !(a.token & 64)) extras_scores(it + 1, se0, se1);
-            if (a.token & 64) {
-                __syncwarp();
-                if (lane == 0 && it + 1 < my_items) mbar_arrive(&k_empty[(it + 1) & 1]);
+            // while the tensor core finishes O: the next item's side work (its operands were requested an item ago)
+            if (it + 1 < my_items) {
+                extras_scores(it + 1, se0, se1);
+                extras_slice(it + 1);
             }
             if (tr) tr[5] = clock64();
 
             // ---- epilogue: O row (fp32) out of TMEM, then release the tile's columns for S_t of the next item
-            mbar_wait(&o_full[t], ph);
+            wait(&o_full[t], ph);
             tc_fence_after();
             if (tr) tr[6] = clock64();
             tmem_ld_32x32b_x32(t_row + 64, va);

@@ -50,6 +50,19 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// try_wait with an explicit suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the time
+// limit passes, instead of returning to a software spin loop that competes for its scheduler's issue slots
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug traps (launch failure) instead of hanging the GPU.
 #ifndef DDB_SPIN_LIMIT
 #define DDB_SPIN_LIMIT (1u << 26)
@@ -58,6 +71,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > DDB_SPIN_LIMIT) __trap();
+    }
+}
+// long waits (hundreds of clocks or more): sleep in hardware, 20 us per try
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (1u << 20)) __trap();
     }
 }
 

@@ -20,7 +20,17 @@ ap.add_argument("--debug", default="0")
 ap.add_argument("--lib", default=None, help="alternative libduodiff_b200.so (A/B builds)")
 ap.add_argument("--opt", action="append", default=[], help="ddb_set_option name=value (repeatable), e.g. attn_token=0")
 a = ap.parse_args()
-Lb = _lib.load(a.lib)
+if a.lib:  # an older build (A/B): bind only what this tool calls
+    import ctypes as C
+    Lb = C.CDLL(a.lib)
+    Lb.ddb_op_attention.restype = C.c_int
+    Lb.ddb_op_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    Lb.ddb_set_option.restype = C.c_int
+    Lb.ddb_set_option.argtypes = [C.c_char_p, C.c_int32]
+    Lb.ddb_last_error.restype = C.c_char_p
+    _lib._lib = Lb  # _lib.check() reads the error text from this library
+else:
+    Lb = _lib.load()
 for o in a.opt:
     k, v = o.split("=")
     _lib.check(Lb.ddb_set_option(k.encode(), int(v)))
