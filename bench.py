@@ -583,6 +583,7 @@ def run_ee(args, rank: int, world: int, local_rank: int) -> None:
     assert torch.isfinite(out).all()
     idx = exit_log.float()  # [1000, B] of the last pass
     mean_exit = idx.mean().item()
+    exit_hist = torch.bincount(exit_log.flatten().long().cpu(), minlength=depth + 1).tolist()
     # FLOPs actually needed: blocks executed per sample = its exit index (depth = never left), + token assembly
     blocks = torch.tensor([block_flops(pf, i) for i in range(depth)], dtype=torch.float64)
     cum = torch.cat([torch.zeros(1, dtype=torch.float64), blocks.cumsum(0)]).to(dev)
@@ -646,7 +647,7 @@ def run_ee(args, rank: int, world: int, local_rank: int) -> None:
                          api="duodiff_b200.eesampler.get_samples(mode=1)"),
                 gpu_launches=int(tt[2].item()),
                 early_exit=dict(mean_exit_layer=round(mean_exit, 3), depth=depth,
-                                exit_histogram=torch.bincount(exit_log.flatten().long().cpu(), minlength=depth + 1).tolist(),
+                                exit_histogram=exit_hist,
                                 flops_executed_per_image=flops_pass / B, **side),
                 roofline=dict(bound="tensor", kernel="executed blocks (sum of exit indices) of the compacted step",
                               achieved=round(achieved, 1), peak=pk["tflops"], unit="TFLOP/s",

@@ -272,12 +272,12 @@ static std::atomic<int> g_gemm_ln_cfg{0};  // ddb_set_option "gemm_ln_cfg": 1 = 
 static std::atomic<int> g_alt_dir{1};  // ddb_set_option "alt_dir": alternate the row direction of consecutive kernels (L2 reuse)
 static std::atomic<int> g_gemm_bn128{0};  // ddb_set_option "gemm_bn128": 256x128 tiles for the N = 512 GEMMs. Measured SLOWER (fc2 63 -> 81 us):
                               // a 256x128x16 MMA takes ~0.75x the time of a 256x256x16 one, not 0.5x (shared-memory operand reads)
-template <int EPI, bool STATS, int STAGES, int NBUF, int BN = 256>
+template <int EPI, bool STATS, int STAGES, int NBUF, int BN = 256, bool PROBE = false>
 static int launch_gemm2_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
     static ddb_host::DeviceOnce configured;
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
-    constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN, BN>::SMEM_BYTES;
-    auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF, BN>;
+    constexpr int kSmem = Gemm2Cfg<STAGES, NBUF, kLN, BN, PROBE>::SMEM_BYTES;
+    auto kfn = gemm2_tcgen05_kernel<EPI, STATS, STAGES, NBUF, BN, PROBE>;
     if (!configured.done()) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         configured.mark();
@@ -373,6 +373,10 @@ static int launch_gemm2(const GemmArgs& a, int epi, int num_sms, cudaStream_t st
             if (short_k)
                 return stats ? launch_gemm2_t<EPI_RES, true, 4, 3>(a, num_sms, st)
                              : launch_gemm2_t<EPI_RES, false, 4, 3>(a, num_sms, st);
+            if (a.probe_w) {  // fc2 of an early-exit model: + the next layer's probe partial dot products
+                if (!stats || !a.probe_out) return fail(DDB_ERR_INVALID, "the probe epilogue needs stats_out and probe_out");
+                return launch_gemm2_t<EPI_RES, true, 5, 2, 256, true>(a, num_sms, st);
+            }
             return stats ? launch_gemm2_t<EPI_RES, true, 5, 2>(a, num_sms, st)
                          : launch_gemm2_t<EPI_RES, false, 5, 2>(a, num_sms, st);
     }
@@ -395,16 +399,16 @@ static int launch_gemm(const GemmArgs& a, int epi, int num_sms, cudaStream_t st)
 }
 
 static int launch_ln_stats(const __nv_bfloat16* x, int M, int D, const int* m_dev, float2* stats, const float* pw,
-                           const float* pb, float* psig, cudaStream_t st) {
+                           float* pp, cudaStream_t st) {
     const int grid = (M + 7) / 8;
     if (grid <= 0) return DDB_OK;
     ProfScope ps(PC_LN_STATS);
     switch (D) {
-        case 256: CUDA_TRY(launch_pdl(ln_stats_kernel<256>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
-        case 512: CUDA_TRY(launch_pdl(ln_stats_kernel<512>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
-        case 768: CUDA_TRY(launch_pdl(ln_stats_kernel<768>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
-        case 1024: CUDA_TRY(launch_pdl(ln_stats_kernel<1024>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
-        case 2048: CUDA_TRY(launch_pdl(ln_stats_kernel<2048>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pb, psig)); break;
+        case 256: CUDA_TRY(launch_pdl(ln_stats_kernel<256>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pp)); break;
+        case 512: CUDA_TRY(launch_pdl(ln_stats_kernel<512>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pp)); break;
+        case 768: CUDA_TRY(launch_pdl(ln_stats_kernel<768>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pp)); break;
+        case 1024: CUDA_TRY(launch_pdl(ln_stats_kernel<1024>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pp)); break;
+        case 2048: CUDA_TRY(launch_pdl(ln_stats_kernel<2048>, dim3(grid), dim3(256), 0, st, x, M, m_dev, stats, pw, pp)); break;
         default: return fail(DDB_ERR_INVALID, "embed_dim %d unsupported (need 256/512/768/1024/2048)", D);
     }
     LAUNCH_CHECK();
@@ -523,9 +527,9 @@ struct ddb_model {
     std::vector<HeadW> ee_heads;
     std::vector<Buf> probe_w, probe_b;
     // workspace
-    Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_sig, scores, outputs, exit_idx;
+    Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_p, scores, outputs, exit_idx;
     // early-exit compaction (mode 1): device-side live counts, slot maps, gather lists, scratch batch of leavers
-    Buf ee_n, ee_slot, ee_keep_src, ee_exit_src, ee_exit_slot, xe, stats_e;
+    Buf ee_n, ee_slot, ee_dest, ee_exit_slot, ee_sc, ee_ticket, xe, stats_e;
     std::vector<GemmArgs> head_dec_x;       // head i on the scratch batch
     std::vector<EeBufList> ee_live;         // buffers that must be compacted when samples leave before block i
     std::vector<int> ee_live_n;
@@ -771,17 +775,18 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     m->xo.resize(cfg->depth);
     for (int i = 0; i < cfg->depth; ++i) DDB_TRY(new_buf(m->xo[i], act));
     if (cfg->early_exit) {
-        DDB_TRY(new_buf(m->probe_sig, (size_t)m->Mpad * 4));
+        DDB_TRY(new_buf(m->probe_p, (size_t)m->Mpad * (D / 64) * 4));
         DDB_TRY(new_buf(m->scores, (size_t)cfg->depth * cfg->max_batch * 4));
         DDB_TRY(new_buf(m->outputs, (size_t)(cfg->depth + 1) * cfg->max_batch * m->chw * 4));
         DDB_TRY(new_buf(m->exit_idx, (size_t)cfg->max_batch * 4));
-        DDB_TRY(new_buf(m->ee_n, 4 * 4));
+        DDB_TRY(new_buf(m->ee_n, 8 * 4));
         DDB_TRY(new_buf(m->ee_slot, (size_t)cfg->max_batch * 4));
-        DDB_TRY(new_buf(m->ee_keep_src, (size_t)cfg->max_batch * 4));
-        DDB_TRY(new_buf(m->ee_exit_src, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_dest, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_sc, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_ticket, 4));
         DDB_TRY(new_buf(m->ee_exit_slot, (size_t)cfg->max_batch * 4));
         DDB_TRY(new_buf(m->xe, act));
-        DDB_TRY(new_buf(m->stats_e, (size_t)m->Mpad * sizeof(float2)));
+        DDB_TRY(new_buf(m->stats_e, (size_t)m->Mpad * (D / 64) * sizeof(float2)));
     }
     // ---- plan (buffer routing of models/uvit.py:367-375)
     m->ops.resize(cfg->depth);
@@ -992,8 +997,13 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     int kind = 0;
     // consecutive kernels walk the rows in alternating directions (GemmArgs::reverse): L2 reuse between kernels
     bool rev = false;
+    int probe_layer = -1;  // >= 0: this (fc2) GEMM also writes the partial dot products of that layer's probe
     auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
         g.M = M;
+        if (probe_layer >= 0) {
+            g.probe_w = m->probe_w[probe_layer]->as<float>();
+            g.probe_out = m->probe_p->as<float>();
+        }
         if (g_alt_dir && pair && epi != EPI_DECODE) {
             g.reverse = rev ? 1 : 0;
             rev = !rev;
@@ -1020,7 +1030,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     }
     const std::vector<ddb_model::HalfOps>* split = nullptr;
     const int rows_h0 = (B / 2) * m->L;
-    if (g_mlp_split && pair && !cp && B >= 2) {
+    if (g_mlp_split && pair && !ee && B >= 2) {
         auto it = m->mlp_split.find(B);
         if (it == m->mlp_split.end()) {
             std::vector<ddb_model::HalfOps> v(c.depth);
@@ -1044,50 +1054,55 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         split = &it->second;
     }
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
+    bool probe_ready = false;  // early exit: the probe partials of the current block input are already in probe_p
     for (int i = 0; i < c.depth; ++i) {
         const BlockOps& op = m->ops[i];
         const BlockW& bw = m->blocks[i];
+        if (ee) {
+            // probe i + head i look at the block input (models/early_exit.py:294-296).  Its LayerNorm statistics and the
+            // probe's partial dot products were written by the fc2 epilogue that produced it; only the first layer (and the
+            // single-CTA GEMM variant) needs a pass of its own over the activations.
+            if (!probe_ready) {
+                DDB_TRY(launch_ln_stats(cur, M, D, cp ? een + 1 : nullptr, st2, m->probe_w[i]->as<float>(),
+                                        m->probe_p->as<float>(), st));
+                kind = 1;
+            }
+            probe_ready = false;
+        }
+        const int np_cur = kind == 2 ? np_p : 1;           // format of the block input's statistics
+        float2* st_cur = kind == 2 ? stp : st2;
         if (cp) {
-            // probe i on the live rows; leavers take head i's output and are squeezed out of every live buffer
-            DDB_TRY(launch_ln_stats(cur, M, D, een + 1, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
-                                    m->probe_sig->as<float>(), st));
-            kind = 1;
+            // leavers take head i's output and are squeezed out of every live buffer
             {
                 ProfScope ps(PC_EE_OTHER);
-                CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(1), dim3(1024), 0, st, m->probe_sig->as<float>(), m->L, cp->threshold, i, B, c.depth, een,
-                                                     m->ee_slot->as<int>(), m->ee_keep_src->as<int>(),
-                                                     m->ee_exit_src->as<int>(), m->ee_exit_slot->as<int>(),
-                                                     m->scores->as<float>(), cp->exit_idx, cp->t_dev, cp->exit_log,
-                                                     cp->score_mean_log));
+                CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
+                                    np_p, (const float*)m->probe_b[i]->as<float>(), m->L, cp->threshold, i, B,
+                                    (int)c.depth, een, m->ee_slot->as<int>(), m->ee_dest->as<int>(),
+                                    m->ee_exit_slot->as<int>(), m->scores->as<float>(), cp->exit_idx, cp->t_dev,
+                                    cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
+                                    m->ee_ticket->as<unsigned>()));
                 LAUNCH_CHECK();
-                CUDA_TRY(launch_pdl(ee_gather_exit_kernel, dim3(m->L, EE_GATHER_Y), dim3(128), 0, st, cur, st2, een, m->ee_exit_src->as<int>(),
-                                                            m->xe->as<__nv_bfloat16>(), m->stats_e->as<float2>(), m->L,
-                                                            D));
+                // stayers compacted in place (block input, pending long skips, statistics), leavers -> scratch batch
+                CUDA_TRY(launch_pdl(ee_move_kernel, dim3(m->L, m->ee_live_n[i] + 1), dim3(128), 0, st, m->ee_live[i],
+                                    m->ee_live_n[i], m->xe->as<__nv_bfloat16>(), st_cur, m->stats_e->as<float2>(), np_cur,
+                                    (const int*)een, (const int*)m->ee_dest->as<int>(), m->L, D));
                 LAUNCH_CHECK();
             }
             {
                 GemmArgs g = m->head_dec_x[i];
                 g.M = M;
+                g.nparts = np_cur;
                 ProfScope ps(PC_GEMM_DECODE);
                 DDB_TRY(launch_gemm(g, EPI_DECODE, nsm, st));
             }
             DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(), eps, B, st, een + 2,
                              m->ee_exit_slot->as<int>()));
-            {
-                ProfScope ps(PC_EE_OTHER);
-                CUDA_TRY(launch_pdl(ee_compact_kernel, dim3(m->L, m->ee_live_n[i] + 1), dim3(128), 0, st, 
-                    m->ee_live[i], m->ee_live_n[i], st2, een, m->ee_keep_src->as<int>(), m->L, D));
-                LAUNCH_CHECK();
-            }
         } else if (ee) {
-            // probe i + head i look at the block input (models/early_exit.py:294-296)
-            DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, m->probe_w[i]->as<float>(), m->probe_b[i]->as<float>(),
-                                    m->probe_sig->as<float>(), st));
-            kind = 1;
             {
                 ProfScope ps(PC_EE_OTHER);
-                CUDA_TRY(launch_pdl(probe_mean_kernel, dim3(B), dim3(128), 0, st, m->probe_sig->as<float>(), m->L,
-                                                     m->scores->as<float>() + (size_t)i * B));
+                CUDA_TRY(launch_pdl(probe_mean_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
+                                    np_p, (const float*)m->probe_b[i]->as<float>(), m->L,
+                                    m->scores->as<float>() + (size_t)i * B));
                 LAUNCH_CHECK();
             }
             DDB_TRY(run_gemm(m->head_dec[i], EPI_DECODE, PC_GEMM_DECODE, true, false));
@@ -1100,7 +1115,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             kind = pair ? 2 : 0;
         }
         if (kind == 0) {
-            DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+            DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, st));
             kind = 1;
         }
         DDB_TRY(run_gemm(op.qkv, EPI_LN, PC_GEMM_QKV, true, false));
@@ -1119,7 +1134,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         if (pair) {
             kind = 2;
         } else {
-            DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+            DDB_TRY(launch_ln_stats(m->xm->as<__nv_bfloat16>(), M, D, nullptr, st2, nullptr, nullptr, st));
             kind = 1;
         }
         if (split) {
@@ -1144,14 +1159,16 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             }
         } else {
             DDB_TRY(run_gemm(op.fc1, EPI_LN_GELU, PC_GEMM_FC1, true, false));
+            if (ee && pair && i + 1 < c.depth) probe_layer = i + 1, probe_ready = true;
             DDB_TRY(run_gemm(op.fc2, EPI_RES, PC_GEMM_FC2, false, true));
+            probe_layer = -1;
         }
         kind = pair ? 2 : 0;
         cur = m->xo[i]->as<__nv_bfloat16>();
     }
     (void)half;
     if (kind == 0) {
-        DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, nullptr, st));
+        DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, st));
         kind = 1;
     }
     DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
@@ -1710,7 +1727,7 @@ int ddb_op_attention(const void* qkv_dev, void* out_dev, int32_t B, int32_t L, i
 int ddb_op_ln_stats(const void* x_dev, int32_t M, int32_t D, float* stats_dev, void* stream) {
     if (!x_dev || !stats_dev) return fail(DDB_ERR_INVALID, "null argument");
     return launch_ln_stats(reinterpret_cast<const __nv_bfloat16*>(x_dev), M, D, nullptr,
-                           reinterpret_cast<float2*>(stats_dev), nullptr, nullptr, nullptr, (cudaStream_t)stream);
+                           reinterpret_cast<float2*>(stats_dev), nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int ddb_op_pack_linear(const float* w_dev, const float* bias_dev, const float* gamma_dev, const float* beta_dev,

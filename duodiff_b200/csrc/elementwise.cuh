@@ -169,15 +169,16 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // =====================================================================================================
 // LayerNorm row statistics (nn.LayerNorm, eps 1e-5; models/uvit.py:206-207,377) as (mean, M2) per row, and --
-// optionally -- the early-exit MLP probe's per-token sigmoid(w.x + b) (models/early_exit.py:34-37).
-// One warp per row, 16-byte loads, exact two-pass statistics in registers.
+// optionally -- the early-exit MLP probe's per-token dot product w.x (models/early_exit.py:34-37) in the layout the
+// GEMM epilogues use for it: probe_p[row, D/64] partial dots (here: the whole dot in part 0, zeros elsewhere).  Only the
+// first layer needs this pass; the input of every later block comes with its statistics and probe partials from the
+// fc2 GEMM that produced it.  One warp per row, 16-byte loads, exact two-pass statistics in registers.
 // =====================================================================================================
 template <int D>
 __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __restrict__ x, int M,
                                                        const int* __restrict__ m_dev, float2* __restrict__ stats,
                                                        const float* __restrict__ probe_w,
-                                                       const float* __restrict__ probe_b,
-                                                       float* __restrict__ probe_sig) {
+                                                       float* __restrict__ probe_p) {
     constexpr int CH = D / 256;  // 16-byte chunks per lane
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -217,10 +218,8 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
         m2 += __shfl_xor_sync(0xffffffffu, m2, o);
         dot += __shfl_xor_sync(0xffffffffu, dot, o);
     }
-    if (lane == 0) {
-        stats[row] = make_float2(mean, m2);
-        if (probe_w) probe_sig[row] = 1.f / (1.f + expf(-(dot + probe_b[0])));
-    }
+    if (lane == 0) stats[row] = make_float2(mean, m2);
+    if (probe_w && lane < D / 64) probe_p[(size_t)row * (D / 64) + lane] = lane == 0 ? dot : 0.f;
 }
 
 // =====================================================================================================
@@ -546,14 +545,22 @@ __global__ void finalize_nhwc_kernel(const float* __restrict__ x, float* __restr
 // =====================================================================================================
 // Early exit (eesampler.py:62-72): probe score per (layer, sample) = mean over tokens of the per-token sigmoid.
 // =====================================================================================================
-// probe_sig [M] (one layer) -> score[b] = mean_l sig[b*L + l]; deterministic tree order.
-__global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict__ sig, int L,
+// per-token probe output sigmoid(w.x + b) from the row's np partial dot products (fixed summation order)
+__device__ __forceinline__ float probe_token(const float* __restrict__ pp, size_t row, int np, float bias) {
+    float d = 0.f;
+    for (int c = 0; c < np; ++c) d += pp[row * np + c];
+    return 1.f / (1.f + expf(-(d + bias)));
+}
+// probe partials [M, np] (one layer) -> score[b] = mean_l sigmoid(w.x_{b,l} + bias); deterministic tree order.
+__global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict__ pp, int np,
+                                                         const float* __restrict__ bias_p, int L,
                                                          float* __restrict__ score /*[B]*/) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x;
+    const float bias = bias_p[0];
     float s = 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) s += sig[(size_t)b * L + l];
+    for (int l = threadIdx.x; l < L; l += blockDim.x) s += probe_token(pp, (size_t)b * L + l, np, bias);
     __shared__ float red[4];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -607,48 +614,69 @@ __global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, 
     if (i < depth * B) scores[i] = __int_as_float(0x7fc00000);  // NaN: "not produced" (sample had already left)
 }
 
-// One CTA of 1024 threads.  Scores the live samples (warp per sample), decides who leaves at `layer`, builds the
-// gather lists with a block-wide scan and updates the state.
-__global__ void __launch_bounds__(1024) ee_decide_kernel(
-    const float* __restrict__ sig, int L, float thr, int layer, int B, int depth, int* __restrict__ ee_n,
-    int* __restrict__ slot, int* __restrict__ keep_src, int* __restrict__ exit_src, int* __restrict__ exit_slot,
+// grid = B CTAs of 128 threads.  CTA b scores live sample b (mean over tokens of the probe's sigmoid, with exactly the
+// summation order of probe_mean_kernel, so the exit decisions of the two modes can never differ by rounding); the LAST
+// CTA to finish (atomic ticket) decides who leaves at `layer`, builds the destination map of the row move with a
+// block-wide scan and updates the state.  (Round 1 scored all samples in one CTA: with the probe's partial dot products
+// coming from the fc2 epilogue that is 1 MB through a single SM, 11 us per layer.)
+//   ee_n[0..4] = {n_active, n_active*L, n_exit, n_exit*L, n_active BEFORE this layer}
+//   dest[b] (b < previous n_active): >= 0 -> the sample stays and becomes compact sample dest[b];
+//                                    <  0 -> it leaves: scratch-batch sample -(dest[b] + 1)
+constexpr int EE_MAX_BATCH = 1024;
+__global__ void __launch_bounds__(128) ee_decide_kernel(
+    const float* __restrict__ pp, int np, const float* __restrict__ bias_p, int L, float thr, int layer, int B,
+    int depth, int* __restrict__ ee_n, int* __restrict__ slot, int* __restrict__ dest, int* __restrict__ exit_slot,
     float* __restrict__ scores, int* __restrict__ exit_idx, const int* __restrict__ t_dev,
-    int* __restrict__ exit_log, float* __restrict__ score_mean_log) {
+    int* __restrict__ exit_log, float* __restrict__ score_mean_log, float* __restrict__ sc_tmp,
+    unsigned* __restrict__ ticket) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float sc[1024];
-    __shared__ int new_slot[1024];
-    __shared__ int wtot[2][32];
-    __shared__ float wsum[32];
-    __shared__ float part[1024][4];
-    const int n = ee_n[0];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // score = mean over tokens, with exactly the summation order of probe_mean_kernel (128 threads per sample), so the
-    // exit decisions of the two modes can never differ by rounding.  Eight groups of 128 threads walk the samples
-    // without any block-wide synchronisation in between (the samples' loads overlap); one barrier at the end.
-    const int grp = threadIdx.x >> 7, gt = threadIdx.x & 127;
-#pragma unroll 4
-    for (int b = grp; b < n; b += 8) {
-        float s = 0.f;
-        for (int l = gt; l < L; l += 128) s += sig[(size_t)b * L + l];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) part[b][(gt >> 5)] = s;
+    __shared__ float red[4];
+    __shared__ int new_slot[EE_MAX_BATCH];
+    __shared__ int wtot[2][4];
+    __shared__ float wsum[4];
+    __shared__ int is_last;
+    const int n = ee_n[0];  // rewritten by the last CTA only after every CTA has passed the ticket below
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const int b = blockIdx.x;
+        if (b < n) {
+            const float bias = bias_p[0];
+            float s = 0.f;
+            for (int l = tid; l < L; l += 128) s += probe_token(pp, (size_t)b * L + l, np, bias);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) red[warp] = s;
+            __syncthreads();
+            if (tid == 0) sc_tmp[b] = (red[0] + red[1] + red[2] + red[3]) / (float)L;
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if ((int)threadIdx.x < n)
-        sc[threadIdx.x] = (part[threadIdx.x][0] + part[threadIdx.x][1] + part[threadIdx.x][2] + part[threadIdx.x][3]) /
-                          (float)L;
-    __syncthreads();
-    const int b = threadIdx.x;
-    const bool live = b < n;
-    const float myscore = live ? sc[b] : 0.f;
-    const int myslot = live ? slot[b] : 0;
-    // threshold < 0: argmax over an all-false mask selects layer 0 for every sample (see ee_select_kernel)
-    const int ex = (live && (myscore <= thr || (thr < 0.f && layer == 0))) ? 1 : 0;
-    const int kp = (live && !ex) ? 1 : 0;
-    // block-wide exclusive scans of ex / kp and the sum of the live scores
-    int ie = ex, ik = kp;
-    float fs = myscore;
+    if (!is_last) return;
+    __threadfence();
+    // ---- decision: thread i owns samples 8i .. 8i+7 (B <= 1024)
+    constexpr int PER = EE_MAX_BATCH / 128;
+    float sc[PER];
+    int ex[PER], myslot[PER];
+    int ce = 0, ck = 0;
+    float fs = 0.f;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int b = tid * PER + u;
+        const bool live = b < n;
+        sc[u] = live ? __ldcg(sc_tmp + b) : 0.f;
+        myslot[u] = live ? slot[b] : 0;
+        // threshold < 0: argmax over an all-false mask selects layer 0 for every sample (see ee_select_kernel)
+        ex[u] = (live && (sc[u] <= thr || (thr < 0.f && layer == 0))) ? 1 : 0;
+        ce += ex[u];
+        ck += (live && !ex[u]) ? 1 : 0;
+        fs += sc[u];
+    }
+    // block-wide exclusive scans of the per-thread counts, and the sum of the live scores
+    int ie = ce, ik = ck;
     for (int o = 1; o < 32; o <<= 1) {
         const int te = __shfl_up_sync(0xffffffffu, ie, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
         if (lane >= o) ie += te, ik += tk;
@@ -657,119 +685,98 @@ __global__ void __launch_bounds__(1024) ee_decide_kernel(
     if (lane == 31) wtot[0][warp] = ie, wtot[1][warp] = ik;
     if (lane == 0) wsum[warp] = fs;
     __syncthreads();
-    if (warp == 0) {
-        int ve = wtot[0][lane], vk = wtot[1][lane];
-        for (int o = 1; o < 32; o <<= 1) {
-            const int te = __shfl_up_sync(0xffffffffu, ve, o), tk = __shfl_up_sync(0xffffffffu, vk, o);
-            if (lane >= o) ve += te, vk += tk;
-        }
-        wtot[0][lane] = ve, wtot[1][lane] = vk;  // inclusive over warps
-        float t = wsum[lane];
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) wsum[0] = t;
-    }
-    __syncthreads();
-    const int base_e = warp ? wtot[0][warp - 1] : 0, base_k = warp ? wtot[1][warp - 1] : 0;
-    const int n_exit = wtot[0][31], n_keep = wtot[1][31];
+    int base_e = ie - ce, base_k = ik - ck;  // exclusive inside the warp
+    for (int w = 0; w < warp; ++w) base_e += wtot[0][w], base_k += wtot[1][w];
+    const int n_exit = wtot[0][0] + wtot[0][1] + wtot[0][2] + wtot[0][3];
+    const int n_keep = wtot[1][0] + wtot[1][1] + wtot[1][2] + wtot[1][3];
     const int t_now = t_dev ? *t_dev : 0;
-    if (live) {
-        scores[(size_t)layer * B + myslot] = myscore;
-        if (ex) {
-            const int j = base_e + ie - 1;
-            exit_src[j] = b;
-            exit_slot[j] = myslot;
-            exit_idx[myslot] = layer;
-            if (exit_log) exit_log[(size_t)t_now * B + myslot] = layer;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int b = tid * PER + u;
+        if (b >= n) break;
+        scores[(size_t)layer * B + myslot[u]] = sc[u];
+        if (ex[u]) {
+            const int j = base_e++;
+            dest[b] = -(j + 1);
+            exit_slot[j] = myslot[u];
+            exit_idx[myslot[u]] = layer;
+            if (exit_log) exit_log[(size_t)t_now * B + myslot[u]] = layer;
         } else {
-            const int j = base_k + ik - 1;
-            keep_src[j] = b;
-            new_slot[j] = myslot;
+            const int j = base_k++;
+            dest[b] = j;
+            new_slot[j] = myslot[u];
         }
     }
     __syncthreads();
-    if (b < n_keep) slot[b] = new_slot[b];
-    if (b == 0) {
-        ee_n[0] = n_keep, ee_n[1] = n_keep * L, ee_n[2] = n_exit, ee_n[3] = n_exit * L;
+    for (int b = tid; b < n_keep; b += 128) slot[b] = new_slot[b];
+    if (tid == 0) {
+        ee_n[0] = n_keep, ee_n[1] = n_keep * L, ee_n[2] = n_exit, ee_n[3] = n_exit * L, ee_n[4] = n;
         // eesampler.py:71 logs the batch mean of every probe; here: the mean over the samples still in the batch
         if (score_mean_log)
-            score_mean_log[(size_t)t_now * depth + layer] = n > 0 ? wsum[0] / (float)n : __int_as_float(0x7fc00000);
+            score_mean_log[(size_t)t_now * depth + layer] =
+                n > 0 ? (wsum[0] + wsum[1] + wsum[2] + wsum[3]) / (float)n : __int_as_float(0x7fc00000);
+        *ticket = 0u;
     }
 }
 
-// rows of the leaving samples -> scratch batch [n_exit*L, D] (+ their LayerNorm statistics); grid = (L, EE_GATHER_Y):
-// the two halves of a CTA and the CTAs along y take different leavers, a thread copies one 16-byte chunk of a row.
-constexpr int EE_GATHER_Y = 4;
-__global__ void __launch_bounds__(128) ee_gather_exit_kernel(const __nv_bfloat16* __restrict__ x,
-                                                             const float2* __restrict__ stats,
-                                                             const int* __restrict__ ee_n,
-                                                             const int* __restrict__ exit_src,
-                                                             __nv_bfloat16* __restrict__ xe,
-                                                             float2* __restrict__ stats_e, int L, int D) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int n_exit = ee_n[2];
-    if (n_exit == 0) return;  // nobody leaves at this layer
-    const int l = blockIdx.x;
-    const int chunks = D / 8;  // 16-byte chunks per row
-    const int half = threadIdx.x >> 6, t = threadIdx.x & 63;
-    for (int j = blockIdx.y * 2 + half; j < n_exit; j += 2 * EE_GATHER_Y) {
-        const size_t src = (size_t)exit_src[j] * L + l, dst = (size_t)j * L + l;
-        const uint4* sp = reinterpret_cast<const uint4*>(x + src * D);
-        uint4* dp = reinterpret_cast<uint4*>(xe + dst * D);
-        for (int c = t; c < chunks; c += 64) dp[c] = sp[c];
-        if (t == 0) stats_e[dst] = stats[src];
-    }
-}
-
-// In-place compaction of the kept samples of up to EE_MAX_LIVE activation buffers (+ the row statistics, blockIdx.y ==
-// nbuf).  Live buffers before block i = the block input + every pending long skip: at most depth/2 + 1 (11 for the
-// depth-21 deediff_imagenet256.yaml).
-// grid = (L, nbuf + 1).  A thread owns one 16-byte column chunk of token l and walks the kept samples in increasing
-// order: keep_src[j] >= j and is increasing, so a row is always read before it can be overwritten, and the loads of
-// the next samples never alias earlier stores (dst_j <= src_j < src_{j+1}).
+// One kernel moves the rows after a decision: in every live activation buffer (the block input bufs.p[0] and the
+// pending long skips) the stayers are compacted IN PLACE, and the leavers' rows of the block input go to the scratch
+// batch xe for their exit head; blockIdx.y == nbuf does the same for the rows' LayerNorm statistics (np float2 each).
+// grid = (L, nbuf + 1).  A thread owns one 16-byte column chunk of token l and walks the previously live samples in
+// increasing order: a stayer's destination index is <= its source index, so every row is read before it can be
+// overwritten -- also inside a batch of four (all four loads precede the four stores, which only target rows <= b+3).
 constexpr int EE_MAX_LIVE = 16;
 struct EeBufList {
     __nv_bfloat16* p[EE_MAX_LIVE];
 };
-__global__ void __launch_bounds__(128) ee_compact_kernel(EeBufList bufs, int nbuf, float2* __restrict__ stats,
-                                                         const int* __restrict__ ee_n,
-                                                         const int* __restrict__ keep_src, int L, int D) {
+template <typename T>
+__device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict__ scratch, int chunks,
+                                             const int* __restrict__ dest, int n_prev, int L, int l) {
+    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+        int b = 0;
+        for (; b + 4 <= n_prev; b += 4) {
+            T v[4];
+            int d[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                d[u] = dest[b + u];
+                v[u] = buf[((size_t)(b + u) * L + l) * chunks + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (d[u] >= 0) {
+                    if (d[u] != b + u) buf[((size_t)d[u] * L + l) * chunks + c] = v[u];
+                } else if (scratch) {
+                    scratch[((size_t)(-d[u] - 1) * L + l) * chunks + c] = v[u];
+                }
+            }
+        }
+        for (; b < n_prev; ++b) {
+            const int d = dest[b];
+            const T v = buf[((size_t)b * L + l) * chunks + c];
+            if (d >= 0) {
+                if (d != b) buf[((size_t)d * L + l) * chunks + c] = v;
+            } else if (scratch) {
+                scratch[((size_t)(-d - 1) * L + l) * chunks + c] = v;
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(128) ee_move_kernel(EeBufList bufs, int nbuf, __nv_bfloat16* __restrict__ xe,
+                                                      float2* __restrict__ stats, float2* __restrict__ stats_e,
+                                                      int np, const int* __restrict__ ee_n,
+                                                      const int* __restrict__ dest, int L, int D) {
     pdl_launch_dependents();
     pdl_wait();
     if (ee_n[2] == 0) return;  // nobody left at this layer
-    const int n_keep = ee_n[0];
+    const int n_prev = ee_n[4];
     const int l = blockIdx.x;
     if ((int)blockIdx.y == nbuf) {
-        if (threadIdx.x == 0)
-            for (int j = 0; j < n_keep; ++j) {
-                const int s = keep_src[j];
-                if (s != j) stats[(size_t)j * L + l] = stats[(size_t)s * L + l];
-            }
+        ee_move_rows<float2>(stats, stats_e, np, dest, n_prev, L, l);
         return;
     }
-    __nv_bfloat16* buf = bufs.p[blockIdx.y];
-    const int chunks = D / 8;
-    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-        int j = 0;
-        for (; j + 4 <= n_keep; j += 4) {
-            uint4 v[4];
-            int s[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                s[u] = keep_src[j + u];
-                v[u] = reinterpret_cast<const uint4*>(buf + ((size_t)s[u] * L + l) * D)[c];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (s[u] != j + u) reinterpret_cast<uint4*>(buf + ((size_t)(j + u) * L + l) * D)[c] = v[u];
-        }
-        for (; j < n_keep; ++j) {
-            const int s = keep_src[j];
-            if (s != j)
-                reinterpret_cast<uint4*>(buf + ((size_t)j * L + l) * D)[c] =
-                    reinterpret_cast<const uint4*>(buf + ((size_t)s * L + l) * D)[c];
-        }
-    }
+    ee_move_rows<uint4>(reinterpret_cast<uint4*>(bufs.p[blockIdx.y]),
+                        blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, dest, n_prev, L, l);
 }
 
 }  // namespace ddb

@@ -51,6 +51,10 @@ struct GemmArgs {
     int debug;          // bench-only knobs (ddb_set_option "gemm_debug"): 1 = epilogue drains TMEM but skips math/stores,
                         // 2 = MMA issue skipped (barrier traffic only), 4 = no TMA operand loads
     float2* stats_out;  // optional [M, N/64]: per-row (mean, M2) of every 64-column output chunk (gemm2 only)
+    // Early-exit probe folded into the producer (gemm2, PROBE instantiation): probe_out[row, N/64] = partial dot products
+    // of the output row (fp32, before the bf16 rounding) with probe_w over every 64-column chunk (models/early_exit.py:34-37)
+    const float* probe_w;  // [N]
+    float* probe_out;      // [M, N/64]
     long long* trace;   // bench-only: cluster 0 / leader records clock64() per tile ([tile][16])
     // Patch-embed mode (CTA-pair kernel): GEMM row r = (sample b = r / 256, patch l = r % 256).  The output goes to
     // token row b*tok_L + tok_extras + l through a 3-D tensor map (tmOut: [B][256][N] view of the token buffer), the

@@ -24,7 +24,7 @@
 
 namespace ddb {
 
-template <int STAGES_, int NBUF_, bool LN_, int BN_ = 256>
+template <int STAGES_, int NBUF_, bool LN_, int BN_ = 256, bool PROBE_ = false>
 struct Gemm2Cfg {
     static constexpr int BM = 128;  // rows per CTA (256 per pair)
     static constexpr int BN = BN_;  // 256, or 128 for the N = 512 GEMMs (wave quantisation: 258 -> 516 tiles on 74 pairs)
@@ -36,6 +36,7 @@ struct Gemm2Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BUF_BYTES = 128 * 128;
     static constexpr int AUX_BYTES = LN_ ? 3072 : 1024;  // per buffer: [rowstats 1 KB][bias 1 KB][colsum 1 KB]
+    static_assert(!PROBE_ || !LN_, "the probe epilogue is a residual epilogue");
     static constexpr int OFF_A = 0;
     static constexpr int OFF_B = OFF_A + STAGES * A_BYTES;
     static constexpr int OFF_OUT = OFF_B + STAGES * B_BYTES;
@@ -46,11 +47,12 @@ struct Gemm2Cfg {
     static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int EPI, bool STATS, int STAGES, int NBUF, int BN_ = 256>
+template <int EPI, bool STATS, int STAGES, int NBUF, int BN_ = 256, bool PROBE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     gemm2_tcgen05_kernel(const __grid_constant__ GemmArgs a) {
     constexpr bool kLN = (EPI == EPI_LN || EPI == EPI_LN_GELU);
-    using Cfg = Gemm2Cfg<STAGES, NBUF, kLN, BN_>;
+    static_assert(!PROBE || (STATS && !kLN && BN_ == 256), "the probe rides on the statistics epilogue");
+    using Cfg = Gemm2Cfg<STAGES, NBUF, kLN, BN_, PROBE>;
     constexpr int BN = Cfg::BN;
     static_assert(BN == 256 || BN == 128, "tile width");
 
@@ -256,6 +258,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             const uint8_t* ab = sAux + as * Cfg::AUX_BYTES;
             const float* sbias = reinterpret_cast<const float*>(ab + (kLN ? 1024 : 0));
             const float* scs = reinterpret_cast<const float*>(ab + 2048);
+            // PROBE: the 5-stage residual configuration has no shared memory left for a third per-tile vector; the probe
+            // weights come through L1 (every thread of the CTA reads the same 32 bytes: one broadcast line per request)
+            const float* spw = PROBE ? a.probe_w + n_blk * BN : nullptr;
 
             long long* tr = (a.trace && cluster_id == 0 && leader && threadIdx.x == 0 && it < 16) ? a.trace + it * 16
                                                                                                    : nullptr;
@@ -322,6 +327,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                     nc0 = *reinterpret_cast<const float4*>(scs + c * 64);
                     nc1 = *reinterpret_cast<const float4*>(scs + c * 64 + 4);
                 }
+                if constexpr (PROBE) {  // the probe weights travel in the (unused) colsum registers
+                    nc0 = __ldg(reinterpret_cast<const float4*>(spw + c * 64));
+                    nc1 = __ldg(reinterpret_cast<const float4*>(spw + c * 64 + 4));
+                }
+                f32x2 pdot = f2_splat(0.f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int cl = c * 64 + j * 8;  // column inside the tile
@@ -336,6 +346,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                         if constexpr (kLN) {
                             nc0 = *reinterpret_cast<const float4*>(scs + cl + 8);
                             nc1 = *reinterpret_cast<const float4*>(scs + cl + 12);
+                        }
+                        if constexpr (PROBE) {
+                            nc0 = __ldg(reinterpret_cast<const float4*>(spw + cl + 8));
+                            nc1 = __ldg(reinterpret_cast<const float4*>(spw + cl + 12));
                         }
                     }
                     const f32x2 bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y),
@@ -363,6 +377,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                         v[1] = f2_add(v[1], f2_pack_u(r.y << 16, r.y & 0xFFFF0000u));
                         v[2] = f2_add(v[2], f2_pack_u(r.z << 16, r.z & 0xFFFF0000u));
                         v[3] = f2_add(v[3], f2_pack_u(r.w << 16, r.w & 0xFFFF0000u));
+                    }
+                    if constexpr (PROBE) {
+                        pdot = f2_fma(v[0], f2_pack(c0.x, c0.y), pdot);
+                        pdot = f2_fma(v[1], f2_pack(c0.z, c0.w), pdot);
+                        pdot = f2_fma(v[2], f2_pack(c1.x, c1.y), pdot);
+                        pdot = f2_fma(v[3], f2_pack(c1.z, c1.w), pdot);
                     }
                     if constexpr (STATS) {
                         // shifted single-pass statistics: s1 = sum(v - v0), s2 = sum((v - v0)^2); lanes = even/odd cols
@@ -398,6 +418,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                                                 ? (size_t)m_blk * a.tok_L + a.tok_extras + (int)rank * 128 + row_in_tile
                                                 : (size_t)row;
                         a.stats_out[orow * (a.N >> 6) + (col0 >> 6)] = make_float2(dm - ns, fmaf(-t1, dm, t2));
+                        if constexpr (PROBE) {
+                            float pa, pb;
+                            f2_unpack(pdot, pa, pb);
+                            a.probe_out[orow * (a.N >> 6) + (col0 >> 6)] = pa + pb;
+                        }
                     }
                 }
                 if (cc == CHUNKS_PER_WG - 1) {
