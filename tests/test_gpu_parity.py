@@ -12,8 +12,13 @@ B200 -- measured values in brackets, from gpurun_out/pytest_gpu*.log of round 1)
                                                             [5.9e-3 after 1000 steps, 13-block model]
   * DDPM update alone (fp32)                               : bit-exact vs the reference expression order
   * early-exit indices: equal except where |probe - threshold| < margin; margin = 2e-3 for reference-init probes
-    (per-token logits ~1e-2) and 1.5e-2 for "hot" probes (per-token logits of several units, where a 1e-2 relative
-    error of the bf16 hidden state moves sigmoid() by up to ~7e-3) [max probe deviation 7.0e-3]
+    (per-token logits ~1e-2) [max probe deviation 2.0e-4] and 1.5e-2 for "hot" probes: the score is mean_l
+    sigmoid(z_l), so its error is <= 0.25 * mean|dz|, and dz = w . dx scales with the logit itself -- heat_() gives
+    per-token logits of several units and the bf16 path carries a ~1e-2 relative error in x (eps rel-L2 1.0e-2..1.7e-2
+    above), i.e. |dz| ~ 3e-2..6e-2 [measured max deviation over all layers and samples, round 2: 8.4e-3 (B = 6),
+    8.8e-3 (B = 9), 2.4e-3 / 3.3e-3 (ImageNet-64 depth 3 / 17), 1.24e-2 (ImageNet-256 depth 21)].  The index logs are
+    checked TEACHER-FORCED on the oracle's own x_t (test_ee_sampler_logs_teacher_forced), so every mismatch must be
+    explained by the margin: 0 mismatches in 160 decisions.
 """
 import numpy as np
 import pytest
@@ -384,12 +389,12 @@ def test_ee_compaction_equals_simulation(dev, name, B, scale):
     depth = CONFIGS[name]["depth"]
     _spread_probes(net, depth)
     if B >= 64:
-        # 128 samples x 13 layers: the maximum of 1 664 probe deviations at x4 probe weights (per-token logits of ~10)
-        # was 1.64e-2 in round 2 -- beyond the 1.5e-2 margin the small-batch cases need.  x2 probes keep the per-sample
-        # spread of the exits and halve the sensitivity of sigmoid(w.x) to the bf16 error of x.
+        # 128 samples x 13 layers: the maximum of 1 664 probe deviations was 1.64e-2 at x4 probe weights (per-token
+        # logits of ~10) and 1.29e-2 at x2 -- the deviation is 0.25 * |d logit|, and |d logit| scales with the logit.
+        # x1.33 probes keep a per-sample spread of the exits with the deviation well inside the margin.
         with torch.no_grad():
             for i in range(depth):
-                net.matrix[f"{i}"].classifier[0].weight.mul_(0.5)
+                net.matrix[f"{i}"].classifier[0].weight.mul_(1.0 / 3.0)
     net = net.eval().to(dev)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     spec = O.UViTSpec.from_params(CONFIGS[name])
