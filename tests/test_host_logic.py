@@ -283,3 +283,33 @@ def test_engine_rejects_threshold_free_early_exit_flag_confusion():
     import inspect
     src = inspect.getsource(ddpm.Sampler.__init__)
     assert "-1 if ee_threshold is None" in src
+
+
+def test_fid_shim_reads_cli_outputs_and_frechet_closed_form(tmp_path):
+    """fid.py keeps the reference's command line (fid.py:8-31) and sample reader (utils/evaluation_utils.py:13-24); the
+    metric itself needs torchmetrics + pretrained InceptionV3 (not bundled) and must say so."""
+    import importlib.util
+    from duodiff_b200 import _io
+    spec = importlib.util.spec_from_file_location("_shim_fid", ROOT / "fid.py")
+    fid = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fid)
+    rng = np.random.default_rng(0)
+    samples = rng.random((5, 8, 8, 3)).astype(np.float32)
+    _io.dump_samples(samples, tmp_path)  # what sampler.py writes: 0.png .. 4.png + grid_image.png
+    got = fid.read_samples(tmp_path)
+    assert got.shape == (5, 3, 8, 8) and got.dtype == torch.float32  # the grid image is skipped
+    want = torch.from_numpy((samples * 255).astype(np.uint8).astype(np.float32) / 255).permute(0, 3, 1, 2)
+    assert torch.equal(got, want)
+    args = fid.get_args(["--dataset", "celeba", "--samples_path", str(tmp_path)])
+    assert args.seed == 0 and args.data_path == "data"
+    # Frechet distance: identical Gaussians -> 0; diagonal case has the closed form sum (sqrt(a) - sqrt(b))^2 + |dmu|^2
+    a, b = rng.random(6) + 0.5, rng.random(6) + 0.5
+    mu = rng.random(6)
+    assert abs(fid.frechet_distance(mu, np.diag(a), mu, np.diag(a))) < 1e-9
+    want = ((np.sqrt(a) - np.sqrt(b)) ** 2).sum() + 0.25 * 6
+    assert abs(fid.frechet_distance(mu, np.diag(a), mu + 0.5, np.diag(b)) - want) < 1e-9
+    try:
+        import torchmetrics  # noqa: F401
+    except ImportError:
+        with pytest.raises(RuntimeError, match="torchmetrics"):
+            fid.fid_evaluation(got, got)
