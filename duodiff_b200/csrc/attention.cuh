@@ -246,6 +246,76 @@ __device__ __forceinline__ void att_extras_slice32(uint32_t sK_u, uint32_t sV_u,
     for (int i = 0; i < 8; ++i) o[i][0] = oacc[i][0], o[i][1] = oacc[i][1];
 }
 
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+    return d;
+}
+// The same slice with the KEYS as the M dimension of the mma (legacy HMMA costs ~27 clk per instruction and scheduler on
+// sm_100, so the count matters): S^T[32 keys x 8 queries] = K_slice Qx^T (2 m-tiles x 4 k-steps = 8 HMMA instead of 16),
+// softmax down the key axis (reductions across the lanes that share t), O^T[64 dims x 8 queries] = V^T P^T (4 m-tiles x
+// 2 k-steps = 8 HMMA instead of 16); P^T reaches its B-fragment layout through movmatrix.  Queries = tokens 0..7 of the
+// sample, of which [0, extras) are real; the columns of the padding queries are computed and ignored.
+// Lane (g, t) returns for queries 2t (index 0) and 2t+1 (index 1): row max, row sum, and o[dm][2h + q] =
+// O^T[dim 16 dm + 8 h + g][query 2t + q].  Only the t == 0 lanes hold the extras queries.
+__device__ __forceinline__ void att_extras_slice32_t(uint32_t sK_u, uint32_t sV_u, uint32_t sQx_u, int kb0,
+                                                     float scale_log2e, int lane, float (&m_out)[2], float (&l_out)[2],
+                                                     float (&o)[4][4]) {
+    uint32_t bq[4][2];  // B fragments of Qx^T: k-step ks -> (dims 16ks..+7, +8..+15) x queries 0..7
+    ldmatrix_x4(sQx_u + att_swz(lane & 7, lane >> 3), bq[0][0], bq[0][1], bq[1][0], bq[1][1]);
+    ldmatrix_x4(sQx_u + att_swz(lane & 7, (lane >> 3) + 4), bq[2][0], bq[2][1], bq[3][0], bq[3][1]);
+    float s[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        s[mt][0] = s[mt][1] = s[mt][2] = s[mt][3] = 0.f;
+        const int row = kb0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t af[4];
+            ldmatrix_x4(sK_u + att_swz(row, ks * 2 + (lane >> 4)), af[0], af[1], af[2], af[3]);
+            mma_bf16_16816(s[mt], af, bq[ks][0], bq[ks][1]);
+        }
+    }
+    // s[mt] = {(key g, q 2t), (key g, q 2t+1), (key g+8, q 2t), (key g+8, q 2t+1)} of key tile mt
+    float ma = fmaxf(fmaxf(s[0][0], s[0][2]), fmaxf(s[1][0], s[1][2]));
+    float mb = fmaxf(fmaxf(s[0][1], s[0][3]), fmaxf(s[1][1], s[1][3]));
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, sh));
+        mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, sh));
+    }
+    const float msa = ma * scale_log2e, msb = mb * scale_log2e;
+    float la = 0.f, lb = 0.f;
+    uint32_t pb[2][2];  // B fragments of P^T per key tile: keys 0-7 / 8-15
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const float p0 = ex2_approx(fmaf(s[mt][0], scale_log2e, -msa)), p1 = ex2_approx(fmaf(s[mt][1], scale_log2e, -msb));
+        const float p2 = ex2_approx(fmaf(s[mt][2], scale_log2e, -msa)), p3 = ex2_approx(fmaf(s[mt][3], scale_log2e, -msb));
+        la += p0 + p2;
+        lb += p1 + p3;
+        pb[mt][0] = movmatrix_trans(pack_bf16(p0, p1));
+        pb[mt][1] = movmatrix_trans(pack_bf16(p2, p3));
+    }
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+        la += __shfl_xor_sync(0xffffffffu, la, sh);
+        lb += __shfl_xor_sync(0xffffffffu, lb, sh);
+    }
+#pragma unroll
+    for (int dm = 0; dm < 4; ++dm) o[dm][0] = o[dm][1] = o[dm][2] = o[dm][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int key = kb0 + kk * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+#pragma unroll
+        for (int dm = 0; dm < 4; ++dm) {
+            uint32_t av[4];  // V^T fragments: (dims 0-7 | 8-15) x (keys 0-7 | 8-15) of dim tile dm
+            ldmatrix_x4_trans(sV_u + att_swz(key, dm * 2 + ((lane >> 3) & 1)), av[0], av[1], av[2], av[3]);
+            mma_bf16_16816(o[dm], av, pb[kk][0], pb[kk][1]);
+        }
+    }
+    m_out[0] = ma, m_out[1] = mb, l_out[0] = la, l_out[1] = lb;
+}
+
 struct AttnArgs {
     CUtensorMap tmQKV;    // [B, L, 3D] bf16, box {64, 128, 1}
     CUtensorMap tmKV;     // [B, L, 3D] bf16, box {64, 256, 1}
@@ -552,9 +622,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         const float c = a.scale_log2e;
         const int q0 = a.extras + t * 128;
 
-        // Per-item side work of a softmax warp on mma.sync, done for item it+1 while the tensor core finishes O of item it
-        // (measured alternatives, profiles/r02_attention_experiments.txt: after the epilogue -- the K / V slots are then
-        // released too late and the refill latency is exposed -- and at the start of the item under its S MMA: both slower):
+        // Per-item side work of a softmax warp on mma.sync (placements measured in profiles/r02_attention_experiments.txt):
         //  extras_scores(it)  scores of this warp's 32 query rows against the extras KEYS (tokens [0, extras)):
         //                     S = Q_rows Kx^T, 8 HMMA;
         //  extras_slice(it)   the extras QUERY rows' partial attention over this warp's own 32 patch keys (one softmax
@@ -600,24 +668,24 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             const uint32_t sph = (it >> 1) & 1;
             const uint8_t* st = smem + s * ATT3_STAGE;
             const int g = lane >> 2, tt = lane & 3;
-            uint32_t qf[4][4];
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                qf[ks][0] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2) + 4 * tt);
-                qf[ks][2] = *reinterpret_cast<const uint32_t*>(st + ATT3_OFF_QX + att_swz(g, ks * 2 + 1) + 4 * tt);
-                qf[ks][1] = qf[ks][3] = 0u;
-            }
             wait(&v_full[s], sph);
-            float m0, l0, o[8][2];
-            att_extras_slice32(smem_u32(st + ATT3_OFF_K), smem_u32(st + ATT3_OFF_V), w8 * 32, qf, a.scale_log2e, lane,
-                               m0, l0, o);
+            float mq[2], lq[2], o[4][4];
+            att_extras_slice32_t(smem_u32(st + ATT3_OFF_K), smem_u32(st + ATT3_OFF_V), smem_u32(st + ATT3_OFF_QX), w8 * 32,
+                                 a.scale_log2e, lane, mq, lq, o);
             wait(&px_empty[s], sph ^ 1);  // the extras warp has merged the record of item it-2
-            if (g < 2) {
-                float* rec = px_buf + ((size_t)s * 8 + w8) * ATT3_PX_REC + g * ATT3_PX_ROW;
+            if (tt == 0) {  // these lanes hold queries 0 and 1 = the extras rows: dims 16 dm + 8 h + g
+                float* rec = px_buf + ((size_t)s * 8 + w8) * ATT3_PX_REC;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    *reinterpret_cast<float2*>(rec + i * 8 + 2 * tt) = make_float2(o[i][0], o[i][1]);
-                if (tt == 0) rec[64] = m0, rec[65] = l0;
+                for (int dm = 0; dm < 4; ++dm)
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        rec[dm * 16 + h2 * 8 + g] = o[dm][2 * h2];
+                        rec[ATT3_PX_ROW + dm * 16 + h2 * 8 + g] = o[dm][2 * h2 + 1];
+                    }
+                if (g == 0) {
+                    rec[64] = mq[0], rec[65] = lq[0];
+                    rec[ATT3_PX_ROW + 64] = mq[1], rec[ATT3_PX_ROW + 65] = lq[1];
+                }
             }
             __syncwarp();
             if (lane == 0) {  // this warp has read K / Kx / Qx / V of the item; its record is written
@@ -628,10 +696,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
         };
 
         float se0 = 0.f, se1 = 0.f;
-        if (my_items > 0) {
-            extras_scores(0, se0, se1);
-            extras_slice(0);
-        }
         for (int it = 0; it < my_items; ++it) {
             const int item = item_of(it);
             const int b = item / a.H, h = item % a.H;
@@ -641,6 +705,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
 
             long long* tr = (a.trace && blockIdx.x == 0 && r == 0) ? a.trace + (it * 2 + t) * 16 : nullptr;
             if (tr) tr[0] = clock64();
+            extras_scores(it, se0, se1);  // under the item's S MMA
             wait(&s_full[t], ph);
             tc_fence_after();
             if (tr) tr[1] = clock64();
@@ -736,11 +801,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             f2_unpack(sum2, sa, sb);
             f2_unpack(sum2b, sc, sd);
             const float inv = 1.f / ((sa + sb) + (sc + sd));
-            // while the tensor core finishes O: the next item's side work (its operands were requested an item ago)
-            if (it + 1 < my_items) {
-                extras_scores(it + 1, se0, se1);
-                extras_slice(it + 1);
-            }
+            // while the tensor core finishes O: the extras rows' slice of THIS item (K and V are in shared memory: no wait
+            // on a refill; the V slot of the next item is only requested when the OTHER tile's PV has retired, ~4 000 clk
+            // before it lands -- working on item it+1 here stalled for ~2 000 clk per item)
+            extras_slice(it);
             if (tr) tr[5] = clock64();
 
             // ---- epilogue: O row (fp32) out of TMEM, then release the tile's columns for S_t of the next item
