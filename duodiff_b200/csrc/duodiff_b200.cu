@@ -251,7 +251,7 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BN>::SMEM_BYTES));
         configured.mark();
     }
-    const int tiles = ((a.M + 127) / 128) * (a.N / BN);
+    const int tiles = a.grp_layer ? a.grp_B * ((a.L + 127) / 128) : ((a.M + 127) / 128) * (a.N / BN);
     const int grid = tiles < num_sms ? tiles : num_sms;
     if (grid <= 0) return DDB_OK;
     CUDA_TRY(launch_pdl(kfn, dim3(grid), dim3(384), GemmCfg<BN>::SMEM_BYTES, st, a));
@@ -530,7 +530,8 @@ struct ddb_model {
     Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_p, scores, outputs, exit_idx;
     // early-exit compaction (mode 1): device-side live counts, slot maps, gather lists, scratch batch of leavers
     Buf ee_n, ee_slot, ee_dest, ee_exit_slot, ee_sc, ee_ticket, xe, stats_e;
-    std::vector<GemmArgs> head_dec_x;       // head i on the scratch batch
+    GemmArgs head_grp;                      // all leavers in one launch, head selected per sample (grouped decode)
+    Buf hg_w, hg_bias, hg_colsum, hg_conv_w, hg_conv_b;  // the depth exit heads stacked for it
     std::vector<EeBufList> ee_live;         // buffers that must be compacted when samples leave before block i
     std::vector<int> ee_live_n;
     std::vector<Buf> xo;
@@ -841,14 +842,39 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
         }
         // compaction mode: head i on the scratch batch of leavers; list of live buffers per layer = the block input
         // plus every long skip that is still pending (models/uvit.py:367-375)
-        m->head_dec_x.resize(cfg->depth);
         m->ee_live.resize(cfg->depth);
         m->ee_live_n.resize(cfg->depth);
+        {
+            // the exit heads stacked: decoder weights [depth][64][D] bf16 (LayerNorm folded), bias / colsum [depth][64],
+            // conv weights [depth][C*C*9], conv bias [depth][C]
+            const int dpt = cfg->depth;
+            const size_t wb = (size_t)64 * D * 2, cw = (size_t)C * C * 9 * 4;
+            DDB_TRY(new_buf(m->hg_w, wb * dpt));
+            DDB_TRY(new_buf(m->hg_bias, (size_t)dpt * 64 * 4));
+            DDB_TRY(new_buf(m->hg_colsum, (size_t)dpt * 64 * 4));
+            DDB_TRY(new_buf(m->hg_conv_w, cw * dpt));
+            DDB_TRY(new_buf(m->hg_conv_b, (size_t)dpt * C * 4));
+            for (int i = 0; i < dpt; ++i) {
+                const HeadW& hw = m->ee_heads[i];
+                CUDA_TRY(cudaMemcpy(m->hg_w->as<char>() + wb * i, hw.dec.w->p, wb, cudaMemcpyDeviceToDevice));
+                CUDA_TRY(cudaMemcpy(m->hg_bias->as<float>() + 64 * i, hw.dec.bias->p, 64 * 4, cudaMemcpyDeviceToDevice));
+                CUDA_TRY(cudaMemcpy(m->hg_colsum->as<float>() + 64 * i, hw.dec.colsum->p, 64 * 4, cudaMemcpyDeviceToDevice));
+                CUDA_TRY(cudaMemcpy(m->hg_conv_w->as<char>() + cw * i, hw.conv_w->p, cw, cudaMemcpyDeviceToDevice));
+                CUDA_TRY(cudaMemcpy(m->hg_conv_b->as<float>() + C * i, hw.conv_b->p, C * 4, cudaMemcpyDeviceToDevice));
+            }
+            GemmArgs& g = m->head_grp;
+            memset(&g, 0, sizeof(g));
+            g.M = m->Mmax, g.N = 64, g.K0 = D, g.K1 = 0;
+            g.bias = m->hg_bias->as<float>(), g.colsum = m->hg_colsum->as<float>();
+            g.stats = m->stats_e->as<float2>();
+            g.nparts = D / 64, g.ln_dim = D, g.ln_eps = cfg->ln_eps;
+            DDB_TRY(make_tmap_bf16_3d(&g.tmA0, m->xe->p, D, m->L, cfg->max_batch, (uint64_t)D * 2,
+                                      (uint64_t)m->L * D * 2, 128));
+            DDB_TRY(make_tmap_bf16_3d(&g.tmB, m->hg_w->p, D, 64, dpt, (uint64_t)D * 2, (uint64_t)64 * D * 2, 64));
+            plan_decode_geometry(g, m, m->img_pre->as<float>());
+            g.grp_depth = dpt;
+        }
         for (int i = 0; i < cfg->depth; ++i) {
-            DDB_TRY(plan_gemm(m->head_dec_x[i], m, m->xe->p, D, nullptr, 0, m->ee_heads[i].dec, 64, nullptr, nullptr,
-                              m->stats_e->as<float2>()));
-            plan_decode_geometry(m->head_dec_x[i], m, m->img_pre->as<float>());
-            m->head_dec_x[i].m_dev = m->ee_n->as<int>() + 3;
             const int last_skip = (i <= half) ? std::min(i, half) - 1 : half - 1 - (i - half - 1);
             EeBufList& bl = m->ee_live[i];
             memset(&bl, 0, sizeof(bl));
@@ -869,16 +895,18 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
 }
 
 static int run_conv(const ddb_model* m, const HeadW& hw, const float* in, float* out, int B, cudaStream_t st,
-                    const int* n_dev = nullptr, const int* slot_map = nullptr) {
+                    const int* n_dev = nullptr, const int* slot_map = nullptr, const int* layer_idx = nullptr) {
     const int C = m->cfg.in_chans, H = m->cfg.img_size, W = m->cfg.img_size;
     const size_t smem = (size_t)C * (CONV_BAND + 2) * (W + 8) * 4;
     const dim3 grid(B * (H / CONV_BAND));
-    const float* w = hw.conv_w->as<float>();
-    const float* bs = hw.conv_b->as<float>();
+    // layer_idx: grouped mode -- image b takes the stacked exit head layer_idx[b] (hw is ignored)
+    const float* w = layer_idx ? m->hg_conv_w->as<float>() : hw.conv_w->as<float>();
+    const float* bs = layer_idx ? m->hg_conv_b->as<float>() : hw.conv_b->as<float>();
+    const int depth = m->cfg.depth;
     ProfScope ps(PC_CONV);
     switch (C) {
-        case 3: CUDA_TRY(launch_pdl(conv3x3_kernel<3>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map)); break;
-        case 4: CUDA_TRY(launch_pdl(conv3x3_kernel<4>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map)); break;
+        case 3: CUDA_TRY(launch_pdl(conv3x3_kernel<3>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map, layer_idx, depth)); break;
+        case 4: CUDA_TRY(launch_pdl(conv3x3_kernel<4>, grid, dim3(256), smem, st, in, w, bs, out, H, W, n_dev, slot_map, layer_idx, depth)); break;
         default: return fail(DDB_ERR_INVALID, "in_chans %d unsupported by the final 3x3 conv (3 or 4)", C);
     }
     LAUNCH_CHECK();
@@ -1020,7 +1048,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         ProfScope ps(cat);
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
-    if (!ee) kind = (pair && m->Np == 256) ? 2 : 1;  // statistics of x0 were written by the token assembly
+    kind = (pair && m->Np == 256) ? 2 : (ee ? 0 : 1);  // statistics of x0 were written by the token assembly
     if (cp) {
         ProfScope ps(PC_EE_OTHER);
         const int n = std::max(B, c.depth * B);
@@ -1055,6 +1083,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     }
     const __nv_bfloat16* cur = m->x0->as<__nv_bfloat16>();
     bool probe_ready = false;  // early exit: the probe partials of the current block input are already in probe_p
+    int np_exit = 1;           // compaction: format of the leavers' statistics in the scratch batch
     for (int i = 0; i < c.depth; ++i) {
         const BlockOps& op = m->ops[i];
         const BlockW& bw = m->blocks[i];
@@ -1065,7 +1094,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             if (!probe_ready) {
                 DDB_TRY(launch_ln_stats(cur, M, D, cp ? een + 1 : nullptr, st2, m->probe_w[i]->as<float>(),
                                         m->probe_p->as<float>(), st));
-                kind = 1;
+                if (kind != 2) kind = 1;  // the token assembly's partial statistics of x0 stay in force (CTA-pair path)
             }
             probe_ready = false;
         }
@@ -1082,21 +1111,15 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                                     cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
                                     m->ee_ticket->as<unsigned>()));
                 LAUNCH_CHECK();
-                // stayers compacted in place (block input, pending long skips, statistics), leavers -> scratch batch
+                // stayers compacted in place (block input, pending long skips, statistics); the leavers' rows and
+                // statistics go to the scratch batch at their ORIGINAL slot -- their heads run once, after the last block
                 CUDA_TRY(launch_pdl(ee_move_kernel, dim3(m->L, m->ee_live_n[i] + 1), dim3(128), 0, st, m->ee_live[i],
                                     m->ee_live_n[i], m->xe->as<__nv_bfloat16>(), st_cur, m->stats_e->as<float2>(), np_cur,
-                                    (const int*)een, (const int*)m->ee_dest->as<int>(), m->L, D));
+                                    (const int*)een, (const int*)m->ee_dest->as<int>(),
+                                    (const int*)m->ee_exit_slot->as<int>(), m->L, D));
                 LAUNCH_CHECK();
             }
-            {
-                GemmArgs g = m->head_dec_x[i];
-                g.M = M;
-                g.nparts = np_cur;
-                ProfScope ps(PC_GEMM_DECODE);
-                DDB_TRY(launch_gemm(g, EPI_DECODE, nsm, st));
-            }
-            DDB_TRY(run_conv(m, m->ee_heads[i], m->img_pre->as<float>(), eps, B, st, een + 2,
-                             m->ee_exit_slot->as<int>()));
+            np_exit = np_cur;
         } else if (ee) {
             {
                 ProfScope ps(PC_EE_OTHER);
@@ -1173,9 +1196,19 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     }
     DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
     if (fuse) return launch_step_tail(m, fuse->tail, B, st);
-    if (cp)  // the samples that never left: full-model output, written to their original slots
+    if (cp) {
+        // the samples that never left: full-model output, written to their original slots ...
         DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st, een, m->ee_slot->as<int>()));
-    else
+        // ... and every sample that left, at whatever layer: ONE grouped decode (the head of sample b's exit layer is
+        // selected through the stacked weight map) + one conv with per-sample weights
+        GemmArgs g = m->head_grp;
+        g.grp_layer = cp->exit_idx, g.grp_B = B, g.nparts = np_exit;
+        {
+            ProfScope ps(PC_GEMM_DECODE);
+            DDB_TRY(launch_gemm(g, EPI_DECODE, nsm, st));
+        }
+        return run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st, nullptr, nullptr, cp->exit_idx);
+    } else
         DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st));
     return DDB_OK;
 }

@@ -230,7 +230,9 @@ constexpr int CONV_BAND = 16;
 // with 128-bit loads, then every thread produces 4 horizontally adjacent pixels of every output channel from
 // registers (a 3 x 6 window per input channel) and stores them as one float4 per channel.  Requires W % 4 == 0.
 // n_dev / slot_map (early-exit compaction): only the first *n_dev input images are live and image b is written to
-// output slot slot_map[b].
+// output slot slot_map[b].  layer_idx (grouped mode, the leavers' heads in one launch): image b uses the weights of
+// head layer_idx[b] from the stacked arrays wgt [depth][C*C*9] / bias [depth][C]; images with layer_idx[b] >= depth are
+// skipped.
 template <int C>
 __device__ __forceinline__ void conv_stage_band(float* __restrict__ conv_smem, const float* __restrict__ in, int b,
                                                 int y0, int H, int W) {
@@ -299,15 +301,24 @@ template <int C>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
                                                       int W, const int* __restrict__ n_dev,
-                                                      const int* __restrict__ slot_map) {
+                                                      const int* __restrict__ slot_map,
+                                                      const int* __restrict__ layer_idx, int depth) {
     extern __shared__ __align__(16) float conv_smem[];  // [C][CONV_BAND+2][W+8] (4 pad floats left and right)
     __shared__ float sw[C * C * 9 + C];
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x) sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
+    if (!layer_idx)
+        for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
+            sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
     pdl_wait();
     if (n_dev && b >= *n_dev) return;
+    if (layer_idx) {
+        const int layer = layer_idx[b];
+        if (layer >= depth) return;
+        for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
+            sw[i] = (i < C * C * 9) ? wgt[(size_t)layer * C * C * 9 + i] : bias[layer * C + i - C * C * 9];
+    }
     const int ob = slot_map ? slot_map[b] : b;
     const int w4 = W / 4;
     conv_stage_band<C>(conv_smem, in, b, y0, H, W);
@@ -729,9 +740,12 @@ constexpr int EE_MAX_LIVE = 16;
 struct EeBufList {
     __nv_bfloat16* p[EE_MAX_LIVE];
 };
+// (the scratch batch is indexed by the sample's ORIGINAL slot, exit_slot[-dest - 1]: the leavers of all layers collect
+// there and one grouped decode serves them at the end of the forward)
 template <typename T>
 __device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict__ scratch, int chunks,
-                                             const int* __restrict__ dest, int n_prev, int L, int l) {
+                                             const int* __restrict__ dest, const int* __restrict__ exit_slot, int n_prev,
+                                             int L, int l) {
     for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
         int b = 0;
         for (; b + 4 <= n_prev; b += 4) {
@@ -747,7 +761,7 @@ __device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict_
                 if (d[u] >= 0) {
                     if (d[u] != b + u) buf[((size_t)d[u] * L + l) * chunks + c] = v[u];
                 } else if (scratch) {
-                    scratch[((size_t)(-d[u] - 1) * L + l) * chunks + c] = v[u];
+                    scratch[((size_t)exit_slot[-d[u] - 1] * L + l) * chunks + c] = v[u];
                 }
             }
         }
@@ -757,7 +771,7 @@ __device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict_
             if (d >= 0) {
                 if (d != b) buf[((size_t)d * L + l) * chunks + c] = v;
             } else if (scratch) {
-                scratch[((size_t)(-d - 1) * L + l) * chunks + c] = v;
+                scratch[((size_t)exit_slot[-d - 1] * L + l) * chunks + c] = v;
             }
         }
     }
@@ -765,18 +779,19 @@ __device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict_
 __global__ void __launch_bounds__(128) ee_move_kernel(EeBufList bufs, int nbuf, __nv_bfloat16* __restrict__ xe,
                                                       float2* __restrict__ stats, float2* __restrict__ stats_e,
                                                       int np, const int* __restrict__ ee_n,
-                                                      const int* __restrict__ dest, int L, int D) {
+                                                      const int* __restrict__ dest,
+                                                      const int* __restrict__ exit_slot, int L, int D) {
     pdl_launch_dependents();
     pdl_wait();
     if (ee_n[2] == 0) return;  // nobody left at this layer
     const int n_prev = ee_n[4];
     const int l = blockIdx.x;
     if ((int)blockIdx.y == nbuf) {
-        ee_move_rows<float2>(stats, stats_e, np, dest, n_prev, L, l);
+        ee_move_rows<float2>(stats, stats_e, np, dest, exit_slot, n_prev, L, l);
         return;
     }
     ee_move_rows<uint4>(reinterpret_cast<uint4*>(bufs.p[blockIdx.y]),
-                        blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, dest, n_prev, L, l);
+                        blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, dest, exit_slot, n_prev, L, l);
 }
 
 }  // namespace ddb

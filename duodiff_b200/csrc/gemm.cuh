@@ -70,6 +70,14 @@ struct GemmArgs {
     // EPI_DECODE scatter geometry
     float* img;  // [B, C, H, W] fp32
     int L, extras, C, P, Wp, H, W, patch_dim;
+    // EPI_DECODE, grouped mode (early-exit compaction): one launch decodes every sample that left the batch, each with
+    // the output head of ITS exit layer.  A = the leavers' hidden rows kept per original slot, tmA0 = 3-D map
+    // [D, L, B] (box {64, 128, 1}), tmB = 3-D map over the stacked head weights [D, 64, depth] (box {64, 64, 1}); tiles =
+    // (sample, 128-row block of its L tokens); grp_layer[b] = exit layer of sample b, samples with grp_layer[b] >=
+    // grp_depth are skipped (they never left: the full model's head handles them).  bias / colsum are stacked
+    // [depth][64]; stats is indexed by b * L + token.
+    const int* grp_layer;
+    int grp_depth, grp_B;
 };
 
 template <int BN>
@@ -112,7 +120,7 @@ __device__ __forceinline__ void ln_row_stats(const float2* __restrict__ stats, i
 struct GemmArgs;
 template <int C, int P>
 __device__ __forceinline__ void decode_store(const uint32_t (&acc)[2][32], const GemmArgs& a, float rstd,
-                                             float mean_rstd, int b, int hh, int ww, int g);
+                                             float mean_rstd, int b, int hh, int ww, int g, int voff);
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmArgs a) {
@@ -142,7 +150,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const int M = a.m_dev ? *a.m_dev : a.M;
     const int nblk_n = a.N / BN;
     const int nblk_m = (M + Cfg::BM - 1) / Cfg::BM;
-    const int num_tiles = nblk_m * nblk_n;
+    // grouped decode: tiles = (sample, 128-row block of its tokens)
+    const bool kGrouped = (EPI == EPI_DECODE) && a.grp_layer != nullptr;
+    const int grp_tps = (a.L + Cfg::BM - 1) / Cfg::BM;
+    const int num_tiles = kGrouped ? a.grp_B * grp_tps : nblk_m * nblk_n;
     const int nkb0 = a.K0 / Cfg::BK;
     const int nkb = nkb0 + a.K1 / Cfg::BK;
 
@@ -179,9 +190,25 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+                int grp_b = 0, grp_l = 0;
+                if (kGrouped) {
+                    grp_b = tile / grp_tps;
+                    grp_l = __ldg(a.grp_layer + grp_b);
+                    if (grp_l >= a.grp_depth) continue;  // every role skips the same tiles
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (kGrouped) {
+                        tma_load_3d(sA + stage * Cfg::A_BYTES, &a.tmA0, &full_bar[stage], kb * Cfg::BK,
+                                    (tile % grp_tps) * Cfg::BM, grp_b);
+                        tma_load_3d(sB + stage * Cfg::B_BYTES, &a.tmB, &full_bar[stage], kb * Cfg::BK, 0, grp_l);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        continue;
+                    }
                     if (kb < nkb0)
                         tma_load_2d(sA + stage * Cfg::A_BYTES, &a.tmA0, &full_bar[stage], kb * Cfg::BK,
                                     m_blk * Cfg::BM);
@@ -203,9 +230,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                if (kGrouped && __ldg(a.grp_layer + tile / grp_tps) >= a.grp_depth) continue;
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
+                ++it;
                 mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -250,13 +279,22 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
         }
 
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / nblk_n, n_blk = tile % nblk_n;
+            int grp_b = 0, grp_l = 0, grp_tok = 0;
+            if (kGrouped) {
+                grp_b = tile / grp_tps;
+                grp_l = __ldg(a.grp_layer + grp_b);
+                if (grp_l >= a.grp_depth) continue;
+                grp_tok = (tile % grp_tps) * Cfg::BM + row_in_tile;
+            }
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int row = m_blk * Cfg::BM + row_in_tile;
+            ++it;
+            const int row = kGrouped ? grp_b * a.L + grp_tok : m_blk * Cfg::BM + row_in_tile;
+            const bool row_ok = kGrouped ? grp_tok < a.L : row < M;
             float rstd = 1.f, mean_rstd = 0.f;
-            if (kLN && row < M) ln_row_stats(a.stats, row, a.nparts, a.ln_dim, a.ln_eps, rstd, mean_rstd);
+            if (kLN && row_ok) ln_row_stats(a.stats, row, a.nparts, a.ln_dim, a.ln_eps, rstd, mean_rstd);
 
             mbar_wait(&tfull_bar[as], aph);
             tc_fence_after();
@@ -370,17 +408,18 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
-                if (row < M) {
-                    const int b = row / a.L, l = row % a.L;
+                if (row_ok) {
+                    const int b = kGrouped ? grp_b : row / a.L, l = kGrouped ? grp_tok : row % a.L;
+                    const int voff = grp_l * 64;  // grouped: this sample's head in the stacked bias / colsum vectors
                     if (l >= a.extras) {
                         const int n = l - a.extras;
                         const int hh = n / a.Wp, ww = n % a.Wp;
                         if (a.C == 3 && a.P == 4)
-                            decode_store<3, 4>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                            decode_store<3, 4>(acc, a, rstd, mean_rstd, b, hh, ww, g, voff);
                         else if (a.C == 3 && a.P == 2)
-                            decode_store<3, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                            decode_store<3, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g, voff);
                         else if (a.C == 4 && a.P == 2)
-                            decode_store<4, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g);
+                            decode_store<4, 2>(acc, a, rstd, mean_rstd, b, hh, ww, g, voff);
                         else
                             __trap();  // plan_decode_geometry() rejects other (in_chans, patch_size) pairs
                     }
@@ -400,7 +439,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
 
 template <int C, int P>
 __device__ __forceinline__ void decode_store(const uint32_t (&acc)[2][32], const GemmArgs& a, float rstd,
-                                             float mean_rstd, int b, int hh, int ww, int g) {
+                                             float mean_rstd, int b, int hh, int ww, int g, int voff) {
     static_assert(P == 2 || P == 4, "patch size");
 #pragma unroll
     for (int pr = 0; pr < P / 2; ++pr) {
@@ -414,7 +453,8 @@ __device__ __forceinline__ void decode_store(const uint32_t (&acc)[2][32], const
                 const int j0 = ((pr)*P + p2) * C + ch, j1 = ((P / 2 + pr) * P + p2) * C + ch;
                 const float raw = __uint_as_float(g ? acc[j1 >> 5][j1 & 31] : acc[j0 >> 5][j0 & 31]);
                 const int j = g ? j1 : j0;
-                v[p2] = fmaf(raw, rstd, fmaf(-mean_rstd, __ldg(a.colsum + j), a.bias ? __ldg(a.bias + j) : 0.f));
+                v[p2] = fmaf(raw, rstd,
+                             fmaf(-mean_rstd, __ldg(a.colsum + voff + j), a.bias ? __ldg(a.bias + voff + j) : 0.f));
             }
             float* dst = a.img + (((size_t)b * C + ch) * a.H + hh * P + p1) * a.W + ww * P;
             if constexpr (P == 4)
