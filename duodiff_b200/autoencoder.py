@@ -76,8 +76,11 @@ class FrozenAutoencoderKL:
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
-            with torch.cuda.device(self.device):
-                self.lib.ddb_ae_destroy(h)
+            try:
+                with torch.cuda.device(self.device):
+                    self.lib.ddb_ae_destroy(h)
+            except (AttributeError, TypeError):  # interpreter shutdown: torch is already torn down
+                pass
             self.handle = None
 
     # nn.Module surface the reference's callers touch

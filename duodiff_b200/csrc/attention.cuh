@@ -728,7 +728,9 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     uint32_t(&cur)[32] = u ? vb : va;
                     uint32_t(&nxt)[32] = u ? va : vb;
                     const int j = jj + u;
-                    if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+                    // (unconditional: a predicate here becomes a branch around the .sync.aligned load and cuts the loop
+                    // body into basic blocks; after the last chunk the load re-reads chunk 0 and is discarded)
+                    tmem_ld_32x32b_x32(t_row + ((j + 1) & 7) * 32, nxt);
 #pragma unroll
                     for (int e = 0; e < 32; e += 8) {
                         m0 = fmax3(m0, __uint_as_float(cur[e + 0]), __uint_as_float(cur[e + 1]));
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                         m2 = fmax3(m2, __uint_as_float(cur[e + 4]), __uint_as_float(cur[e + 5]));
                         m3 = fmax3(m3, __uint_as_float(cur[e + 6]), __uint_as_float(cur[e + 7]));
                     }
-                    if (j < 7) tmem_ld_wait();
+                    tmem_ld_wait();
                 }
             }
             const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
@@ -744,6 +746,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             // the tiles take turns in the exp pass: tile t waits for its token (the other tile's previous exp pass has
             // ended), so that tile's MMA waits, row max and epilogue always run under this tile's exponentials
             if ((a.token & 1) && (t == 1 || it > 0)) wait(&tok[t], (t == 1 ? it : it - 1) & 1);
+            if (tr) tr[14] = clock64();
             const float pe0 = ex2_approx(fmaf(se0, c, -mc));
             const float pe1 = (a.extras == 2) ? ex2_approx(fmaf(se1, c, -mc)) : 0.f;
             // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
@@ -760,7 +763,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     uint32_t(&cur)[32] = u ? vb : va;
                     uint32_t(&nxt)[32] = u ? va : vb;
                     const int j = jj + u;
-                    if (j < 7) tmem_ld_32x32b_x32(t_row + (j + 1) * 32, nxt);
+                    // (unconditional, see pass 1: the branch around this load kept ptxas from interleaving the chunk's 32
+                    // MUFU with its FADD2 / F2FP -- 438 vs 255 issue cycles per chunk; the extra load after the last
+                    // chunk reads already-overwritten columns and is discarded)
+                    tmem_ld_32x32b_x32(t_row + ((j + 1) & 7) * 32, nxt);
                     uint32_t pk[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
@@ -773,7 +779,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                             sum2 = f2_add(sum2, p);
                         pk[e] = f2_to_bf16x2(p);
                     }
-                    if (j < 7) tmem_ld_wait();
+                    tmem_ld_wait();
                     // P chunk j < 4 -> columns [16j, 16j+16) (inside S chunk j/2), j >= 4 -> [128 + 16(j-4), ..)
                     // (inside S chunks 4, 5): always columns whose scores are already in registers
                     tmem_st_32x32b_x16(t_row + (j < 4 ? j * 16 : 64 + j * 16), pk);

@@ -137,8 +137,11 @@ class Sampler:
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
-            with torch.cuda.device(self.device):
-                self.lib.ddb_sampler_destroy(h)
+            try:
+                with torch.cuda.device(self.device):
+                    self.lib.ddb_sampler_destroy(h)
+            except (AttributeError, TypeError):  # interpreter shutdown: torch is already torn down
+                pass
             self.handle = None
 
     def set_noise_offset(self, first_row: int) -> None:

@@ -48,8 +48,11 @@ class Engine:
     def __del__(self):
         h = getattr(self, "handle", None)
         if h:
-            with torch.cuda.device(self.device):
-                self.lib.ddb_model_destroy(h)
+            try:
+                with torch.cuda.device(self.device):
+                    self.lib.ddb_model_destroy(h)
+            except (AttributeError, TypeError):  # interpreter shutdown: torch is already torn down
+                pass
             self.handle = None
 
     # ------------------------------------------------------------------ single forwards

@@ -57,7 +57,7 @@ def run(opts):
     pw = sorted(r[1] for r in smi.rows)[len(smi.rows) // 2] if smi.rows else 0
     print(f"{opts}: {ms:.1f} ms / 1000 steps = {B / ms * 1e3:.2f} img/s   sm {clk:.0f} MHz  {pw:.0f} W", flush=True)
     for k in opts:
-        _lib.check(lib.ddb_set_option(k.encode(), {"pdl": 1, "gemm_variant": 2, "alt_dir": 1, "conv_mt2": 1, "attn_discard": 1, "mlp_split": 0, "l2_hints": 0, "gemm_ln_cfg": 0}.get(k, 0)))
+        _lib.check(lib.ddb_set_option(k.encode(), {"pdl": 1, "gemm_variant": 2, "alt_dir": 1, "conv_mt2": 1, "attn_discard": 1, "mlp_split": 0, "l2_hints": 0, "gemm_ln_cfg": 0, "attn_token": 1}.get(k, 0)))
 
 
 run({})

@@ -28,6 +28,7 @@ for tile in range(2):
         v = [int(x) - t0 for x in t[it, tile, :8]]
         d = [v[i + 1] - v[i] for i in range(7)]
         m = [int(x) - t0 for x in t[it, tile, 8:14]]
-        print(f"{tile:4d} {it:5d} " + " ".join(f"{x:8d}" for x in v) + "   | " + " ".join(f"{x:6d}" for x in d)
+        print(f"{tile:4d} {it:5d} tokwait {int(t[it, tile, 14]) - t0 - v[3]:5d} " + " ".join(f"{x:8d}" for x in v) + "   | " + " ".join(f"{x:6d}" for x in d)
               + f"   || mma: s_issued {m[0]} phalf_seen {m[1]} pv1_issued {m[2]} pfull_seen {m[3]} pv2_issued {m[4]} o_done {m[5]}"
-              + f"  (WG p_done->mma seen {m[3] - v[4]}, issue {m[4] - m[3]}, exec {m[5] - m[4]}, mma o_done->WG o_ok {v[6] - m[5]})")
+              + f"  (WG p_done->mma seen {m[3] - v[4]}, issue {m[4] - m[3]}, exec {m[5] - m[4]}, mma o_done->WG o_ok {v[6] - m[5]})"
+              + f"  token wait {int(t[it, tile, 14]) - t0 - v[3]}")
