@@ -330,6 +330,7 @@ struct AttnArgs {
     int reverse;       // walk the (sample, head) items from the last to the first (see GemmArgs::reverse)
     int discard;       // drop the consumed q|k|v lines from L2 instead of letting them be written back (model path only)
     int token;         // the two query tiles take turns in the exp pass (one MUFU pipe per SM: see the kernel header)
+    int direct_store;  // epilogue writes the output rows straight from registers instead of staging + TMA store
     long long* trace;  // bench-only: CTA 0 records clock64() at the phase boundaries of every item ([it][tile][8])
 };
 
@@ -711,7 +712,11 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             if (tr) tr[1] = clock64();
             // this warp's store of the previous item was issued ~1000 clk ago: once it has read its 32 staging rows
             // (in the Q_t buffer of the other stage) that Q slot may be refilled
-            if (lane == 0 && it > 0) {
+            if (a.direct_store) {
+                // nothing is staged in the Q slot: it is free as soon as the S MMA has retired (s_full) and this warp has
+                // read its rows for the extras-key scores (above)
+                if (lane == 0) mbar_arrive(&q_empty[t * 2 + s]);
+            } else if (lane == 0 && it > 0) {
                 tma_store_wait_read<0>();
                 mbar_arrive(&q_empty[t * 2 + (s ^ 1)]);
             }
@@ -823,29 +828,45 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_free[t]);
-            // row r of the Q tile is only ever touched by this thread and by the (retired) S MMA: reuse it as staging
-            uint8_t* srow = sQ + r * 128;
             const f32x2 inv2 = f2_splat(inv);
+            if (a.direct_store) {
+                // the thread's output row is one full 128-byte line: eight 16-byte stores straight from registers -- no
+                // staging tile, no generic->async proxy fence (MEMBAR.ALL.CTA, ~300 clk with the stores in flight), no TMA
+                uint4* orow = reinterpret_cast<uint4*>(a.out + ((size_t)b * a.L + q0 + r) * D + h * 64);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t* o = (j < 4) ? &va[j * 8] : &vb[(j - 4) * 8];
-                uint4 w;
-                w.x = f2_to_bf16x2(f2_mul(f2_pack_u(o[0], o[1]), inv2));
-                w.y = f2_to_bf16x2(f2_mul(f2_pack_u(o[2], o[3]), inv2));
-                w.z = f2_to_bf16x2(f2_mul(f2_pack_u(o[4], o[5]), inv2));
-                w.w = f2_to_bf16x2(f2_mul(f2_pack_u(o[6], o[7]), inv2));
-                *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
-            }
-            // each warp stores its own 32 rows (4 KB, a whole number of 1 KB swizzle atoms): no warpgroup barrier
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                tma_store_3d(&a.tmOut32, sQ + quarter * 4096, h * 64, q0 + quarter * 32, b);
-                tma_store_commit();
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t* o = (j < 4) ? &va[j * 8] : &vb[(j - 4) * 8];
+                    uint4 w;
+                    w.x = f2_to_bf16x2(f2_mul(f2_pack_u(o[0], o[1]), inv2));
+                    w.y = f2_to_bf16x2(f2_mul(f2_pack_u(o[2], o[3]), inv2));
+                    w.z = f2_to_bf16x2(f2_mul(f2_pack_u(o[4], o[5]), inv2));
+                    w.w = f2_to_bf16x2(f2_mul(f2_pack_u(o[6], o[7]), inv2));
+                    orow[j] = w;
+                }
+            } else {
+                // row r of the Q tile is only ever touched by this thread and by the (retired) S MMA: reuse it as staging
+                uint8_t* srow = sQ + r * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t* o = (j < 4) ? &va[j * 8] : &vb[(j - 4) * 8];
+                    uint4 w;
+                    w.x = f2_to_bf16x2(f2_mul(f2_pack_u(o[0], o[1]), inv2));
+                    w.y = f2_to_bf16x2(f2_mul(f2_pack_u(o[2], o[3]), inv2));
+                    w.z = f2_to_bf16x2(f2_mul(f2_pack_u(o[4], o[5]), inv2));
+                    w.w = f2_to_bf16x2(f2_mul(f2_pack_u(o[6], o[7]), inv2));
+                    *reinterpret_cast<uint4*>(srow + ((j ^ (r & 7)) << 4)) = w;
+                }
+                // each warp stores its own 32 rows (4 KB, a whole number of 1 KB swizzle atoms): no warpgroup barrier
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&a.tmOut32, sQ + quarter * 4096, h * 64, q0 + quarter * 32, b);
+                    tma_store_commit();
+                }
             }
             if (tr) tr[7] = clock64();
         }
-        if (lane == 0 && my_items > 0) {
+        if (lane == 0 && my_items > 0 && !a.direct_store) {
             tma_store_wait_read<0>();
             mbar_arrive(&q_empty[t * 2 + ((my_items - 1) & 1)]);
             tma_store_wait_all<0>();

@@ -431,6 +431,9 @@ static int plan_attention(AttnArgs& a, const __nv_bfloat16* qkv, __nv_bfloat16* 
 static std::atomic<long long*> g_attn_trace{nullptr};  // bench-only (ddb_debug_set_ptr "attn_trace")
 // persistent tcgen05 attention: one CTA per SM, (sample, head) work items; covers the extras rows too
 static std::atomic<int> g_attn_x2{0};
+static std::atomic<int> g_attn_direct{0};  // ddb_set_option "attn_direct": attention epilogue stores its rows straight from registers
+                                           // (eight 16-byte global stores per thread) instead of staging + TMA store.  Measured
+                                           // SLOWER: 42.0 vs 37.9 us per launch (ImageNet-64 shape 117.4 vs 96.6 us)
 static std::atomic<int> g_attn_token{1};  // ddb_set_option "attn_token": the two query tiles alternate in the exp pass  // ddb_set_option "attn_x2": two softmax threads per query row (attention2.cuh)
 static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, int force_x2 = -1) {
     static ddb_host::DeviceOnce configured;
@@ -447,6 +450,7 @@ static int launch_attention_tc(AttnArgs a, int B, int num_sms, cudaStream_t st, 
     a.B = B;
     a.trace = g_attn_trace;
     a.token = g_attn_token;
+    a.direct_store = g_attn_direct;
     const int items = B * a.H;
     const dim3 grid(items < num_sms ? items : num_sms);
     if (force_x2 >= 0 ? force_x2 != 0 : g_attn_x2 != 0) {
@@ -1375,6 +1379,10 @@ int ddb_set_option(const char* name, int32_t value) {
     }
     if (!strcmp(name, "attn_x2")) {
         g_attn_x2 = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "attn_direct")) {
+        g_attn_direct = value != 0;
         return DDB_OK;
     }
     if (!strcmp(name, "attn_token")) {
