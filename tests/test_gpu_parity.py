@@ -124,7 +124,9 @@ def test_op_gemm(dev, M, N, K0, K1, epi, variant):
 
 @pytest.mark.parametrize("B,L,H,variant", [(1, 257, 1, 2), (2, 257, 8, 2), (3, 258, 12, 2), (2, 258, 16, 0),
                                               (2, 257, 8, 1), (3, 258, 12, 1), (1, 17, 2, 0), (2, 100, 2, 1),
-                                              (1, 257, 1, 3), (2, 257, 8, 3), (3, 258, 12, 3), (40, 258, 16, 3)])
+                                              (1, 257, 1, 3), (2, 257, 8, 3), (3, 258, 12, 3), (40, 258, 16, 3),
+                                              # several (sample, head) items per CTA: 640 / 1024 items on 148 SMs
+                                              (40, 258, 16, 2), (128, 257, 8, 0)])
 def test_op_attention(dev, B, L, H, variant):
     """variant 2 = tcgen05/TMEM kernel (the model path), 3 = the same with two softmax threads per query row,
     1 = generic mma.sync kernel, 0 = dispatcher.  Variants 1 and 3 (and L != 256 + extras) need an experimental build."""
