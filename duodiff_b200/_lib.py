@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from ._build import LIB_PATH
@@ -76,7 +77,7 @@ def load(path: Path | None = None):
     global _lib
     if _lib is not None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    p = Path(path or os.environ.get("DDB_LIB") or LIB_PATH)  # DDB_LIB: an A/B build (tools/, never the tests)
     if not p.exists():
         raise DuoDiffError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

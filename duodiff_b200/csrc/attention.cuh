@@ -386,10 +386,6 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = a.H * 64;
     pdl_launch_dependents();   // PDL: the set-up below overlaps the predecessor's tail
-    if (a.b_dev) pdl_wait();   // the live batch size is written by an earlier kernel of the step
-    const int n_items = (a.b_dev ? *a.b_dev : a.B) * a.H;
-    const int my_items =
-        (n_items > (int)blockIdx.x) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();  // swizzled tiles need 1024-byte alignment
     if (warp == 8 && lane == 0) {
@@ -422,7 +418,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
-    pdl_wait();  // qkv is the predecessor's output
+    pdl_wait();  // qkv is the predecessor's output -- and so is the live batch size of the early-exit compaction
+    const int n_items = (a.b_dev ? ld_state(a.b_dev) : a.B) * a.H;
+    const int my_items =
+        (n_items > (int)blockIdx.x) ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     auto wait = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
     auto item_of = [&](int it) {
@@ -636,6 +635,10 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             const uint8_t* st = smem + s * ATT3_STAGE;
             wait(&k_full[s], sph);
             wait(&q_full[t * 2 + s], sph);
+#ifdef ATT_EXP_NOSCORES
+            se0 = se1 = -INFINITY;
+            return;
+#endif
             const uint32_t sQ_u = smem_u32(st + t * 16384), sKx_u = smem_u32(st + ATT3_OFF_KX);
             uint32_t bk[4][2];  // B fragments of Kx: k-step ks -> (dims 16ks..+7, +8..+15) x keys 0..7
             ldmatrix_x4(sKx_u + att_swz(lane & 7, lane >> 3), bk[0][0], bk[0][1], bk[1][0], bk[1][1]);
@@ -671,8 +674,13 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             const int g = lane >> 2, tt = lane & 3;
             wait(&v_full[s], sph);
             float mq[2], lq[2], o[4][4];
+#ifdef ATT_EXP_NOSLICE
+            mq[0] = mq[1] = 0.f, lq[0] = lq[1] = 1.f;
+            for (int i = 0; i < 4; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#else
             att_extras_slice32_t(smem_u32(st + ATT3_OFF_K), smem_u32(st + ATT3_OFF_V), smem_u32(st + ATT3_OFF_QX), w8 * 32,
                                  a.scale_log2e, lane, mq, lq, o);
+#endif
             wait(&px_empty[s], sph ^ 1);  // the extras warp has merged the record of item it-2
             if (tt == 0) {  // these lanes hold queries 0 and 1 = the extras rows: dims 16 dm + 8 h + g
                 float* rec = px_buf + ((size_t)s * 8 + w8) * ATT3_PX_REC;
@@ -734,7 +742,7 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
                     uint32_t(&nxt)[32] = u ? va : vb;
                     const int j = jj + u;
                     // (unconditional: a predicate here becomes a branch around the .sync.aligned load and cuts the loop
-                    // body into basic blocks; after the last chunk the load re-reads chunk 0 and is discarded)
+                    // body into basic blocks; after the last chunk the load wraps around to chunk 0, which pass 2 starts on)
                     tmem_ld_32x32b_x32(t_row + ((j + 1) & 7) * 32, nxt);
 #pragma unroll
                     for (int e = 0; e < 32; e += 8) {
@@ -757,8 +765,8 @@ __global__ void __launch_bounds__(ATT3_THREADS, 1) attention_tcgen05_kernel(cons
             // ---- pass 2: P = exp2(s*c - m*c) -> bf16, written over the already-consumed S columns
             const f32x2 c2 = f2_splat(c), nmc2 = f2_splat(-mc);
             f32x2 sum2 = f2_pack(pe0, pe1), sum2b = f2_splat(0.f);
-            tmem_ld_32x32b_x32(t_row, va);
-            tmem_ld_wait();
+            // (va already holds chunk 0: pass 1's last prefetch wrapped around to it -- no TMEM round trip in front of
+            // the first exponentials)
             // (fully unrolled, one basic block: the scheduler can run chunk j's exponentials on the MUFU pipe under the
             // conversions / row sums of chunk j-1 and the scaling of chunk j+1)
 #pragma unroll 1

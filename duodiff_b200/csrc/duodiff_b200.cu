@@ -261,6 +261,11 @@ static int launch_gemm_t(const GemmArgs& a, int num_sms, cudaStream_t st) {
 // runtime options (ddb_set_option): gemm_variant 2 = CTA-pair kernel (default), 1 = single-CTA kernel
 static std::atomic<int> g_gemm_variant{2};
 static std::atomic<int> g_gemm_debug{0};
+// bench-only (tools/ee_overhead.py): price the early-exit bookkeeping of a NEVER-EXIT step by leaving parts of it out --
+// 1 no row move, 2 no decision, 4 no probe partials in the fc2 epilogue, 8 no probe pass over the first block input
+static std::atomic<int> g_ee_debug{0};
+// ddb_set_option "ee_fuse": the early-exit step in compaction mode ends in the fused step tail (per-sample conv weights)
+static std::atomic<int> g_ee_fuse{1};
 static std::atomic<long long*> g_gemm_trace{nullptr};  // bench-only (ddb_debug_set_ptr "gemm_trace")
 
 static std::atomic<int> g_attn_discard{1};  // ddb_set_option "attn_discard": discard consumed q|k|v lines from L2 (attention.cuh)
@@ -786,7 +791,7 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
         DDB_TRY(new_buf(m->exit_idx, (size_t)cfg->max_batch * 4));
         DDB_TRY(new_buf(m->ee_n, 8 * 4));
         DDB_TRY(new_buf(m->ee_slot, (size_t)cfg->max_batch * 4));
-        DDB_TRY(new_buf(m->ee_dest, (size_t)cfg->max_batch * 4));
+        DDB_TRY(new_buf(m->ee_dest, (size_t)cfg->max_batch * 2 * 4));  // leavers' positions | the stayers that replace them
         DDB_TRY(new_buf(m->ee_sc, (size_t)cfg->max_batch * 4));
         DDB_TRY(new_buf(m->ee_ticket, 4));
         DDB_TRY(new_buf(m->ee_exit_slot, (size_t)cfg->max_batch * 4));
@@ -977,7 +982,8 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     if (m->extras == 2 && !y) return fail(DDB_ERR_INVALID, "class-conditional model needs y (models/uvit.py:361)");
     if (ee && !c.early_exit) return fail(DDB_ERR_INVALID, "model was not created with early_exit=1");
     if (cp && (!ee || B > 1024)) return fail(DDB_ERR_INVALID, "compaction needs an early-exit model and batch <= 1024");
-    if (fuse && (ee || g_gemm_variant != 2)) return fail(DDB_ERR_INVALID, "the fused step needs the plain CTA-pair path");
+    if (fuse && ((ee && !cp) || g_gemm_variant != 2 || m->Np != 256))
+        return fail(DDB_ERR_INVALID, "the fused step needs the CTA-pair path (plain backbone, or early exit with compaction)");
     const int D = m->D, M = B * m->L, nsm = m->dev.num_sms, half = c.depth / 2;
     // compaction: live sample / row counts are read from device memory by every kernel after the token assembly
     int* een = cp ? m->ee_n->as<int>() : nullptr;
@@ -1026,6 +1032,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     // LayerNorm statistics travel either as one (mean, M2) per row from ln_stats_kernel (kind 1) or as D/64
     // partials per row written by the producing CTA-pair GEMM's epilogue (kind 2).
     const int np_p = D / 64;
+    const int eed = cp ? (int)g_ee_debug : 0;
     int kind = 0;
     // consecutive kernels walk the rows in alternating directions (GemmArgs::reverse): L2 reuse between kernels
     bool rev = false;
@@ -1095,7 +1102,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             // probe i + head i look at the block input (models/early_exit.py:294-296).  Its LayerNorm statistics and the
             // probe's partial dot products were written by the fc2 epilogue that produced it; only the first layer (and the
             // single-CTA GEMM variant) needs a pass of its own over the activations.
-            if (!probe_ready) {
+            if (!probe_ready && !(eed & 8)) {
                 DDB_TRY(launch_ln_stats(cur, M, D, cp ? een + 1 : nullptr, st2, m->probe_w[i]->as<float>(),
                                         m->probe_p->as<float>(), st));
                 if (kind != 2) kind = 1;  // the token assembly's partial statistics of x0 stay in force (CTA-pair path)
@@ -1108,19 +1115,23 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             // leavers take head i's output and are squeezed out of every live buffer
             {
                 ProfScope ps(PC_EE_OTHER);
-                CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
-                                    np_p, (const float*)m->probe_b[i]->as<float>(), m->L, cp->threshold, i, B,
-                                    (int)c.depth, een, m->ee_slot->as<int>(), m->ee_dest->as<int>(),
-                                    m->ee_exit_slot->as<int>(), m->scores->as<float>(), cp->exit_idx, cp->t_dev,
-                                    cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
-                                    m->ee_ticket->as<unsigned>()));
+                if (!(eed & 2))
+                    CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
+                                        np_p, (const float*)m->probe_b[i]->as<float>(), m->L, cp->threshold, i, B,
+                                        (int)c.depth, een, m->ee_slot->as<int>(), m->ee_dest->as<int>(),
+                                        m->ee_dest->as<int>() + c.max_batch, m->ee_exit_slot->as<int>(), m->scores->as<float>(), cp->exit_idx, cp->t_dev,
+                                        cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
+                                        m->ee_ticket->as<unsigned>()));
                 LAUNCH_CHECK();
-                // stayers compacted in place (block input, pending long skips, statistics); the leavers' rows and
-                // statistics go to the scratch batch at their ORIGINAL slot -- their heads run once, after the last block
-                CUDA_TRY(launch_pdl(ee_move_kernel, dim3(m->L, m->ee_live_n[i] + 1), dim3(128), 0, st, m->ee_live[i],
-                                    m->ee_live_n[i], m->xe->as<__nv_bfloat16>(), st_cur, m->stats_e->as<float2>(), np_cur,
-                                    (const int*)een, (const int*)m->ee_dest->as<int>(),
-                                    (const int*)m->ee_exit_slot->as<int>(), m->L, D));
+                // the batch stays dense: stayers from its end take the leavers' places (block input, pending long skips,
+                // statistics); the leavers' rows and statistics go to the scratch batch at their ORIGINAL slot -- their
+                // heads run once, after the last block
+                if (!(eed & 1))
+                    CUDA_TRY(launch_pdl(ee_move_kernel, dim3(EE_MOVE_GRID, m->ee_live_n[i] + 1), dim3(128), 0, st, m->ee_live[i],
+                                        m->ee_live_n[i], m->xe->as<__nv_bfloat16>(), st_cur, m->stats_e->as<float2>(), np_cur,
+                                        (const int*)een, (const int*)m->ee_dest->as<int>(),
+                                        (const int*)(m->ee_dest->as<int>() + c.max_batch),
+                                        (const int*)m->ee_exit_slot->as<int>(), m->L, D));
                 LAUNCH_CHECK();
             }
             np_exit = np_cur;
@@ -1186,7 +1197,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             }
         } else {
             DDB_TRY(run_gemm(op.fc1, EPI_LN_GELU, PC_GEMM_FC1, true, false));
-            if (ee && pair && i + 1 < c.depth) probe_layer = i + 1, probe_ready = true;
+            if (ee && pair && i + 1 < c.depth) probe_layer = (eed & 4) ? -1 : i + 1, probe_ready = true;
             DDB_TRY(run_gemm(op.fc2, EPI_RES, PC_GEMM_FC2, false, true));
             probe_layer = -1;
         }
@@ -1198,8 +1209,24 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         DDB_TRY(launch_ln_stats(cur, M, D, nullptr, st2, nullptr, nullptr, st));
         kind = 1;
     }
-    DDB_TRY(run_gemm(m->final_dec, EPI_DECODE, PC_GEMM_DECODE, true, false));
-    if (fuse) return launch_step_tail(m, fuse->tail, B, st);
+    {
+        GemmArgs g = m->final_dec;
+        // fused early-exit step: the stayers are un-patchified at their ORIGINAL slots, next to the leavers (below)
+        if (cp && fuse) g.dec_slot = m->ee_slot->as<int>();
+        DDB_TRY(run_gemm(g, EPI_DECODE, PC_GEMM_DECODE, true, false));
+    }
+    if (fuse && !cp) return launch_step_tail(m, fuse->tail, B, st);
+    if (cp && fuse) {
+        // every sample that left, at whatever layer: one grouped decode into the same image buffer, then the step tail
+        // with per-sample conv weights (head of layer exit_idx[b], or final_layer for the samples that never left)
+        GemmArgs g = m->head_grp;
+        g.grp_layer = cp->exit_idx, g.grp_B = B, g.nparts = np_exit;
+        {
+            ProfScope ps(PC_GEMM_DECODE);
+            DDB_TRY(launch_gemm(g, EPI_DECODE, nsm, st));
+        }
+        return launch_step_tail(m, fuse->tail, B, st);
+    }
     if (cp) {
         // the samples that never left: full-model output, written to their original slots ...
         DDB_TRY(run_conv(m, m->final_head, m->img_pre->as<float>(), eps, B, st, een, m->ee_slot->as<int>()));
@@ -1269,6 +1296,9 @@ struct ddb_sampler {
         bool operator==(const Key& o) const { return z_all == o.z_all && has_y == o.has_y && epoch == o.epoch; }
     } graph_key[2];
     bool early_exit() const { return ee_mode >= 0 && early->cfg.early_exit; }
+    // every step ends in step_tail_kernel, which also prepares the head of the next step (plain backbones always;
+    // early exit in compaction mode on the CTA-pair path, option "ee_fuse")
+    bool fused() const { return !early_exit() || (ee_mode == 1 && g_ee_fuse != 0 && g_gemm_variant == 2 && early->Np == 256); }
 };
 
 __global__ void set_t_kernel(int* t_dev, int t) { *t_dev = t; }
@@ -1282,7 +1312,7 @@ __global__ void score_mean_kernel(const float* __restrict__ scores, int depth, i
     float s = 0.f;
     for (int b = threadIdx.x; b < B; b += 32) s += scores[(size_t)i * B + b];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) out[(size_t)(*t_dev) * depth + i] = s / (float)B;
+    if (threadIdx.x == 0) out[(size_t)ld_state(t_dev) * depth + i] = s / (float)B;
 }
 
 static void tail_target(TailTarget& tg, const ddb_model* m) {
@@ -1298,12 +1328,15 @@ static void tail_target(TailTarget& tg, const ddb_model* m) {
 // One sampling step on the stream: forward + update + bookkeeping.  t comes from s->t_dev, the Philox key from
 // s->seed_dev (device memory), labels from s->y_buf.
 //   plain U-ViT:  embed GEMM -> blocks -> decode GEMM -> step_tail_kernel (conv + update + head of the next step)
-//   early exit:   fill_t -> EarlyExitUViT forward + selection -> ddpm_step -> next_t
+//   early exit, compaction:  the same, with the probes / decisions / row moves between the blocks, a second (grouped)
+//                 decode GEMM for the samples that left, and per-sample conv weights in the tail
+//   early exit, simulate (or ee_fuse = 0):  fill_t -> EarlyExitUViT forward + selection -> ddpm_step -> next_t
 static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, bool has_y, const float* z_all, float* eps_save,
                         float* x_save, cudaStream_t st) {
     const int B = s->B;
     const int64_t* y = has_y ? s->y_buf->as<int64_t>() : nullptr;
-    if (s->early_exit() && m->cfg.early_exit) {
+    const bool ee_on = s->early_exit() && m->cfg.early_exit;
+    if (ee_on && !s->fused()) {
         fill_t_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->t_dev->as<int>(), s->t_vec->as<float>(), B);
         LAUNCH_CHECK();
         float* eps = eps_save ? eps_save : s->eps->as<float>();
@@ -1341,6 +1374,14 @@ static int sampler_step(ddb_sampler* s, ddb_model* m, float* x, bool has_y, cons
     ta.n = s->n, ta.H = m->cfg.img_size, ta.W = m->cfg.img_size, ta.mode = s->step_mode;
     tail_target(ta.tgt[0], s->early);
     tail_target(ta.tgt[1], s->late ? s->late : s->early);
+    if (ee_on) {
+        // early exit with compaction: the same fused step; the tail picks every sample's conv weights by its exit layer
+        EeCompact cp{s->ee_threshold, m->exit_idx->as<int32_t>(), s->t_dev->as<int>(), s->exit_log->as<int32_t>(),
+                     s->score_log->as<float>()};
+        ta.layer_idx = cp.exit_idx, ta.depth = m->cfg.depth;
+        ta.grp_w = m->hg_conv_w->as<float>(), ta.grp_b = m->hg_conv_b->as<float>();
+        return forward_impl(m, x, nullptr, y, B, nullptr, true, st, &cp, &f);
+    }
     return forward_impl(m, x, nullptr, y, B, nullptr, false, st, nullptr, &f);
 }
 
@@ -1367,6 +1408,14 @@ int ddb_set_option(const char* name, int32_t value) {
     if (!strcmp(name, "gemm_variant")) {
         if (value != 1 && value != 2) return fail(DDB_ERR_INVALID, "gemm_variant must be 1 or 2");
         g_gemm_variant = value;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "ee_fuse")) {
+        g_ee_fuse = value != 0;
+        return DDB_OK;
+    }
+    if (!strcmp(name, "ee_debug")) {
+        g_ee_debug = value;
         return DDB_OK;
     }
     if (!strcmp(name, "gemm_debug")) {
@@ -1584,7 +1633,7 @@ static int sampler_run_impl(ddb_sampler* s, float* x_dev, const int64_t* y_dev, 
         xw = s->x_buf->as<float>();
         CUDA_TRY(cudaMemcpyAsync(xw, x_dev, s->n * 4, cudaMemcpyDeviceToDevice, st));
     }
-    if (!s->early_exit()) {
+    if (s->fused()) {
         // head of the first step (every later step's head is written by its predecessor's tail kernel)
         ddb_model* m0 = late[0] ? s->late : s->early;
         DDB_TRY(launch_patch_gather(m0, xw, s->B, st));

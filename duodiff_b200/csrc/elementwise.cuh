@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) token_extras_kernel(const float* __restri
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x;
-    const float tau = t_dev ? (float)(*t_dev) : tsteps[b];
+    const float tau = t_dev ? (float)ld_state(t_dev) : tsteps[b];
     write_token_extras(b, tau, y, pos, label_emb, tokens, stats_p, D, L, extras, normalize_t, num_classes);
 }
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const __nv_bfloat16* __re
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();
     pdl_wait();
-    const int Mr = m_dev ? *m_dev : M;
+    const int Mr = m_dev ? ld_state(m_dev) : M;
     if (row >= Mr) return;
     const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * D);
     float v[CH][8];
@@ -312,14 +312,14 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
         for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
             sw[i] = (i < C * C * 9) ? wgt[i] : bias[i - C * C * 9];
     pdl_wait();
-    if (n_dev && b >= *n_dev) return;
+    if (n_dev && b >= ld_state(n_dev)) return;
     if (layer_idx) {
-        const int layer = layer_idx[b];
+        const int layer = ld_state(layer_idx + b);
         if (layer >= depth) return;
         for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
             sw[i] = (i < C * C * 9) ? wgt[(size_t)layer * C * C * 9 + i] : bias[layer * C + i - C * C * 9];
     }
-    const int ob = slot_map ? slot_map[b] : b;
+    const int ob = slot_map ? ld_state(slot_map + b) : b;
     const int w4 = W / 4;
     conv_stage_band<C>(conv_smem, in, b, y0, H, W);
     __syncthreads();
@@ -399,9 +399,9 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(float* __restrict__ x, c
                                                         float* __restrict__ x_save) {
     pdl_launch_dependents();
     pdl_wait();
-    const int t = t_dev ? *t_dev : t_host;
+    const int t = t_dev ? ld_state(t_dev) : t_host;
     unsigned long long off4 = 0;
-    if (seed_dev) seed = seed_dev[0], off4 = seed_dev[1];
+    if (seed_dev) seed = ld_state(seed_dev), off4 = ld_state(seed_dev + 1);
     const StepCoef k{coef[t * 4 + 0], coef[t * 4 + 1], coef[t * 4 + 2], coef[t * 4 + 3]};
     const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 * 4 >= n) return;
@@ -448,6 +448,13 @@ struct TailArgs {
     unsigned* ticket;      // CTA completion counter (self-resetting)
     size_t n;              // B*C*H*W
     int H, W, mode;
+    // early-exit compaction (eesampler.py:62-68): image b went through the output head of layer layer_idx[b]; its conv
+    // weights come from the stacked arrays grp_w [depth][C*C*9] / grp_b [depth][C] (layer_idx[b] >= depth: the full
+    // model's final_layer, conv_w / conv_b)
+    const int* layer_idx;
+    const float* grp_w;
+    const float* grp_b;
+    int depth;
     TailTarget tgt[2];     // [0] early backbone, [1] late backbone
 };
 template <int C, int W>
@@ -461,14 +468,21 @@ __global__ void __launch_bounds__(256, 4) step_tail_kernel(const __grid_constant
     const int bands = H / CONV_BAND;
     const int b = blockIdx.x / bands, y0 = (blockIdx.x % bands) * CONV_BAND;
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
-        sw[i] = (i < C * C * 9) ? a.conv_w[i] : a.conv_b[i - C * C * 9];
+    if (!a.layer_idx)
+        for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x)
+            sw[i] = (i < C * C * 9) ? a.conv_w[i] : a.conv_b[i - C * C * 9];
     pdl_wait();
-    const int t = *a.t_dev;
+    if (a.layer_idx) {  // which head the sample left through is this step's own result
+        const int layer = ld_state(a.layer_idx + b);
+        const float* cw = layer < a.depth ? a.grp_w + (size_t)layer * C * C * 9 : a.conv_w;
+        const float* cb = layer < a.depth ? a.grp_b + layer * C : a.conv_b;
+        for (int i = threadIdx.x; i < C * C * 9 + C; i += blockDim.x) sw[i] = (i < C * C * 9) ? cw[i] : cb[i - C * C * 9];
+    }
+    const int t = ld_state(a.t_dev);
     // everything that depends on t is requested at once (one further round trip, not three)
     const int t_next = a.next_t[t], late_next = a.next_t[1000 + t];
     const float4 kc = *reinterpret_cast<const float4*>(a.coef + t * 4);
-    const unsigned long long seed = a.seed_dev[0], off4 = a.seed_dev[1];
+    const unsigned long long seed = ld_state(a.seed_dev), off4 = ld_state(a.seed_dev + 1);
     // band of the decoder image: all loads of a thread are in flight before its first shared-memory store
     {
         constexpr int PER = (N_STAGE + 255) / 256;
@@ -530,12 +544,12 @@ __global__ void __launch_bounds__(256, 4) step_tail_kernel(const __grid_constant
 // step bookkeeping for graph replay: t_vec[b] = float(*t_dev) for the next forward; (*t_dev) -= 1 after a step
 __global__ void fill_t_kernel(const int* __restrict__ t_dev, float* __restrict__ t_vec, int B) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) t_vec[i] = (float)(*t_dev);
+    if (i < B) t_vec[i] = (float)ld_state(t_dev);
 }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 // t <- next_t[t]: the timestep sequence of the run (t-1 for DDPM, the strided DDIM schedule, ...) lives in a table
 __global__ void next_t_kernel(int* t_dev, const int* __restrict__ next_t) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev = next_t[*t_dev];
+    if (threadIdx.x == 0 && blockIdx.x == 0) *t_dev = next_t[ld_state(t_dev)];
 }
 
 // samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146)
@@ -562,6 +576,41 @@ __device__ __forceinline__ float probe_token(const float* __restrict__ pp, size_
     for (int c = 0; c < np; ++c) d += pp[row * np + c];
     return 1.f / (1.f + expf(-(d + bias)));
 }
+// sum over the tokens l = tid, tid + stride, ... of one sample of the per-token probe outputs, in that order.  For the
+// usual np (a multiple of 4, <= 16) the partials of four tokens are requested at once with 16-byte loads -- one memory
+// round trip per four tokens instead of np dependent ones per token (7.5 -> 5.2 us per layer in the compaction chain);
+// the additions are those of probe_token, in the same order.
+__device__ __forceinline__ float probe_tokens_sum(const float* __restrict__ pp, size_t row0, int L, int np, float bias,
+                                                  int tid, int stride) {
+    float s = 0.f;
+    if ((np & 3) == 0 && np <= 16) {
+        const int n4 = np >> 2;
+        for (int l0 = tid; l0 < L; l0 += 4 * stride) {
+            float4 v[4][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int l = l0 + k * stride;
+                const float4* q = reinterpret_cast<const float4*>(pp + (row0 + l) * np);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (l < L && c < n4) v[k][c] = q[c];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (l0 + k * stride < L) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < n4) d += v[k][c].x, d += v[k][c].y, d += v[k][c].z, d += v[k][c].w;
+                    s += 1.f / (1.f + expf(-(d + bias)));
+                }
+            }
+        }
+    } else {
+        for (int l = tid; l < L; l += stride) s += probe_token(pp, row0 + l, np, bias);
+    }
+    return s;
+}
 // probe partials [M, np] (one layer) -> score[b] = mean_l sigmoid(w.x_{b,l} + bias); deterministic tree order.
 __global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict__ pp, int np,
                                                          const float* __restrict__ bias_p, int L,
@@ -570,8 +619,7 @@ __global__ void __launch_bounds__(128) probe_mean_kernel(const float* __restrict
     pdl_wait();
     const int b = blockIdx.x;
     const float bias = bias_p[0];
-    float s = 0.f;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) s += probe_token(pp, (size_t)b * L + l, np, bias);
+    float s = probe_tokens_sum(pp, (size_t)b * L, L, np, bias, threadIdx.x, blockDim.x);
     __shared__ float red[4];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -597,7 +645,7 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         exit_idx[b] = idx;
-        if (exit_log) exit_log[(size_t)(t_dev ? *t_dev : 0) * B + b] = idx;
+        if (exit_log) exit_log[(size_t)(t_dev ? ld_state(t_dev) : 0) * B + b] = idx;
     }
     const float4* src = reinterpret_cast<const float4*>(outputs + ((size_t)idx * B + b) * chw);
     float4* dst = reinterpret_cast<float4*>(eps + (size_t)b * chw);
@@ -620,41 +668,44 @@ __global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, 
     if (i < B) {
         slot[i] = i;
         exit_idx[i] = depth;
-        if (exit_log) exit_log[(size_t)(t_dev ? *t_dev : 0) * B + i] = depth;
+        if (exit_log) exit_log[(size_t)(t_dev ? ld_state(t_dev) : 0) * B + i] = depth;
     }
     if (i < depth * B) scores[i] = __int_as_float(0x7fc00000);  // NaN: "not produced" (sample had already left)
 }
 
 // grid = B CTAs of 128 threads.  CTA b scores live sample b (mean over tokens of the probe's sigmoid, with exactly the
 // summation order of probe_mean_kernel, so the exit decisions of the two modes can never differ by rounding); the LAST
-// CTA to finish (atomic ticket) decides who leaves at `layer`, builds the destination map of the row move with a
-// block-wide scan and updates the state.  (Round 1 scored all samples in one CTA: with the probe's partial dot products
-// coming from the fc2 epilogue that is 1 MB through a single SM, 11 us per layer.)
+// CTA to finish (atomic ticket) decides who leaves at `layer` and plans the row move.  (Round 1 scored all samples in
+// one CTA: with the probe's partial dot products coming from the fc2 epilogue that is 1 MB through a single SM, 11 us
+// per layer.)
+// The batch is kept dense by SWAPPING, not by shifting: with n_keep samples staying, every leaver at a position
+// < n_keep is a hole, and the stayers at positions >= n_keep fill the holes in order.  Only n_exit rows per buffer move
+// (an order-preserving squeeze re-wrote every row behind the first leaver: all live buffers, ~0.5 GB per event at
+// B = 128); the order of the samples inside the batch carries no meaning -- slot[] maps a position to the sample.
 //   ee_n[0..4] = {n_active, n_active*L, n_exit, n_exit*L, n_active BEFORE this layer}
-//   dest[b] (b < previous n_active): >= 0 -> the sample stays and becomes compact sample dest[b];
-//                                    <  0 -> it leaves: scratch-batch sample -(dest[b] + 1)
+//   leaver j (in position order): ex_pos[j] = its position, exit_slot[j] = its sample index (the scratch batch is indexed
+//   by sample), ex_fill[j] = position of the stayer that takes its place, or -1 (the leaver sat behind the new end)
 constexpr int EE_MAX_BATCH = 1024;
 __global__ void __launch_bounds__(128) ee_decide_kernel(
     const float* __restrict__ pp, int np, const float* __restrict__ bias_p, int L, float thr, int layer, int B,
-    int depth, int* __restrict__ ee_n, int* __restrict__ slot, int* __restrict__ dest, int* __restrict__ exit_slot,
-    float* __restrict__ scores, int* __restrict__ exit_idx, const int* __restrict__ t_dev,
-    int* __restrict__ exit_log, float* __restrict__ score_mean_log, float* __restrict__ sc_tmp,
-    unsigned* __restrict__ ticket) {
+    int depth, int* __restrict__ ee_n, int* __restrict__ slot, int* __restrict__ ex_pos, int* __restrict__ ex_fill,
+    int* __restrict__ exit_slot, float* __restrict__ scores, int* __restrict__ exit_idx,
+    const int* __restrict__ t_dev, int* __restrict__ exit_log, float* __restrict__ score_mean_log,
+    float* __restrict__ sc_tmp, unsigned* __restrict__ ticket) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[4];
-    __shared__ int new_slot[EE_MAX_BATCH];
-    __shared__ int wtot[2][4];
+    __shared__ int s_pos[EE_MAX_BATCH];
+    __shared__ int wtot[3][4];
     __shared__ float wsum[4];
     __shared__ int is_last;
-    const int n = ee_n[0];  // rewritten by the last CTA only after every CTA has passed the ticket below
+    const int n = ld_state(ee_n);  // rewritten by the last CTA only after every CTA has passed the ticket below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
         const int b = blockIdx.x;
         if (b < n) {
             const float bias = bias_p[0];
-            float s = 0.f;
-            for (int l = tid; l < L; l += 128) s += probe_token(pp, (size_t)b * L + l, np, bias);
+            float s = probe_tokens_sum(pp, (size_t)b * L, L, np, bias, tid, 128);
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) red[warp] = s;
             __syncthreads();
@@ -668,7 +719,7 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // ---- decision: thread i owns samples 8i .. 8i+7 (B <= 1024)
+    // ---- decision: thread i owns positions 8i .. 8i+7 (B <= 1024)
     constexpr int PER = EE_MAX_BATCH / 128;
     float sc[PER];
     int ex[PER], myslot[PER];
@@ -679,28 +730,44 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
         const int b = tid * PER + u;
         const bool live = b < n;
         sc[u] = live ? __ldcg(sc_tmp + b) : 0.f;
-        myslot[u] = live ? slot[b] : 0;
+        myslot[u] = live ? ld_state(slot + b) : 0;
         // threshold < 0: argmax over an all-false mask selects layer 0 for every sample (see ee_select_kernel)
         ex[u] = (live && (sc[u] <= thr || (thr < 0.f && layer == 0))) ? 1 : 0;
         ce += ex[u];
         ck += (live && !ex[u]) ? 1 : 0;
         fs += sc[u];
     }
-    // block-wide exclusive scans of the per-thread counts, and the sum of the live scores
-    int ie = ce, ik = ck;
+    // block-wide exclusive scan of the leavers, totals of leavers / stayers, and the sum of the live scores
+    int ie = ce, tk = ck;
     for (int o = 1; o < 32; o <<= 1) {
-        const int te = __shfl_up_sync(0xffffffffu, ie, o), tk = __shfl_up_sync(0xffffffffu, ik, o);
-        if (lane >= o) ie += te, ik += tk;
+        const int te = __shfl_up_sync(0xffffffffu, ie, o);
+        if (lane >= o) ie += te;
     }
-    for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
-    if (lane == 31) wtot[0][warp] = ie, wtot[1][warp] = ik;
-    if (lane == 0) wsum[warp] = fs;
+    for (int o = 16; o > 0; o >>= 1) {
+        tk += __shfl_xor_sync(0xffffffffu, tk, o);
+        fs += __shfl_xor_sync(0xffffffffu, fs, o);
+    }
+    if (lane == 31) wtot[0][warp] = ie;
+    if (lane == 0) wtot[1][warp] = tk, wsum[warp] = fs;
     __syncthreads();
-    int base_e = ie - ce, base_k = ik - ck;  // exclusive inside the warp
-    for (int w = 0; w < warp; ++w) base_e += wtot[0][w], base_k += wtot[1][w];
+    int base_e = ie - ce;  // exclusive inside the warp
+    for (int w = 0; w < warp; ++w) base_e += wtot[0][w];
     const int n_exit = wtot[0][0] + wtot[0][1] + wtot[0][2] + wtot[0][3];
     const int n_keep = wtot[1][0] + wtot[1][1] + wtot[1][2] + wtot[1][3];
-    const int t_now = t_dev ? *t_dev : 0;
+    // movers: stayers behind the new end of the batch; second scan
+    int cm = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int b = tid * PER + u;
+        cm += (b < n && !ex[u] && b >= n_keep) ? 1 : 0;
+    }
+    int im = cm;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int tm = __shfl_up_sync(0xffffffffu, im, o);
+        if (lane >= o) im += tm;
+    }
+    if (lane == 31) wtot[2][warp] = im;
+    const int t_now = t_dev ? ld_state(t_dev) : 0;
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const int b = tid * PER + u;
@@ -708,18 +775,26 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
         scores[(size_t)layer * B + myslot[u]] = sc[u];
         if (ex[u]) {
             const int j = base_e++;
-            dest[b] = -(j + 1);
+            s_pos[j] = b;
+            ex_pos[j] = b;
+            if (b >= n_keep) ex_fill[j] = -1;  // (the holes' entries are written by the movers below)
             exit_slot[j] = myslot[u];
             exit_idx[myslot[u]] = layer;
             if (exit_log) exit_log[(size_t)t_now * B + myslot[u]] = layer;
-        } else {
-            const int j = base_k++;
-            dest[b] = j;
-            new_slot[j] = myslot[u];
         }
     }
     __syncthreads();
-    for (int b = tid; b < n_keep; b += 128) slot[b] = new_slot[b];
+    int base_m = im - cm;
+    for (int w = 0; w < warp; ++w) base_m += wtot[2][w];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int b = tid * PER + u;
+        if (b < n && !ex[u] && b >= n_keep) {
+            const int q = base_m++;  // the q-th mover takes the q-th hole (holes = the leavers at positions < n_keep)
+            ex_fill[q] = b;
+            slot[s_pos[q]] = myslot[u];
+        }
+    }
     if (tid == 0) {
         ee_n[0] = n_keep, ee_n[1] = n_keep * L, ee_n[2] = n_exit, ee_n[3] = n_exit * L, ee_n[4] = n;
         // eesampler.py:71 logs the batch mean of every probe; here: the mean over the samples still in the batch
@@ -730,68 +805,64 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
     }
 }
 
-// One kernel moves the rows after a decision: in every live activation buffer (the block input bufs.p[0] and the
-// pending long skips) the stayers are compacted IN PLACE, and the leavers' rows of the block input go to the scratch
-// batch xe for their exit head; blockIdx.y == nbuf does the same for the rows' LayerNorm statistics (np float2 each).
-// grid = (L, nbuf + 1).  A thread owns one 16-byte column chunk of token l and walks the previously live samples in
-// increasing order: a stayer's destination index is <= its source index, so every row is read before it can be
-// overwritten -- also inside a batch of four (all four loads precede the four stores, which only target rows <= b+3).
+// One kernel moves the rows after a decision, in every live activation buffer (the block input bufs.p[0] and the
+// pending long skips): per leaver, its row of the block input goes to the scratch batch xe for its exit head (indexed by
+// the sample, so the leavers of all layers collect there and one grouped decode serves them at the end of the forward),
+// and the stayer ex_fill[j] -- if any -- is copied into its place.  blockIdx.y == nbuf does the same for the rows'
+// LayerNorm statistics (np float2 each).  grid = (EE_MOVE_GRID, nbuf + 1): a CTA walks the tokens l = blockIdx.x,
+// + gridDim.x, ... of every moved row (a small grid: at most layers nobody leaves and the launch is a no-op whose cost
+// is draining its CTAs); a work item is one 16-byte chunk.  Sources (positions >= n_keep) and destinations (< n_keep) are disjoint, and the thread that
+// overwrites a hole is the one that saved its old content first.
 constexpr int EE_MAX_LIVE = 16;
+constexpr int EE_MOVE_GRID = 64;
 struct EeBufList {
     __nv_bfloat16* p[EE_MAX_LIVE];
 };
-// (the scratch batch is indexed by the sample's ORIGINAL slot, exit_slot[-dest - 1]: the leavers of all layers collect
-// there and one grouped decode serves them at the end of the forward)
 template <typename T>
-__device__ __forceinline__ void ee_move_rows(T* __restrict__ buf, T* __restrict__ scratch, int chunks,
-                                             const int* __restrict__ dest, const int* __restrict__ exit_slot, int n_prev,
-                                             int L, int l) {
-    for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-        int b = 0;
-        for (; b + 4 <= n_prev; b += 4) {
-            T v[4];
-            int d[4];
+__device__ __forceinline__ void ee_move_rows(T* buf, T* scratch, int chunks, const int* __restrict__ ex_pos,
+                                             const int* __restrict__ ex_fill, const int* __restrict__ exit_slot,
+                                             int n_exit, int L, int l) {
+    const int total = n_exit * chunks;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+        T hv[4], fv[4];
+        int pos[4], fill[4], cc[4], jj[4];
+        // all loads first (up to eight in flight per thread), then the stores
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                d[u] = dest[b + u];
-                v[u] = buf[((size_t)(b + u) * L + l) * chunks + c];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (d[u] >= 0) {
-                    if (d[u] != b + u) buf[((size_t)d[u] * L + l) * chunks + c] = v[u];
-                } else if (scratch) {
-                    scratch[((size_t)exit_slot[-d[u] - 1] * L + l) * chunks + c] = v[u];
-                }
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * blockDim.x;
+            fill[u] = -1, pos[u] = -1;
+            if (i < total) {
+                jj[u] = i / chunks, cc[u] = i - jj[u] * chunks;
+                pos[u] = ld_state(ex_pos + jj[u]), fill[u] = ld_state(ex_fill + jj[u]);
+                if (scratch) hv[u] = buf[((size_t)pos[u] * L + l) * chunks + cc[u]];
+                if (fill[u] >= 0) fv[u] = buf[((size_t)fill[u] * L + l) * chunks + cc[u]];
             }
         }
-        for (; b < n_prev; ++b) {
-            const int d = dest[b];
-            const T v = buf[((size_t)b * L + l) * chunks + c];
-            if (d >= 0) {
-                if (d != b) buf[((size_t)d * L + l) * chunks + c] = v;
-            } else if (scratch) {
-                scratch[((size_t)exit_slot[-d - 1] * L + l) * chunks + c] = v;
-            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (pos[u] < 0) continue;
+            if (scratch) scratch[((size_t)ld_state(exit_slot + jj[u]) * L + l) * chunks + cc[u]] = hv[u];
+            if (fill[u] >= 0) buf[((size_t)pos[u] * L + l) * chunks + cc[u]] = fv[u];
         }
     }
 }
-__global__ void __launch_bounds__(128) ee_move_kernel(EeBufList bufs, int nbuf, __nv_bfloat16* __restrict__ xe,
+__global__ void __launch_bounds__(128) ee_move_kernel(const __grid_constant__ EeBufList bufs, int nbuf, __nv_bfloat16* __restrict__ xe,
                                                       float2* __restrict__ stats, float2* __restrict__ stats_e,
                                                       int np, const int* __restrict__ ee_n,
-                                                      const int* __restrict__ dest,
+                                                      const int* __restrict__ ex_pos, const int* __restrict__ ex_fill,
                                                       const int* __restrict__ exit_slot, int L, int D) {
     pdl_launch_dependents();
     pdl_wait();
-    if (ee_n[2] == 0) return;  // nobody left at this layer
-    const int n_prev = ee_n[4];
-    const int l = blockIdx.x;
-    if ((int)blockIdx.y == nbuf) {
-        ee_move_rows<float2>(stats, stats_e, np, dest, exit_slot, n_prev, L, l);
-        return;
+    const int n_exit = ld_state(ee_n + 2);
+    if (n_exit == 0) return;  // nobody left at this layer
+    for (int l = blockIdx.x; l < L; l += gridDim.x) {
+        if ((int)blockIdx.y == nbuf)
+            ee_move_rows<float2>(stats, stats_e, np, ex_pos, ex_fill, exit_slot, n_exit, L, l);
+        else
+            ee_move_rows<uint4>(reinterpret_cast<uint4*>(bufs.p[blockIdx.y]),
+                                blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, ex_pos, ex_fill,
+                                exit_slot, n_exit, L, l);
     }
-    ee_move_rows<uint4>(reinterpret_cast<uint4*>(bufs.p[blockIdx.y]),
-                        blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, dest, exit_slot, n_prev, L, l);
 }
 
 }  // namespace ddb

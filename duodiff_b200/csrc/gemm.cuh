@@ -78,6 +78,9 @@ struct GemmArgs {
     // [depth][64]; stats is indexed by b * L + token.
     const int* grp_layer;
     int grp_depth, grp_B;
+    // EPI_DECODE after early-exit compaction: compact sample j is un-patchified into image slot dec_slot[j] (its original
+    // position in the batch), so the stayers' and the leavers' decodes fill one image buffer
+    const int* dec_slot;
 };
 
 template <int BN>
@@ -146,14 +149,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
 
     pdl_launch_dependents();
-    if (a.m_dev) pdl_wait();
-    const int M = a.m_dev ? *a.m_dev : a.M;
-    const int nblk_n = a.N / BN;
-    const int nblk_m = (M + Cfg::BM - 1) / Cfg::BM;
     // grouped decode: tiles = (sample, 128-row block of its tokens)
     const bool kGrouped = (EPI == EPI_DECODE) && a.grp_layer != nullptr;
     const int grp_tps = (a.L + Cfg::BM - 1) / Cfg::BM;
-    const int num_tiles = kGrouped ? a.grp_B * grp_tps : nblk_m * nblk_n;
     const int nkb0 = a.K0 / Cfg::BK;
     const int nkb = nkb0 + a.K1 / Cfg::BK;
 
@@ -182,6 +180,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();
+    // the live row count (early-exit compaction) is an earlier kernel's output: read after the wait, set-up before it
+    const int M = a.m_dev ? ld_state(a.m_dev) : a.M;
+    const int nblk_n = a.N / BN;
+    const int nblk_m = (M + Cfg::BM - 1) / Cfg::BM;
+    const int num_tiles = kGrouped ? a.grp_B * grp_tps : nblk_m * nblk_n;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 int grp_b = 0, grp_l = 0;
                 if (kGrouped) {
                     grp_b = tile / grp_tps;
-                    grp_l = __ldg(a.grp_layer + grp_b);
+                    grp_l = ld_state(a.grp_layer + grp_b);
                     if (grp_l >= a.grp_depth) continue;  // every role skips the same tiles
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             uint32_t phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                if (kGrouped && __ldg(a.grp_layer + tile / grp_tps) >= a.grp_depth) continue;
+                if (kGrouped && ld_state(a.grp_layer + tile / grp_tps) >= a.grp_depth) continue;
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 ++it;
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
             int grp_b = 0, grp_l = 0, grp_tok = 0;
             if (kGrouped) {
                 grp_b = tile / grp_tps;
-                grp_l = __ldg(a.grp_layer + grp_b);
+                grp_l = ld_state(a.grp_layer + grp_b);
                 if (grp_l >= a.grp_depth) continue;
                 grp_tok = (tile % grp_tps) * Cfg::BM + row_in_tile;
             }
@@ -409,7 +412,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tcgen05_kernel(const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[as]);
                 if (row_ok) {
-                    const int b = kGrouped ? grp_b : row / a.L, l = kGrouped ? grp_tok : row % a.L;
+                    const int b = kGrouped ? grp_b : (a.dec_slot ? ld_state(a.dec_slot + row / a.L) : row / a.L);
+                    const int l = kGrouped ? grp_tok : row % a.L;
                     const int voff = grp_l * 64;  // grouped: this sample's head in the stacked bias / colsum vectors
                     if (l >= a.extras) {
                         const int n = l - a.extras;

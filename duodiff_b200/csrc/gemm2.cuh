@@ -80,11 +80,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
     // PDL: the set-up below (barriers, TMEM, descriptor prefetch, cluster sync) overlaps the predecessor's tail
     pdl_launch_dependents();
-    if (a.m_dev) pdl_wait();  // the live row count is written by an earlier kernel of the step
-    const int M = a.m_dev ? *a.m_dev : a.M;
-    const int nblk_n = a.N / BN;
-    const int nblk_m = (M + 255) / 256;
-    const int num_tiles = nblk_m * nblk_n;
     const int nkb0 = a.K0 / Cfg::BK;
     const int nkb = nkb0 + a.K1 / Cfg::BK;
 
@@ -117,6 +112,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     pdl_wait();  // everything below reads or overwrites buffers of earlier kernels
+    // (the live row count of the early-exit compaction is one of them: read it only now, so that the set-up above still
+    // overlaps the predecessor's tail -- reading it first cost every kernel of the compacted step ~1 us)
+    const int M = a.m_dev ? ld_state(a.m_dev) : a.M;
+    const int nblk_n = a.N / BN;
+    const int nblk_m = (M + 255) / 256;
+    const int num_tiles = nblk_m * nblk_n;
 
     if (warp == kProducerWarp) {
         // ===================================================================== TMA producer (both CTAs)

@@ -9,6 +9,15 @@
 
 namespace ddb {
 
+// Device-side step state -- the live sample / row counts of the early-exit compaction, slot maps, exit indices, the
+// step counter -- is rewritten by one kernel of a step and read by the next.  With programmatic dependent launch the
+// reader's CTAs are resident BEFORE the writer has finished: if anything on the same SM reads the line in that window
+// (the writer itself, e.g. ee_decide_kernel reading ee_n[0] before its last CTA rewrites ee_n[2]), the reader's load
+// after griddepcontrol.wait hits the stale L1 line (seen on B200: ee_move_kernel read n_exit = 0 and skipped the move).
+// All such state is therefore read through L2.
+__device__ __forceinline__ int ld_state(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) { return __ldcg(p); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -438,27 +438,40 @@ def test_ee_compaction_equals_simulation(dev, name, B, scale):
         assert i.eq(0).all() and rel_l2(e, r_outs[0]) <= EPS_REL_L2
 
 
-def test_ee_sampler_compact_mode_matches_simulate(dev):
+@pytest.mark.parametrize("name", ["cifar10", "imagenet256_3"])
+def test_ee_sampler_compact_mode_matches_simulate(dev, name):
     """eesampler.get_samples(mode=1): same samples and the same indices log as mode 0 (bit-exact), over a window that
-    contains many exits; the batch-mean probe log is taken over the samples still in the batch (documented)."""
+    contains many exits; the batch-mean probe log is taken over the samples still in the batch (documented).  Mode 1
+    runs the FUSED step (stayers + leavers decoded into one image buffer, step tail with per-sample conv weights, head
+    of the next step prepared by the tail); with ee_fuse = 0 it runs the stand-alone kernels: all three must agree."""
     import duodiff_b200 as ddb
     from duodiff_b200 import eesampler as ES
+    lib, L = _lib()
     torch.manual_seed(8)
-    net = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["cifar10"]), "mlp_probe_per_layer")
+    cfg = CONFIGS[name]
+    depth, C, H = cfg["depth"], cfg["in_chans"], cfg["img_size"]
+    net = ddb.EarlyExitUViT(ddb.UViT(**cfg), "mlp_probe_per_layer")
     heat_(net, 9)
-    _spread_probes(net, 13)
+    _spread_probes(net, depth)
     net = net.eval().to(dev)
     B, thr = 5, 0.4
     g = torch.Generator().manual_seed(6)
-    noise = torch.randn(1000, B, 3, 32, 32, generator=g)
-    kw = dict(seed=1, num_channels=3, sample_height=32, sample_width=32, threshold=thr, depth=13, noise=noise)
+    noise = torch.randn(1000, B, C, H, H, generator=g)
+    y = torch.randint(0, cfg["num_classes"], (B,), generator=g).to(dev) if cfg["num_classes"] > 0 else None
+    kw = dict(seed=1, num_channels=C, sample_height=H, sample_width=H, threshold=thr, depth=depth, noise=noise, y=y)
     s0, err0, idx0 = ES.get_samples(net, B, mode=0, **kw)
     s1, err1, idx1 = ES.get_samples(net, B, mode=1, **kw)
-    assert np.array_equal(s0, s1)
-    assert torch.equal(idx0, idx1)
-    assert idx1.min() < 13, "no early exits happened: the test would not exercise compaction"
-    assert err1.shape == (1000, 13)
-    full = (idx0 >= 12).all(dim=1)  # steps where nobody left before the last probe: the two logs coincide
+    lib.check(L.ddb_set_option(b"ee_fuse", 0))
+    try:
+        s2, err2, idx2 = ES.get_samples(net, B, mode=1, **kw)
+    finally:
+        lib.check(L.ddb_set_option(b"ee_fuse", 1))
+    assert np.array_equal(s0, s1) and np.array_equal(s1, s2)
+    assert torch.equal(idx0, idx1) and torch.equal(idx1, idx2)
+    assert torch.equal(torch.nan_to_num(err1, nan=-1.0), torch.nan_to_num(err2, nan=-1.0))
+    assert idx1.min() < depth, "no early exits happened: the test would not exercise compaction"
+    assert err1.shape == (1000, depth)
+    full = (idx0 >= depth - 1).all(dim=1)  # steps where nobody left before the last probe: the two logs coincide
     if full.any():
         assert torch.allclose(err0[full], err1[full], atol=1e-6)
 

@@ -5,7 +5,8 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from duodiff_b200 import _lib
-Lb = _lib.load()
+import os
+Lb = _lib.load(os.environ.get("DDB_LIB"))  # DDB_LIB=build/lib_x.so: trace an A/B build
 dev = torch.device("cuda:0")
 B, L, H = 128, 257, 8
 D = H * 64
