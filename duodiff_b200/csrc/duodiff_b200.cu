@@ -1127,7 +1127,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                 // statistics); the leavers' rows and statistics go to the scratch batch at their ORIGINAL slot -- their
                 // heads run once, after the last block
                 if (!(eed & 1))
-                    CUDA_TRY(launch_pdl(ee_move_kernel, dim3(EE_MOVE_GRID, m->ee_live_n[i] + 1), dim3(128), 0, st, m->ee_live[i],
+                    CUDA_TRY(launch_pdl(ee_move_kernel, dim3(EE_MOVE_GRID, m->ee_live_n[i] + 1), dim3(256), 0, st, m->ee_live[i],
                                         m->ee_live_n[i], m->xe->as<__nv_bfloat16>(), st_cur, m->stats_e->as<float2>(), np_cur,
                                         (const int*)een, (const int*)m->ee_dest->as<int>(),
                                         (const int*)(m->ee_dest->as<int>() + c.max_batch),

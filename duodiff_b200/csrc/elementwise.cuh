@@ -812,56 +812,71 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
 // LayerNorm statistics (np float2 each).  grid = (EE_MOVE_GRID, nbuf + 1): a CTA walks the tokens l = blockIdx.x,
 // + gridDim.x, ... of every moved row (a small grid: at most layers nobody leaves and the launch is a no-op whose cost
 // is draining its CTAs); a work item is one 16-byte chunk.  Sources (positions >= n_keep) and destinations (< n_keep) are disjoint, and the thread that
-// overwrites a hole is the one that saved its old content first.
+// overwrites a hole is the one that saved its old content first.  256 threads x 8 work items per round keep enough
+// loads in flight for the big events (most of a 128-sample batch leaving at one layer: 67 MB through one launch).
 constexpr int EE_MAX_LIVE = 16;
 constexpr int EE_MOVE_GRID = 64;
 struct EeBufList {
     __nv_bfloat16* p[EE_MAX_LIVE];
 };
+// s_pos / s_fill / s_slot: the CTA's shared-memory copy of the plan (one L2 round trip per CTA instead of three
+// dependent ones per work item)
 template <typename T>
-__device__ __forceinline__ void ee_move_rows(T* buf, T* scratch, int chunks, const int* __restrict__ ex_pos,
-                                             const int* __restrict__ ex_fill, const int* __restrict__ exit_slot,
-                                             int n_exit, int L, int l) {
+__device__ __forceinline__ void ee_move_rows(T* buf, T* scratch, int chunks, const int* s_pos, const int* s_fill,
+                                             const int* s_slot, int n_exit, int L, int l) {
+    constexpr int NB = 8;  // work items per thread and round: up to 16 loads in flight, then the stores
     const int total = n_exit * chunks;
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
-        T hv[4], fv[4];
-        int pos[4], fill[4], cc[4], jj[4];
-        // all loads first (up to eight in flight per thread), then the stores
+    for (int i0 = threadIdx.x; i0 < total; i0 += NB * blockDim.x) {
+        T hv[NB], fv[NB];
+        int pos[NB], fill[NB], cc[NB], jj[NB];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const int i = i0 + u * blockDim.x;
             fill[u] = -1, pos[u] = -1;
             if (i < total) {
                 jj[u] = i / chunks, cc[u] = i - jj[u] * chunks;
-                pos[u] = ld_state(ex_pos + jj[u]), fill[u] = ld_state(ex_fill + jj[u]);
+                pos[u] = s_pos[jj[u]], fill[u] = s_fill[jj[u]];
                 if (scratch) hv[u] = buf[((size_t)pos[u] * L + l) * chunks + cc[u]];
                 if (fill[u] >= 0) fv[u] = buf[((size_t)fill[u] * L + l) * chunks + cc[u]];
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < NB; ++u) {
             if (pos[u] < 0) continue;
-            if (scratch) scratch[((size_t)ld_state(exit_slot + jj[u]) * L + l) * chunks + cc[u]] = hv[u];
+            if (scratch) scratch[((size_t)s_slot[jj[u]] * L + l) * chunks + cc[u]] = hv[u];
             if (fill[u] >= 0) buf[((size_t)pos[u] * L + l) * chunks + cc[u]] = fv[u];
         }
     }
 }
-__global__ void __launch_bounds__(128) ee_move_kernel(const __grid_constant__ EeBufList bufs, int nbuf, __nv_bfloat16* __restrict__ xe,
-                                                      float2* __restrict__ stats, float2* __restrict__ stats_e,
-                                                      int np, const int* __restrict__ ee_n,
-                                                      const int* __restrict__ ex_pos, const int* __restrict__ ex_fill,
+__global__ void __launch_bounds__(256) ee_move_kernel(const __grid_constant__ EeBufList bufs, int nbuf,
+                                                      __nv_bfloat16* __restrict__ xe, float2* __restrict__ stats,
+                                                      float2* __restrict__ stats_e, int np,
+                                                      const int* __restrict__ ee_n, const int* __restrict__ ex_pos,
+                                                      const int* __restrict__ ex_fill,
                                                       const int* __restrict__ exit_slot, int L, int D) {
+    __shared__ int s_pos[EE_MAX_BATCH], s_fill[EE_MAX_BATCH], s_slot[EE_MAX_BATCH];
     pdl_launch_dependents();
     pdl_wait();
     const int n_exit = ld_state(ee_n + 2);
     if (n_exit == 0) return;  // nobody left at this layer
+    const bool is_stats = (int)blockIdx.y == nbuf;
+    const bool to_scratch = is_stats || blockIdx.y == 0;
+    bool any_fill = false;
+    for (int j = threadIdx.x; j < n_exit; j += blockDim.x) {
+        s_pos[j] = ld_state(ex_pos + j), s_slot[j] = ld_state(exit_slot + j);
+        const int f = ld_state(ex_fill + j);
+        s_fill[j] = f;
+        any_fill |= f >= 0;
+    }
+    // a skip buffer with no hole to fill has nothing to do (e.g. the whole batch left)
+    if (!__syncthreads_or(any_fill) && !to_scratch) return;
     for (int l = blockIdx.x; l < L; l += gridDim.x) {
-        if ((int)blockIdx.y == nbuf)
-            ee_move_rows<float2>(stats, stats_e, np, ex_pos, ex_fill, exit_slot, n_exit, L, l);
+        if (is_stats)
+            ee_move_rows<float2>(stats, stats_e, np, s_pos, s_fill, s_slot, n_exit, L, l);
         else
             ee_move_rows<uint4>(reinterpret_cast<uint4*>(bufs.p[blockIdx.y]),
-                                blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, ex_pos, ex_fill,
-                                exit_slot, n_exit, L, l);
+                                blockIdx.y == 0 ? reinterpret_cast<uint4*>(xe) : nullptr, D / 8, s_pos, s_fill, s_slot,
+                                n_exit, L, l);
     }
 }
 
