@@ -377,11 +377,11 @@ def test_ee_forward_matches_oracle(dev, hot):
                                           # deediff_imagenet64.yaml (depth 17: 9 live buffers before block 8) and
                                           # deediff_imagenet256.yaml (depth 21: 11 live buffers) -- EE_MAX_LIVE = 16
                                           ("imagenet64", 4, 2.0), ("imagenet256", 3, 2.0),
-                                          # BASELINE batch: ee_decide's single 1024-thread CTA and the in-place
-                                          # compaction at 128 samples
+                                          # BASELINE batch: the multi-CTA decision and the swap compaction at 128
+                                          # samples
                                           ("celeba", 128, 4.0)])
 def test_ee_compaction_equals_simulation(dev, name, B, scale):
-    """mode 1 (leavers are squeezed out of the batch, later kernels run on fewer rows) must give every sample the
+    """mode 1 (leavers are replaced by stayers from the end of the batch, later kernels run on fewer rows) must give every sample the
     same eps and exit index as mode 0 (the reference's evaluate-everything semantics) -- bit for bit, because every
     kernel is batch-invariant -- and both must agree with the oracle's selection."""
     import duodiff_b200 as ddb
