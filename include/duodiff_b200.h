@@ -141,7 +141,7 @@ int ddb_sampler_run_list(ddb_sampler* s, float* x_dev, const int64_t* y_dev, con
 /* samples = (x + 1) / 2, NCHW -> NHWC (sampler.py:145-146). */
 int ddb_finalize_nhwc(const float* x_dev, float* out_dev, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
 /* Process-wide runtime switches for A/B measurements (DESIGN.md lists them): "alt_dir", "attn_discard", "pdl",
- * "mlp_split", "l2_hints", ...; the measured-and-rejected kernel variants ("gemm_variant" = 1, "gemm_ts", "attn_x2",
+ * "attn_token", "ee_fuse", "mlp_split", "l2_hints", ...; the measured-and-rejected kernel variants ("gemm_variant" = 1, "gemm_ts", "attn_x2",
  * "gemm_bn128", "gemm_ln_cfg") exist only in libraries built with DDB_EXPERIMENTAL=1 (ddb_version() then ends in
  * "+experimental"); selecting one in a product build fails with DDB_ERR_INVALID.  Captured step graphs are
  * re-captured after any change. */
