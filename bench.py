@@ -140,13 +140,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm, mx, reasons, power = [], 0, set(), 0.0
+        sm, mx, reasons, power, watts = [], 0, set(), 0.0, []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
                 power = max(power, float(r[6]))
+                watts.append(float(r[6]))
             except (ValueError, IndexError):
                 continue
             for n, v in zip(names, r[2:6]):
@@ -154,7 +155,8 @@ class ClockSampler:
                     reasons.add(n)
         busy = [c for c in sm if c > 0]
         return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=mx or None,
-                    reasons=sorted(reasons), power_w_max=power or None, samples=len(sm))
+                    reasons=sorted(reasons), power_w_max=power or None,
+                    power_w_median=statistics.median(watts) if watts else None, samples=len(sm))
 
 
 # ------------------------------------------------------------------------------------------------ reference (CPU) arm
