@@ -534,7 +534,15 @@ struct ddb_model {
     std::vector<BlockW> blocks;
     HeadW final_head;
     std::vector<HeadW> ee_heads;
-    std::vector<Buf> probe_w, probe_b;
+    // MLP probes (models/early_exit.py:31-37, 194-204).  The kernels read the probe of layer i from the working set
+    // probe_w [depth][D] / probe_b [depth].  probe_kind 1 (mlp_probe_per_layer): the working set IS the parameters.
+    // 2 (mlp_probe_per_timestep: matrix["t"]) and 3 (mlp_probe_per_layer_per_timestep: matrix["i, t"]): the parameters
+    // live in probe_tab_w [1000 (x depth)][D] / probe_tab_b and probe_select_kernel copies the depth rows of the current
+    // timestep into the working set at the start of every forward (t from device memory: graph-replay safe).
+    int probe_kind = 0;
+    Buf probe_w, probe_b, probe_tab_w, probe_tab_b;
+    float* pw(int i) const { return probe_w->as<float>() + (size_t)i * D; }
+    float* pb(int i) const { return probe_b->as<float>() + i; }
     // workspace
     Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_p, scores, outputs, exit_idx;
     // early-exit compaction (mode 1): device-side live counts, slot maps, gather lists, scratch batch of leavers
@@ -755,21 +763,46 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     DDB_TRY(load_head(m, tm, up, m->final_head));
     if (cfg->early_exit) {
         m->ee_heads.resize(cfg->depth);
-        m->probe_w.resize(cfg->depth), m->probe_b.resize(cfg->depth);
+        m->probe_kind = cfg->early_exit;
+        if (m->probe_kind < 1 || m->probe_kind > 3)
+            return fail(DDB_ERR_INVALID, "early_exit must be 0 (plain), 1 (mlp_probe_per_layer), 2 (mlp_probe_per_timestep) "
+                                         "or 3 (mlp_probe_per_layer_per_timestep)");
+        DDB_TRY(new_buf(m->probe_w, (size_t)cfg->depth * D * 4));
+        DDB_TRY(new_buf(m->probe_b, (size_t)cfg->depth * 4));
+        auto load_probe = [&](const std::string& key, float* w_dst, float* b_dst) -> int {
+            const float *w, *b;
+            const std::string pp = "matrix." + key + ".classifier.0.";
+            DDB_TRY(get_tensor(tm, pp + "weight", D, &w));
+            DDB_TRY(get_tensor(tm, pp + "bias", 1, &b));
+            CUDA_TRY(cudaMemcpyAsync(w_dst, w, (size_t)D * 4, cudaMemcpyDeviceToDevice, 0));
+            CUDA_TRY(cudaMemcpyAsync(b_dst, b, 4, cudaMemcpyDeviceToDevice, 0));
+            return DDB_OK;
+        };
+        if (m->probe_kind > 1) {
+            const int n = m->probe_kind == 2 ? 1000 : 1000 * cfg->depth;
+            DDB_TRY(new_buf(m->probe_tab_w, (size_t)n * D * 4));
+            DDB_TRY(new_buf(m->probe_tab_b, (size_t)n * 4));
+            for (int t = 0; t < 1000; ++t) {
+                if (m->probe_kind == 2) {
+                    DDB_TRY(load_probe(std::to_string(t), m->probe_tab_w->as<float>() + (size_t)t * D,
+                                       m->probe_tab_b->as<float>() + t));
+                } else {
+                    for (int i = 0; i < cfg->depth; ++i) {
+                        const size_t r = (size_t)t * cfg->depth + i;  // row of matrix["i, t"]
+                        DDB_TRY(load_probe(std::to_string(i) + ", " + std::to_string(t),
+                                           m->probe_tab_w->as<float>() + r * D, m->probe_tab_b->as<float>() + r));
+                    }
+                }
+            }
+        }
         for (int i = 0; i < cfg->depth; ++i) {
             std::string hp = i < half    ? "in_blocks_heads." + std::to_string(i) + "."
                              : i == half ? std::string("mid_block_head.")
                                          : "out_blocks_heads." + std::to_string(i - half - 1) + ".";
             DDB_TRY(load_head(m, tm, hp, m->ee_heads[i]));
-            const float *w, *b;
-            const std::string pp = "matrix." + std::to_string(i) + ".classifier.0.";
-            DDB_TRY(get_tensor(tm, pp + "weight", D, &w));
-            DDB_TRY(get_tensor(tm, pp + "bias", 1, &b));
-            DDB_TRY(new_buf(m->probe_w[i], (size_t)D * 4));
-            DDB_TRY(new_buf(m->probe_b[i], 4));
-            CUDA_TRY(cudaMemcpy(m->probe_w[i]->p, w, (size_t)D * 4, cudaMemcpyDeviceToDevice));
-            CUDA_TRY(cudaMemcpy(m->probe_b[i]->p, b, 4, cudaMemcpyDeviceToDevice));
+            if (m->probe_kind == 1) DDB_TRY(load_probe(std::to_string(i), m->pw(i), m->pb(i)));
         }
+        CUDA_TRY(cudaStreamSynchronize(0));
     }
     // ---- workspace
     const size_t act = (size_t)m->Mpad * D * 2;
@@ -1040,7 +1073,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
     auto run_gemm = [&](GemmArgs g, int epi, int cat, bool ln_in, bool stats_out) -> int {
         g.M = M;
         if (probe_layer >= 0) {
-            g.probe_w = m->probe_w[probe_layer]->as<float>();
+            g.probe_w = m->pw(probe_layer);
             g.probe_out = m->probe_p->as<float>();
         }
         if (g_alt_dir && pair && epi != EPI_DECODE) {
@@ -1060,6 +1093,15 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
     kind = (pair && m->Np == 256) ? 2 : (ee ? 0 : 1);  // statistics of x0 were written by the token assembly
+    if (ee && m->probe_kind > 1) {
+        // timestep-indexed probes: this step's depth probes -> working set (t = int(timesteps[0]), early_exit.py:269)
+        ProfScope ps(PC_EE_OTHER);
+        CUDA_TRY(launch_pdl(probe_select_kernel, dim3(c.depth), dim3(128), 0, st,
+                            (const float*)m->probe_tab_w->as<float>(), (const float*)m->probe_tab_b->as<float>(),
+                            m->probe_w->as<float>(), m->probe_b->as<float>(), (int)c.depth, D, m->probe_kind, t,
+                            cp ? cp->t_dev : (const int*)nullptr));
+        LAUNCH_CHECK();
+    }
     if (cp) {
         ProfScope ps(PC_EE_OTHER);
         const int n = std::max(B, c.depth * B);
@@ -1103,7 +1145,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             // probe's partial dot products were written by the fc2 epilogue that produced it; only the first layer (and the
             // single-CTA GEMM variant) needs a pass of its own over the activations.
             if (!probe_ready && !(eed & 8)) {
-                DDB_TRY(launch_ln_stats(cur, M, D, cp ? een + 1 : nullptr, st2, m->probe_w[i]->as<float>(),
+                DDB_TRY(launch_ln_stats(cur, M, D, cp ? een + 1 : nullptr, st2, m->pw(i),
                                         m->probe_p->as<float>(), st));
                 if (kind != 2) kind = 1;  // the token assembly's partial statistics of x0 stay in force (CTA-pair path)
             }
@@ -1117,7 +1159,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                 ProfScope ps(PC_EE_OTHER);
                 if (!(eed & 2))
                     CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
-                                        np_p, (const float*)m->probe_b[i]->as<float>(), m->L, cp->threshold, i, B,
+                                        np_p, (const float*)m->pb(i), m->L, cp->threshold, i, B,
                                         (int)c.depth, een, m->ee_slot->as<int>(), m->ee_dest->as<int>(),
                                         m->ee_dest->as<int>() + c.max_batch, m->ee_exit_slot->as<int>(), m->scores->as<float>(), cp->exit_idx, cp->t_dev,
                                         cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
@@ -1139,7 +1181,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             {
                 ProfScope ps(PC_EE_OTHER);
                 CUDA_TRY(launch_pdl(probe_mean_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
-                                    np_p, (const float*)m->probe_b[i]->as<float>(), m->L,
+                                    np_p, (const float*)m->pb(i), m->L,
                                     m->scores->as<float>() + (size_t)i * B));
                 LAUNCH_CHECK();
             }

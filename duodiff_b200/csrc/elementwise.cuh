@@ -570,6 +570,21 @@ __global__ void finalize_nhwc_kernel(const float* __restrict__ x, float* __restr
 // =====================================================================================================
 // Early exit (eesampler.py:62-72): probe score per (layer, sample) = mean over tokens of the per-token sigmoid.
 // =====================================================================================================
+// timestep-indexed probe types (models/early_exit.py:199-202, 228-239): layer i of a forward at timestep t uses
+// matrix["t"] (kind 2) or matrix["i, t"] (kind 3, row t * depth + i of the table).  grid = depth, any block size.
+__global__ void probe_select_kernel(const float* __restrict__ tab_w, const float* __restrict__ tab_b,
+                                    float* __restrict__ work_w, float* __restrict__ work_b, int depth, int D, int kind,
+                                    const float* __restrict__ tsteps, const int* __restrict__ t_dev) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x;
+    int t = t_dev ? ld_state(t_dev) : (int)tsteps[0];  // int(timesteps[0]) (early_exit.py:269)
+    t = min(max(t, 0), 999);
+    const size_t r = kind == 2 ? (size_t)t : (size_t)t * depth + i;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) work_w[(size_t)i * D + k] = tab_w[r * D + k];
+    if (threadIdx.x == 0) work_b[i] = tab_b[r];
+}
+
 // per-token probe output sigmoid(w.x + b) from the row's np partial dot products (fixed summation order)
 __device__ __forceinline__ float probe_token(const float* __restrict__ pp, size_t row, int np, float bias) {
     float d = 0.f;

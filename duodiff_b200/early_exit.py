@@ -1,7 +1,9 @@
 """Drop-in for the reference's ``models/early_exit.py`` interface: ``EarlyExitUViT(uvit, classifier_type, exit_threshold)``
 with the checkpoint layout of SURVEY.md Q16 (``uvit.*``, ``matrix.{i}.classifier.0.*``, ``in_blocks_heads.*``,
 ``mid_block_head.*``, ``out_blocks_heads.*``) and ``forward -> (eps, [probe_i], [head_output_i])``
-(models/early_exit.py:268-320).  Only ``mlp_probe_per_layer`` (the type of every configs/deediff_*.yaml) has kernels.
+(models/early_exit.py:268-320).  The three MLP probe layouts are supported -- ``mlp_probe_per_layer`` (the type of
+every configs/deediff_*.yaml), ``mlp_probe_per_timestep`` and ``mlp_probe_per_layer_per_timestep``
+(models/early_exit.py:194-239: ``matrix["i"]``, ``matrix["t"]``, ``matrix["i, t"]``); ``attention_probe`` is not.
 """
 from __future__ import annotations
 
@@ -29,18 +31,32 @@ class MLPProbe(nn.Module):  # models/early_exit.py:31-34
         self.classifier = nn.Sequential(nn.Linear(embed_dim, 1), nn.Sigmoid())
 
 
+# classifier_type -> ddb_uvit_config.early_exit (include/duodiff_b200.h)
+PROBE_KINDS = {"mlp_probe_per_layer": 1, "mlp_probe_per_timestep": 2, "mlp_probe_per_layer_per_timestep": 3}
+
+
+def probe_keys(classifier_type: str, depth: int) -> list[str]:
+    """Keys of ``EarlyExitUViT.matrix`` in the reference's construction order (models/early_exit.py:217-239)."""
+    if classifier_type == "mlp_probe_per_layer":
+        return [f"{i}" for i in range(depth)]
+    if classifier_type == "mlp_probe_per_timestep":
+        return [f"{t}" for t in range(1000)]
+    if classifier_type == "mlp_probe_per_layer_per_timestep":
+        return [f"{i}, {t}" for t in range(1000) for i in range(depth)]
+    raise NotImplementedError(
+        f"classifier_type={classifier_type!r}: the MLP probe layouts {sorted(PROBE_KINDS)} are on the B200 path; "
+        "'attention_probe' (models/early_exit.py:40-80; no shipped config uses it) is out of scope")
+
+
 class EarlyExitUViT(nn.Module):
     def __init__(self, uvit: UViT, classifier_type="attention_probe", exit_threshold=0.2):
         super().__init__()
-        if classifier_type != "mlp_probe_per_layer":
-            raise NotImplementedError(
-                f"classifier_type={classifier_type!r}: only 'mlp_probe_per_layer' (configs/deediff_*.yaml) is on "
-                "the B200 path; the other probe variants are out of scope (SURVEY.md §2.1)")
+        keys = probe_keys(classifier_type, uvit.depth)
         self.uvit = uvit
         self.exit_threshold = exit_threshold
         self.classifier_type = classifier_type
         d, half = uvit.embed_dim, uvit.depth // 2
-        self.matrix = nn.ModuleDict({f"{i}": MLPProbe(d) for i in range(uvit.depth)})
+        self.matrix = nn.ModuleDict({k: MLPProbe(d) for k in keys})
         head = lambda: OutputHead(d, uvit.patch_dim, uvit.in_chans)  # noqa: E731
         self.in_blocks_heads = nn.ModuleList([head() for _ in range(half)])
         self.mid_block_head = head()
@@ -57,7 +73,7 @@ class EarlyExitUViT(nn.Module):
         if self._engine is None or self._engine_key != key or self._engine.max_batch < batch:
             self._engine = None
             cap = max(batch, self.uvit.max_batch or 0)
-            self._engine = Engine(self.state_dict(), max_batch=cap, **self.uvit.engine_kwargs(early_exit=True))
+            self._engine = Engine(self.state_dict(), max_batch=cap, **self.uvit.engine_kwargs(early_exit=PROBE_KINDS[self.classifier_type]))
             self._engine_key = key
         return self._engine
 

@@ -18,12 +18,14 @@ class Engine:
 
     def __init__(self, state_dict: dict, *, img_size: int, patch_size: int, in_chans: int, embed_dim: int,
                  depth: int, num_heads: int, mlp_hidden: int, num_classes: int, normalize_timesteps: bool,
-                 early_exit: bool, max_batch: int, ln_eps: float = 1e-5):
+                 early_exit: int, max_batch: int, ln_eps: float = 1e-5):
+        """early_exit: 0 = plain U-ViT, 1 / 2 / 3 = EarlyExitUViT with MLP probes per layer / per timestep / per layer and
+        timestep (ddb_uvit_config.early_exit)."""
         if not torch.cuda.is_available():
             raise _lib.DuoDiffError("duodiff_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         self.lib = _lib.load()
         self.cfg = _lib.UViTConfig(img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_hidden,
-                                   num_classes, int(bool(normalize_timesteps)), int(bool(early_exit)), max_batch,
+                                   num_classes, int(bool(normalize_timesteps)), int(early_exit), max_batch,
                                    ln_eps)
         self.in_chans, self.img_size, self.depth, self.max_batch = in_chans, img_size, depth, max_batch
         self.early_exit = bool(early_exit)

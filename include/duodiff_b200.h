@@ -43,7 +43,10 @@ typedef struct {
     int32_t mlp_hidden;           /* int(embed_dim * mlp_ratio) */
     int32_t num_classes;          /* <= 0: unconditional (extras = 1), else class-conditional (extras = 2) */
     int32_t normalize_timesteps;  /* models/uvit.py:352-353 */
-    int32_t early_exit;           /* 1: weights carry the EarlyExitUViT prefix `uvit.` + probes + heads */
+    int32_t early_exit;           /* > 0: weights carry the EarlyExitUViT prefix `uvit.` + probes + heads; the value is
+                                   * the probe layout (models/early_exit.py:194-204): 1 mlp_probe_per_layer
+                                   * (matrix["i"]), 2 mlp_probe_per_timestep (matrix["t"], t < 1000),
+                                   * 3 mlp_probe_per_layer_per_timestep (matrix["i, t"]) */
     int32_t max_batch;            /* workspace is sized for this many samples */
     float ln_eps;                 /* nn.LayerNorm default 1e-5 */
 } ddb_uvit_config;

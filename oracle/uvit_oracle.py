@@ -155,15 +155,29 @@ def uvit_forward(sd: dict, spec: UViTSpec, x: torch.Tensor, timesteps: torch.Ten
     return output_head(sd, pfx, h, spec)
 
 
-def mlp_probe(sd: dict, i: int, x: torch.Tensor) -> torch.Tensor:
-    """models/early_exit.py:31-37 — mean over all tokens of sigmoid(Linear(D,1))."""
+def mlp_probe(sd: dict, i, x: torch.Tensor) -> torch.Tensor:
+    """models/early_exit.py:31-37 — mean over all tokens of sigmoid(Linear(D,1)); i = key of EarlyExitUViT.matrix."""
     w, b = sd[f"matrix.{i}.classifier.0.weight"], sd[f"matrix.{i}.classifier.0.bias"]
     return torch.sigmoid(F.linear(x, w, b)).mean(dim=1).squeeze()
 
 
-def ee_forward(sd: dict, spec: UViTSpec, x: torch.Tensor, timesteps: torch.Tensor, y: torch.Tensor | None = None):
-    """models/early_exit.py:268-320 (classifier_type == 'mlp_probe_per_layer') -> (eps, [cls_i], [out_i])."""
+def probe_key(classifier_type: str, i: int, t: int) -> str:
+    """models/early_exit.py:194-204 (get_classifer): which entry of ``matrix`` scores layer i at timestep t."""
+    if classifier_type == "mlp_probe_per_layer":
+        return f"{i}"
+    if classifier_type == "mlp_probe_per_timestep":
+        return f"{t}"
+    if classifier_type == "mlp_probe_per_layer_per_timestep":
+        return f"{i}, {t}"
+    raise ValueError(f"Unknown classifier type: {classifier_type}")
+
+
+def ee_forward(sd: dict, spec: UViTSpec, x: torch.Tensor, timesteps: torch.Tensor, y: torch.Tensor | None = None,
+               classifier_type: str = "mlp_probe_per_layer"):
+    """models/early_exit.py:268-320 (MLP probe types; t = int(timesteps[0]) picks the probes of the timestep-indexed
+    layouts, :269) -> (eps, [cls_i], [out_i])."""
     pfx = "uvit."
+    t_int = int(timesteps[0])
     h = embed_tokens(sd, pfx, spec, x, timesteps, y)
     half = spec.depth // 2
     head_pfx = ([f"in_blocks_heads.{i}." for i in range(half)] + ["mid_block_head."]
@@ -171,7 +185,7 @@ def ee_forward(sd: dict, spec: UViTSpec, x: torch.Tensor, timesteps: torch.Tenso
     skips, cls, outs = [], [], []
     for i, bp in enumerate(_block_prefixes(spec, pfx)):
         outs.append(output_head(sd, head_pfx[i], h, spec))
-        cls.append(mlp_probe(sd, i, h))
+        cls.append(mlp_probe(sd, probe_key(classifier_type, i, t_int), h))
         if i < half:
             h = block(sd, bp, h, None, spec.num_heads)
             skips.append(h)

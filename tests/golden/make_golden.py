@@ -212,8 +212,46 @@ def ae_decode_fixture():
     print("ae_decode", tuple(out.shape), float(out.abs().max()))
 
 
+def ee_probe_types_fixture():
+    """The two timestep-indexed MLP probe layouts (models/early_exit.py:199-202, 228-239): the reference model holds
+    1000 (x depth) probes; the fixture keeps the backbone / heads and only the probes of the timesteps it runs.  The
+    third call mixes timesteps inside the batch: int(timesteps[0]) picks the probes (early_exit.py:269)."""
+    fx = {}
+    calls = [torch.full((3,), 321.0), torch.full((3,), 7.0), torch.tensor([500.0, 3.0, 999.0])]
+    for tag, ctype in (("pt", "mlp_probe_per_timestep"), ("plt", "mlp_probe_per_layer_per_timestep")):
+        torch.manual_seed(21)
+        m = EarlyExitUViT(UViT(**TINY), ctype).eval()
+        heat(m, 22)
+        used = sorted({int(t[0]) for t in calls})
+        with torch.no_grad():
+            for k, t in enumerate(used):
+                keys = [f"{t}"] if tag == "pt" else [f"{i}, {t}" for i in range(TINY["depth"])]
+                for j, key in enumerate(keys):
+                    m.matrix[key].classifier[0].weight.mul_(6.0)
+                    m.matrix[key].classifier[0].bias.fill_(0.4 - 0.5 * j - 0.2 * k)
+        x = torch.randn(3, 3, 8, 8)
+        for c, t in enumerate(calls):
+            with torch.no_grad():
+                eps, cls, outs = m(x, t, None)
+            fx[f"{tag}::t{c}"] = t.numpy()
+            fx[f"{tag}::eps{c}"] = eps.numpy()
+            fx[f"{tag}::cls{c}"] = torch.stack(cls).numpy()
+            fx[f"{tag}::outs{c}"] = torch.stack(outs).numpy()
+        fx[f"{tag}::x"] = x.numpy()
+        keep = lambda k: not k.startswith("matrix.") or any(  # noqa: E731
+            k.startswith(f"matrix.{t}.") or k.split(".")[1].endswith(f", {t}") for t in used)
+        for k, v in m.state_dict().items():
+            if keep(k):
+                fx[f"{tag}::w::{k}"] = v.detach().numpy().copy()
+        print("ee_probe_types", ctype, torch.stack(cls).numpy().round(3).tolist())
+    np.savez_compressed(OUT / "ee_probe_types_tiny.npz", **params_np(TINY), **fx)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "probe_types":  # add the probe-layout fixture without touching the others
+        ee_probe_types_fixture()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "ae":  # add the autoencoder fixture without touching the others
         ae_decode_fixture()
         sys.exit(0)
@@ -228,3 +266,4 @@ if __name__ == "__main__":
     ddim_sampler_fixture()
     ee_sampler_fixture(ee_model)
     ae_decode_fixture()
+    ee_probe_types_fixture()

@@ -476,6 +476,56 @@ def test_ee_sampler_compact_mode_matches_simulate(dev, name):
         assert torch.allclose(err0[full], err1[full], atol=1e-6)
 
 
+@pytest.mark.parametrize("ctype", ["mlp_probe_per_timestep", "mlp_probe_per_layer_per_timestep"])
+def test_ee_timestep_indexed_probes(dev, ctype):
+    """models/early_exit.py:194-204, 228-239: matrix["t"] / matrix["i, t"], t = int(timesteps[0]).  The library keeps
+    the 1000 (x depth) probes in a device table and copies the step's probes into the working set at the start of
+    every forward (t from device memory inside the sampler's graph).  Forward vs the oracle (pinned to the reference by
+    tests/golden/ee_probe_types_tiny.npz) at two timesteps and with mixed timesteps; compact == simulate; and the
+    sampler's logs follow the timestep."""
+    import duodiff_b200 as ddb
+    from duodiff_b200 import eesampler as ES
+    torch.manual_seed(31)
+    cfg = CONFIGS["celeba_3"]
+    depth = cfg["depth"]
+    net = ddb.EarlyExitUViT(ddb.UViT(**cfg), ctype)
+    heat_(net, 32)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(cfg)
+    B = 4
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, 3, 64, 64, generator=g).to(dev)
+    eng = net.engine(B)
+    seen = []
+    for t in (torch.full((B,), 321.0), torch.full((B,), 7.0), torch.tensor([500.0, 3.0, 999.0, 42.0])):
+        t = t.to(dev)
+        with torch.no_grad():
+            r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t, None, classifier_type=ctype)
+        eps, _, cls, outs = eng.ee_forward(x, t, None, threshold=0.0, mode=0)
+        r_cls_t = torch.stack([c.reshape(-1) for c in r_cls])
+        assert (cls - r_cls_t).abs().max().item() <= PROBE_MARGIN_HOT
+        assert rel_l2(eps, r_eps) <= EPS_REL_L2
+        for i in range(depth):
+            assert rel_l2(outs[i], r_outs[i]) <= EPS_REL_L2, i
+        seen.append(cls.clone())
+        for thr in (0.3, 0.5, 0.7):
+            e0, i0, _, _ = eng.ee_forward(x, t, None, threshold=thr, mode=0)
+            e1, i1, _, _ = eng.ee_forward(x, t, None, threshold=thr, mode=1)
+            assert torch.equal(i0, i1) and torch.equal(e0, e1), (thr, i0.tolist(), i1.tolist())
+    assert (seen[0] - seen[1]).abs().max().item() > 1e-2, "the probes must depend on the timestep"
+    # sampler: the graph-replayed step picks the probes by the device-side step counter
+    noise = torch.randn(1000, B, 3, 64, 64, generator=g)
+    kw = dict(seed=2, num_channels=3, sample_height=64, sample_width=64, threshold=0.5, depth=depth, noise=noise)
+    s0, err0, idx0 = ES.get_samples(net, B, mode=0, **kw)
+    s1, _err1, idx1 = ES.get_samples(net, B, mode=1, **kw)
+    assert np.array_equal(s0, s1) and torch.equal(idx0, idx1)
+    assert idx0.min() < depth and idx0.max() == depth, "thresholds should split the steps"
+    # row t of the score log = the probes of timestep t applied to that step's activations: teacher-forced check of
+    # three rows against the oracle is covered above; here: consecutive timesteps use DIFFERENT probes
+    assert (err0[500] - err0[499]).abs().max().item() > 1e-3
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
     from duodiff_b200.ddpm import Sampler

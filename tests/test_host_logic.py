@@ -120,6 +120,15 @@ def test_state_dict_layout_matches_reference_checkpoints():
     d13 = ddb.UViT(**CONFIGS["celeba"])
     assert len(d13.state_dict()) == 164
     assert len(ddb.EarlyExitUViT(d13, "mlp_probe_per_layer").state_dict()) == 268
+    # the timestep-indexed MLP probe layouts carry the reference's ModuleDict keys (models/early_exit.py:228-239)
+    d3 = ddb.UViT(**CONFIGS["celeba_3"])
+    pt = ddb.EarlyExitUViT(d3, "mlp_probe_per_timestep").state_dict()
+    assert "matrix.999.classifier.0.weight" in pt and sum(k.startswith("matrix.") for k in pt) == 2000
+    from duodiff_b200.early_exit import probe_keys
+    keys = probe_keys("mlp_probe_per_layer_per_timestep", 3)
+    assert keys[:4] == ["0, 0", "1, 0", "2, 0", "0, 1"] and len(keys) == 3000
+    fx = load_fixture("ee_probe_types_tiny")  # key spelling as saved by the reference's own state_dict()
+    assert "plt::w::matrix.2, 321.classifier.0.bias" in fx and "pt::w::matrix.7.classifier.0.weight" in fx
 
 
 def test_unsupported_options_raise():

@@ -1,6 +1,7 @@
 """Pins oracle/ (the CPU restatement) to the reference: fixtures in tests/golden/*.npz were produced by the
 unmodified reference modules (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import uvit_oracle as O
@@ -46,6 +47,23 @@ def test_ee_forward_probes_and_heads():
     np.testing.assert_allclose(eps.numpy(), fx["eps"], atol=ATOL, rtol=1e-5)
     np.testing.assert_allclose(torch.stack(cls).numpy(), fx["cls"], atol=1e-6)
     np.testing.assert_allclose(torch.stack(outs).numpy(), fx["outs"], atol=ATOL, rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag,ctype", [("pt", "mlp_probe_per_timestep"), ("plt", "mlp_probe_per_layer_per_timestep")])
+def test_ee_forward_timestep_indexed_probes(tag, ctype):
+    """models/early_exit.py:194-204: matrix["t"] / matrix["i, t"] with t = int(timesteps[0]) -- also when the batch
+    mixes timesteps (third call of the fixture)."""
+    fx = load_fixture("ee_probe_types_tiny")
+    sd, params = split_fixture(fx, f"{tag}::w::", "p::")
+    spec = O.UViTSpec.from_params(params)
+    x = torch.from_numpy(fx[f"{tag}::x"])
+    for c in range(3):
+        eps, cls, outs = O.ee_forward(sd, spec, x, torch.from_numpy(fx[f"{tag}::t{c}"]), classifier_type=ctype)
+        np.testing.assert_allclose(eps.numpy(), fx[f"{tag}::eps{c}"], atol=ATOL, rtol=1e-5)
+        np.testing.assert_allclose(torch.stack(cls).numpy(), fx[f"{tag}::cls{c}"], atol=1e-6)
+        np.testing.assert_allclose(torch.stack(outs).numpy(), fx[f"{tag}::outs{c}"], atol=ATOL, rtol=1e-5)
+    # the probes depend on the timestep: the scores of calls 0 and 1 must differ
+    assert np.abs(fx[f"{tag}::cls0"] - fx[f"{tag}::cls1"]).max() > 1e-2
 
 
 def _replay_reference_rng(seed, shape):
