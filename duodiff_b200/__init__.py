@@ -3,7 +3,7 @@
 Host-side mirror of the reference's module surface (``UViT``, ``EarlyExitUViT``, ``sampler.get_samples``,
 ``eesampler.get_samples``) over a C-ABI CUDA library (include/duodiff_b200.h).  No CPU / PyTorch compute fallback.
 """
-from .early_exit import EarlyExitUViT, MLPProbe, OutputHead  # noqa: F401
+from .early_exit import AttentionProbe, EarlyExitUViT, MLPProbe, OutputHead  # noqa: F401
 from .uvit import UViT  # noqa: F401
 
 __all__ = ["UViT", "EarlyExitUViT", "OutputHead", "MLPProbe"]

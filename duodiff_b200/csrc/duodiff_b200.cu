@@ -539,8 +539,11 @@ struct ddb_model {
     // 2 (mlp_probe_per_timestep: matrix["t"]) and 3 (mlp_probe_per_layer_per_timestep: matrix["i, t"]): the parameters
     // live in probe_tab_w [1000 (x depth)][D] / probe_tab_b and probe_select_kernel copies the depth rows of the current
     // timestep into the working set at the start of every forward (t from device memory: graph-replay safe).
+    // 4 (attention_probe, early_exit.py:40-80): the working set holds u = Wk^T q / sqrt(D) per layer (the per-token
+    // logits then come from the same partial dot products); ap_wc [depth][D][D] = W1 Wv, ap_bc = W1 bv + b1, ap_w2, ap_b2
+    // feed attn_probe_score_kernel (elementwise.cuh).
     int probe_kind = 0;
-    Buf probe_w, probe_b, probe_tab_w, probe_tab_b;
+    Buf probe_w, probe_b, probe_tab_w, probe_tab_b, ap_wc, ap_bc, ap_w2, ap_b2;
     float* pw(int i) const { return probe_w->as<float>() + (size_t)i * D; }
     float* pb(int i) const { return probe_b->as<float>() + i; }
     // workspace
@@ -764,9 +767,9 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
     if (cfg->early_exit) {
         m->ee_heads.resize(cfg->depth);
         m->probe_kind = cfg->early_exit;
-        if (m->probe_kind < 1 || m->probe_kind > 3)
-            return fail(DDB_ERR_INVALID, "early_exit must be 0 (plain), 1 (mlp_probe_per_layer), 2 (mlp_probe_per_timestep) "
-                                         "or 3 (mlp_probe_per_layer_per_timestep)");
+        if (m->probe_kind < 1 || m->probe_kind > 4)
+            return fail(DDB_ERR_INVALID, "early_exit must be 0 (plain), 1 (mlp_probe_per_layer), 2 (mlp_probe_per_timestep), "
+                                         "3 (mlp_probe_per_layer_per_timestep) or 4 (attention_probe)");
         DDB_TRY(new_buf(m->probe_w, (size_t)cfg->depth * D * 4));
         DDB_TRY(new_buf(m->probe_b, (size_t)cfg->depth * 4));
         auto load_probe = [&](const std::string& key, float* w_dst, float* b_dst) -> int {
@@ -778,7 +781,29 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
             CUDA_TRY(cudaMemcpyAsync(b_dst, b, 4, cudaMemcpyDeviceToDevice, 0));
             return DDB_OK;
         };
-        if (m->probe_kind > 1) {
+        if (m->probe_kind == 4) {
+            DDB_TRY(new_buf(m->ap_wc, (size_t)cfg->depth * D * D * 4));
+            DDB_TRY(new_buf(m->ap_bc, (size_t)cfg->depth * D * 4));
+            DDB_TRY(new_buf(m->ap_w2, (size_t)cfg->depth * D * 4));
+            DDB_TRY(new_buf(m->ap_b2, (size_t)cfg->depth * 4));
+            for (int i = 0; i < cfg->depth; ++i) {
+                const std::string pp = "matrix." + std::to_string(i) + ".";
+                const float *q, *wkv, *bkv, *w1, *b1, *w2, *b2;
+                DDB_TRY(get_tensor(tm, pp + "q", D, &q));  // [1, num_heads = 1, 1, D]
+                DDB_TRY(get_tensor(tm, pp + "weight_kv.weight", (int64_t)2 * D * D, &wkv));
+                DDB_TRY(get_tensor(tm, pp + "weight_kv.bias", 2 * D, &bkv));
+                DDB_TRY(get_tensor(tm, pp + "classification.0.weight", (int64_t)D * D, &w1));
+                DDB_TRY(get_tensor(tm, pp + "classification.0.bias", D, &b1));
+                DDB_TRY(get_tensor(tm, pp + "classification.2.weight", D, &w2));
+                DDB_TRY(get_tensor(tm, pp + "classification.2.bias", 1, &b2));
+                attn_probe_pack_kernel<<<dim3(D, 2), 256>>>(q, wkv, bkv, w1, b1, D, m->pw(i),
+                                                            m->ap_wc->as<float>() + (size_t)i * D * D,
+                                                            m->ap_bc->as<float>() + (size_t)i * D);
+                LAUNCH_CHECK();
+                CUDA_TRY(cudaMemcpyAsync(m->ap_w2->as<float>() + (size_t)i * D, w2, (size_t)D * 4, cudaMemcpyDeviceToDevice, 0));
+                CUDA_TRY(cudaMemcpyAsync(m->ap_b2->as<float>() + i, b2, 4, cudaMemcpyDeviceToDevice, 0));
+            }
+        } else if (m->probe_kind > 1) {
             const int n = m->probe_kind == 2 ? 1000 : 1000 * cfg->depth;
             DDB_TRY(new_buf(m->probe_tab_w, (size_t)n * D * 4));
             DDB_TRY(new_buf(m->probe_tab_b, (size_t)n * 4));
@@ -1093,7 +1118,20 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         return (pair && epi != EPI_DECODE) ? launch_gemm2(g, epi, nsm, st) : launch_gemm(g, epi, nsm, st);
     };
     kind = (pair && m->Np == 256) ? 2 : (ee ? 0 : 1);  // statistics of x0 were written by the token assembly
-    if (ee && m->probe_kind > 1) {
+    // attention probes: per-sample softmax pooling of the block input + the classification MLP -> score[b]
+    auto attn_probe_score = [&](int i, const __nv_bfloat16* xin, const int* n_dev, float* out) -> int {
+        ProfScope ps(PC_EE_OTHER);
+        const size_t smem = (size_t)(m->L + D + 8) * 4;
+        CUDA_TRY(launch_pdl(attn_probe_score_kernel, dim3(B), dim3(256), smem, st, xin,
+                            (const float*)m->probe_p->as<float>(), np_p,
+                            (const float*)(m->ap_wc->as<float>() + (size_t)i * D * D),
+                            (const float*)(m->ap_bc->as<float>() + (size_t)i * D),
+                            (const float*)(m->ap_w2->as<float>() + (size_t)i * D),
+                            (const float*)(m->ap_b2->as<float>() + i), m->L, D, n_dev, out));
+        LAUNCH_CHECK();
+        return DDB_OK;
+    };
+    if (ee && (m->probe_kind == 2 || m->probe_kind == 3)) {
         // timestep-indexed probes: this step's depth probes -> working set (t = int(timesteps[0]), early_exit.py:269)
         ProfScope ps(PC_EE_OTHER);
         CUDA_TRY(launch_pdl(probe_select_kernel, dim3(c.depth), dim3(128), 0, st,
@@ -1102,11 +1140,14 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                             cp ? cp->t_dev : (const int*)nullptr));
         LAUNCH_CHECK();
     }
+    // real-valued (attention) probes with a negative threshold: a sample that never triggers takes head 0
+    // (eesampler.py:62-67), which is only known after the last layer -- every sample's layer-0 rows are kept
+    const bool neg_real = cp && m->probe_kind == 4 && cp->threshold < 0.f;
     if (cp) {
         ProfScope ps(PC_EE_OTHER);
         const int n = std::max(B, c.depth * B);
         CUDA_TRY(launch_pdl(ee_reset_kernel, dim3((n + 255) / 256), dim3(256), 0, st, een, m->ee_slot->as<int>(), B, m->L, m->scores->as<float>(),
-                                                        c.depth, cp->exit_idx, cp->t_dev, cp->exit_log));
+                                                        c.depth, neg_real ? 0 : (int)c.depth, cp->exit_idx, cp->t_dev, cp->exit_log));
         LAUNCH_CHECK();
     }
     const std::vector<ddb_model::HalfOps>* split = nullptr;
@@ -1156,6 +1197,12 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
         if (cp) {
             // leavers take head i's output and are squeezed out of every live buffer
             {
+                if (neg_real && i == 0) {  // positions == samples before the first move
+                    ProfScope ps(PC_EE_OTHER);
+                    CUDA_TRY(cudaMemcpyAsync(m->xe->p, cur, (size_t)M * D * 2, cudaMemcpyDeviceToDevice, st));
+                    CUDA_TRY(cudaMemcpyAsync(m->stats_e->p, st_cur, (size_t)M * np_cur * 8, cudaMemcpyDeviceToDevice, st));
+                }
+                if (m->probe_kind == 4) DDB_TRY(attn_probe_score(i, cur, een, m->ee_sc->as<float>()));
                 ProfScope ps(PC_EE_OTHER);
                 if (!(eed & 2))
                     CUDA_TRY(launch_pdl(ee_decide_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
@@ -1163,7 +1210,7 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
                                         (int)c.depth, een, m->ee_slot->as<int>(), m->ee_dest->as<int>(),
                                         m->ee_dest->as<int>() + c.max_batch, m->ee_exit_slot->as<int>(), m->scores->as<float>(), cp->exit_idx, cp->t_dev,
                                         cp->exit_log, cp->score_mean_log, m->ee_sc->as<float>(),
-                                        m->ee_ticket->as<unsigned>()));
+                                        m->ee_ticket->as<unsigned>(), m->probe_kind == 4 ? 1 : 0));
                 LAUNCH_CHECK();
                 // the batch stays dense: stayers from its end take the leavers' places (block input, pending long skips,
                 // statistics); the leavers' rows and statistics go to the scratch batch at their ORIGINAL slot -- their
@@ -1178,7 +1225,9 @@ static int forward_impl(ddb_model* m, const float* x, const float* t, const int6
             }
             np_exit = np_cur;
         } else if (ee) {
-            {
+            if (m->probe_kind == 4) {
+                DDB_TRY(attn_probe_score(i, cur, nullptr, m->scores->as<float>() + (size_t)i * B));
+            } else {
                 ProfScope ps(PC_EE_OTHER);
                 CUDA_TRY(launch_pdl(probe_mean_kernel, dim3(B), dim3(128), 0, st, (const float*)m->probe_p->as<float>(),
                                     np_p, (const float*)m->pb(i), m->L,

@@ -585,6 +585,115 @@ __global__ void probe_select_kernel(const float* __restrict__ tab_w, const float
     if (threadIdx.x == 0) work_b[i] = tab_b[r];
 }
 
+// =====================================================================================================
+// AttentionProbe (models/early_exit.py:40-80): one learned query attends over the tokens 1.. of the block input (the
+// first token is dropped, :73), the pooled value goes through Linear(D,D) -> SiLU -> Linear(D,1); no sigmoid.
+// Restated without the [B, L, 2D] key / value GEMM (the reference's own TODO asks for a cheaper classifier):
+//   logit_l = q.(Wk x_l + bk) / sqrt(D) = u.x_l + const     u = Wk^T q / sqrt(D): the constant cancels in the softmax
+//   pooled  = sum_l a_l (Wv x_l + bv) = Wv (sum_l a_l x_l) + bv                    (the weights a_l sum to one)
+//   score   = w2 . SiLU(W1 pooled + b1) + b2 = w2 . SiLU(Wc xbar + bc) + b2        Wc = W1 Wv, bc = W1 bv + b1
+// u sits in the probe working set, so the per-token logits arrive as the same partial dot products the MLP probes use
+// (fc2 epilogue / ln_stats_kernel); u, Wc, bc are computed once at model creation by attn_probe_pack_kernel.
+// =====================================================================================================
+// grid = (D, 2): y == 0: row j of Wc (and bc[j]); y == 1, block 0..: u.  Parameter layouts are the state_dict's.
+__global__ void __launch_bounds__(256) attn_probe_pack_kernel(const float* __restrict__ q /*[D]*/,
+                                                              const float* __restrict__ wkv /*[2D, D]*/,
+                                                              const float* __restrict__ bkv /*[2D]*/,
+                                                              const float* __restrict__ w1 /*[D, D]*/,
+                                                              const float* __restrict__ b1 /*[D]*/, int D,
+                                                              float* __restrict__ u, float* __restrict__ wc,
+                                                              float* __restrict__ bc) {
+    const int j = blockIdx.x;
+    if (blockIdx.y == 1) {  // u[j] = sum_e q[e] Wk[e][j] / sqrt(D)
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int e = 0; e < D; ++e) s = fmaf(q[e], wkv[(size_t)e * D + j], s);
+            u[j] = s * rsqrtf((float)D);
+        }
+        return;
+    }
+    const float* wv = wkv + (size_t)D * D;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int e = 0; e < D; ++e) s = fmaf(w1[(size_t)j * D + e], wv[(size_t)e * D + d], s);
+        wc[(size_t)j * D + d] = s;
+    }
+    if (threadIdx.x == 0) {
+        float s = b1[j];
+        for (int e = 0; e < D; ++e) s = fmaf(w1[(size_t)j * D + e], bkv[D + e], s);
+        bc[j] = s;
+    }
+}
+// grid = B (live samples), 256 threads, dynamic smem (L + D + 8) floats.  Fixed summation order: a sample's score does
+// not depend on its position in the batch (compact == simulate bit for bit).
+__global__ void __launch_bounds__(256) attn_probe_score_kernel(
+    const __nv_bfloat16* __restrict__ x /*[M, D] block input*/, const float* __restrict__ pp /*[M, np] u.x partials*/,
+    int np, const float* __restrict__ wc, const float* __restrict__ bc, const float* __restrict__ w2,
+    const float* __restrict__ b2, int L, int D, const int* __restrict__ n_dev, float* __restrict__ score /*[B]*/) {
+    extern __shared__ float ap_smem[];
+    float* s_a = ap_smem;          // [L] logits -> softmax weights
+    float* s_x = ap_smem + L;      // [D] pooled input row
+    float* s_red = s_x + D;        // [8]
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.x;
+    if (n_dev && b >= ld_state(n_dev)) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto block_reduce = [&](float v, bool is_max) -> float {
+        for (int o = 16; o > 0; o >>= 1) {
+            const float w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmaxf(v, w) : v + w;
+        }
+        __syncthreads();  // s_red is reused
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        float r = s_red[0];
+        for (int w = 1; w < 8; ++w) r = is_max ? fmaxf(r, s_red[w]) : r + s_red[w];
+        return r;
+    };
+    // logits of tokens 1 .. L-1 (token 0 is dropped: x[:, 1:, :], early_exit.py:73)
+    float mx = -INFINITY;
+    for (int l = 1 + tid; l < L; l += 256) {
+        float d = 0.f;
+        for (int c = 0; c < np; ++c) d += pp[((size_t)b * L + l) * np + c];
+        s_a[l] = d;
+        mx = fmaxf(mx, d);
+    }
+    mx = block_reduce(mx, true);
+    float sum = 0.f;
+    for (int l = 1 + tid; l < L; l += 256) {
+        const float e = expf(s_a[l] - mx);
+        s_a[l] = e;
+        sum += e;
+    }
+    sum = block_reduce(sum, false);
+    const float inv = 1.f / sum;
+    // xbar = sum_l a_l x_l: a thread owns column pairs, rows in increasing order
+    for (int c2 = tid; c2 < D / 2; c2 += 256) {
+        float a0 = 0.f, a1 = 0.f;
+        const uint32_t* col = reinterpret_cast<const uint32_t*>(x + (size_t)b * L * D) + c2;
+        for (int l = 1; l < L; ++l) {
+            const uint32_t v = col[(size_t)l * (D / 2)];
+            const float w = s_a[l];
+            a0 = fmaf(w, bf16_lo(v), a0);
+            a1 = fmaf(w, bf16_hi(v), a1);
+        }
+        s_x[2 * c2] = a0 * inv, s_x[2 * c2 + 1] = a1 * inv;
+    }
+    __syncthreads();
+    // h_j = SiLU(Wc[j] . xbar + bc[j]); score = w2 . h + b2: one warp per row j, lanes stride the columns
+    float part = 0.f;
+    for (int j = warp; j < D; j += 8) {
+        float d = 0.f;
+        for (int k = lane; k < D; k += 32) d = fmaf(wc[(size_t)j * D + k], s_x[k], d);
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        const float z = d + bc[j];
+        part += w2[j] * (z / (1.f + expf(-z)));  // every lane holds the same value
+    }
+    const float tot = block_reduce(lane == 0 ? part : 0.f, false);
+    if (tid == 0) score[b] = tot + b2[0];
+}
+
 // per-token probe output sigmoid(w.x + b) from the row's np partial dot products (fixed summation order)
 __device__ __forceinline__ float probe_token(const float* __restrict__ pp, size_t row, int np, float bias) {
     float d = 0.f;
@@ -673,8 +782,10 @@ __global__ void __launch_bounds__(256) ee_select_kernel(const float* __restrict_
 // head_i's output and leave the batch, so every later kernel works on M = n_active * L rows.
 // Device-side state ee_n[4] = {n_active, n_active*L, n_exit, n_exit*L}; slot[b] = original index of compact sample b.
 // =====================================================================================================
+// def_idx: the index of a sample that never triggers -- `depth` (the full model), or 0 when the threshold is negative
+// (eesampler.py:62-67: the appended zero row only matches for 0 <= threshold; argmax over an all-false mask is 0).
 __global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, int B, int L,
-                                float* __restrict__ scores, int depth, int* __restrict__ exit_idx,
+                                float* __restrict__ scores, int depth, int def_idx, int* __restrict__ exit_idx,
                                 const int* __restrict__ t_dev, int* __restrict__ exit_log) {
     pdl_launch_dependents();
     pdl_wait();
@@ -682,8 +793,8 @@ __global__ void ee_reset_kernel(int* __restrict__ ee_n, int* __restrict__ slot, 
     if (i == 0) ee_n[0] = B, ee_n[1] = B * L, ee_n[2] = 0, ee_n[3] = 0;
     if (i < B) {
         slot[i] = i;
-        exit_idx[i] = depth;
-        if (exit_log) exit_log[(size_t)(t_dev ? ld_state(t_dev) : 0) * B + i] = depth;
+        exit_idx[i] = def_idx;
+        if (exit_log) exit_log[(size_t)(t_dev ? ld_state(t_dev) : 0) * B + i] = def_idx;
     }
     if (i < depth * B) scores[i] = __int_as_float(0x7fc00000);  // NaN: "not produced" (sample had already left)
 }
@@ -706,7 +817,7 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
     int depth, int* __restrict__ ee_n, int* __restrict__ slot, int* __restrict__ ex_pos, int* __restrict__ ex_fill,
     int* __restrict__ exit_slot, float* __restrict__ scores, int* __restrict__ exit_idx,
     const int* __restrict__ t_dev, int* __restrict__ exit_log, float* __restrict__ score_mean_log,
-    float* __restrict__ sc_tmp, unsigned* __restrict__ ticket) {
+    float* __restrict__ sc_tmp, unsigned* __restrict__ ticket, int prescored) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[4];
@@ -716,7 +827,7 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
     __shared__ int is_last;
     const int n = ld_state(ee_n);  // rewritten by the last CTA only after every CTA has passed the ticket below
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    {
+    if (!prescored) {  // (attention probes are scored by attn_probe_score_kernel: sc_tmp is already filled)
         const int b = blockIdx.x;
         if (b < n) {
             const float bias = bias_p[0];
@@ -746,8 +857,11 @@ __global__ void __launch_bounds__(128) ee_decide_kernel(
         const bool live = b < n;
         sc[u] = live ? __ldcg(sc_tmp + b) : 0.f;
         myslot[u] = live ? ld_state(slot + b) : 0;
-        // threshold < 0: argmax over an all-false mask selects layer 0 for every sample (see ee_select_kernel)
-        ex[u] = (live && (sc[u] <= thr || (thr < 0.f && layer == 0))) ? 1 : 0;
+        // threshold < 0 with sigmoid probes (scores in (0, 1)): nothing ever matches, argmax over the all-false mask
+        // selects layer 0 for every sample (see ee_select_kernel) -- everybody leaves at once.  (Attention probes are
+        // real-valued: a negative threshold is an ordinary one; the forward saves every sample's layer-0 rows and
+        // makes 0 the default index instead.)
+        ex[u] = (live && (sc[u] <= thr || (thr < 0.f && layer == 0 && !prescored))) ? 1 : 0;
         ce += ex[u];
         ck += (live && !ex[u]) ? 1 : 0;
         fs += sc[u];

@@ -1,9 +1,10 @@
 """Drop-in for the reference's ``models/early_exit.py`` interface: ``EarlyExitUViT(uvit, classifier_type, exit_threshold)``
 with the checkpoint layout of SURVEY.md Q16 (``uvit.*``, ``matrix.{i}.classifier.0.*``, ``in_blocks_heads.*``,
 ``mid_block_head.*``, ``out_blocks_heads.*``) and ``forward -> (eps, [probe_i], [head_output_i])``
-(models/early_exit.py:268-320).  The three MLP probe layouts are supported -- ``mlp_probe_per_layer`` (the type of
-every configs/deediff_*.yaml), ``mlp_probe_per_timestep`` and ``mlp_probe_per_layer_per_timestep``
-(models/early_exit.py:194-239: ``matrix["i"]``, ``matrix["t"]``, ``matrix["i, t"]``); ``attention_probe`` is not.
+(models/early_exit.py:268-320).  All four classifier types of the reference are supported -- ``mlp_probe_per_layer``
+(the type of every configs/deediff_*.yaml), ``mlp_probe_per_timestep``, ``mlp_probe_per_layer_per_timestep``
+(models/early_exit.py:194-239: ``matrix["i"]``, ``matrix["t"]``, ``matrix["i, t"]``) and ``attention_probe`` (the
+constructor's default; one ``AttentionProbe`` per layer, whose scores are not sigmoids).
 """
 from __future__ import annotations
 
@@ -31,21 +32,32 @@ class MLPProbe(nn.Module):  # models/early_exit.py:31-34
         self.classifier = nn.Sequential(nn.Linear(embed_dim, 1), nn.Sigmoid())
 
 
+class AttentionProbe(nn.Module):  # parameter names / shapes of models/early_exit.py:46-60
+    def __init__(self, embed_dim: int, num_heads: int = 1):
+        super().__init__()
+        if num_heads != 1:
+            raise NotImplementedError("AttentionProbe: the reference only ever builds num_heads = 1")
+        self.num_heads = num_heads
+        self.q = nn.Parameter(torch.zeros(1, num_heads, 1, embed_dim // num_heads))
+        self.weight_kv = nn.Linear(embed_dim, 2 * embed_dim)
+        self.classification = nn.Sequential(nn.Linear(embed_dim, embed_dim), nn.SiLU(), nn.Linear(embed_dim, 1))
+
+
 # classifier_type -> ddb_uvit_config.early_exit (include/duodiff_b200.h)
-PROBE_KINDS = {"mlp_probe_per_layer": 1, "mlp_probe_per_timestep": 2, "mlp_probe_per_layer_per_timestep": 3}
+PROBE_KINDS = {"mlp_probe_per_layer": 1, "mlp_probe_per_timestep": 2, "mlp_probe_per_layer_per_timestep": 3,
+               "attention_probe": 4}
 
 
 def probe_keys(classifier_type: str, depth: int) -> list[str]:
     """Keys of ``EarlyExitUViT.matrix`` in the reference's construction order (models/early_exit.py:217-239)."""
-    if classifier_type == "mlp_probe_per_layer":
+    if classifier_type in ("mlp_probe_per_layer", "attention_probe"):
         return [f"{i}" for i in range(depth)]
     if classifier_type == "mlp_probe_per_timestep":
         return [f"{t}" for t in range(1000)]
     if classifier_type == "mlp_probe_per_layer_per_timestep":
         return [f"{i}, {t}" for t in range(1000) for i in range(depth)]
-    raise NotImplementedError(
-        f"classifier_type={classifier_type!r}: the MLP probe layouts {sorted(PROBE_KINDS)} are on the B200 path; "
-        "'attention_probe' (models/early_exit.py:40-80; no shipped config uses it) is out of scope")
+    # (the reference constructs the module without probes and fails at the first forward, early_exit.py:203-204)
+    raise ValueError(f"Unknown classifier type: {classifier_type}")
 
 
 class EarlyExitUViT(nn.Module):
@@ -56,7 +68,8 @@ class EarlyExitUViT(nn.Module):
         self.exit_threshold = exit_threshold
         self.classifier_type = classifier_type
         d, half = uvit.embed_dim, uvit.depth // 2
-        self.matrix = nn.ModuleDict({k: MLPProbe(d) for k in keys})
+        probe = AttentionProbe if classifier_type == "attention_probe" else MLPProbe
+        self.matrix = nn.ModuleDict({k: probe(d) for k in keys})
         head = lambda: OutputHead(d, uvit.patch_dim, uvit.in_chans)  # noqa: E731
         self.in_blocks_heads = nn.ModuleList([head() for _ in range(half)])
         self.mid_block_head = head()

@@ -46,7 +46,8 @@ typedef struct {
     int32_t early_exit;           /* > 0: weights carry the EarlyExitUViT prefix `uvit.` + probes + heads; the value is
                                    * the probe layout (models/early_exit.py:194-204): 1 mlp_probe_per_layer
                                    * (matrix["i"]), 2 mlp_probe_per_timestep (matrix["t"], t < 1000),
-                                   * 3 mlp_probe_per_layer_per_timestep (matrix["i, t"]) */
+                                   * 3 mlp_probe_per_layer_per_timestep (matrix["i, t"]), 4 attention_probe
+                                   * (AttentionProbe per layer, num_heads = 1; scores are not sigmoids) */
     int32_t max_batch;            /* workspace is sized for this many samples */
     float ln_eps;                 /* nn.LayerNorm default 1e-5 */
 } ddb_uvit_config;

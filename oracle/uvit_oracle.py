@@ -161,9 +161,24 @@ def mlp_probe(sd: dict, i, x: torch.Tensor) -> torch.Tensor:
     return torch.sigmoid(F.linear(x, w, b)).mean(dim=1).squeeze()
 
 
+def attention_probe(sd: dict, i: int, x: torch.Tensor) -> torch.Tensor:
+    """models/early_exit.py:40-80 (num_heads = 1) — a learned query attends over x[:, 1:], the pooled value goes
+    through Linear -> SiLU -> Linear(D, 1); explicit softmax instead of F.scaled_dot_product_attention."""
+    p = f"matrix.{i}."
+    xs = x[:, 1:, :]                                                      # :73 "ignore time vector"
+    kv = F.linear(xs, sd[p + "weight_kv.weight"], sd[p + "weight_kv.bias"])
+    D = xs.shape[-1]
+    k, v = kv[..., :D], kv[..., D:]                                       # "b l (k h hd) -> k b h l hd", k=2, h=1
+    q = sd[p + "q"].reshape(1, 1, D)
+    att = torch.softmax((q @ k.transpose(-2, -1)) / math.sqrt(D), dim=-1)  # [B, 1, L-1]
+    pooled = att @ v                                                      # [B, 1, D]
+    h = F.silu(F.linear(pooled, sd[p + "classification.0.weight"], sd[p + "classification.0.bias"]))
+    return F.linear(h, sd[p + "classification.2.weight"], sd[p + "classification.2.bias"]).squeeze()
+
+
 def probe_key(classifier_type: str, i: int, t: int) -> str:
     """models/early_exit.py:194-204 (get_classifer): which entry of ``matrix`` scores layer i at timestep t."""
-    if classifier_type == "mlp_probe_per_layer":
+    if classifier_type in ("mlp_probe_per_layer", "attention_probe"):
         return f"{i}"
     if classifier_type == "mlp_probe_per_timestep":
         return f"{t}"
@@ -185,7 +200,10 @@ def ee_forward(sd: dict, spec: UViTSpec, x: torch.Tensor, timesteps: torch.Tenso
     skips, cls, outs = [], [], []
     for i, bp in enumerate(_block_prefixes(spec, pfx)):
         outs.append(output_head(sd, head_pfx[i], h, spec))
-        cls.append(mlp_probe(sd, probe_key(classifier_type, i, t_int), h))
+        if classifier_type == "attention_probe":
+            cls.append(attention_probe(sd, i, h))
+        else:
+            cls.append(mlp_probe(sd, probe_key(classifier_type, i, t_int), h))
         if i < half:
             h = block(sd, bp, h, None, spec.num_heads)
             skips.append(h)

@@ -247,8 +247,39 @@ def ee_probe_types_fixture():
     np.savez_compressed(OUT / "ee_probe_types_tiny.npz", **params_np(TINY), **fx)
 
 
+def ee_attention_probe_fixture():
+    """classifier_type = "attention_probe" (models/early_exit.py:40-80, the constructor's default).  The learned query
+    is zero-initialised (uniform attention): it is given random values so that the softmax matters; one unconditional
+    and one class-conditional model (two extra tokens: x[:, 1:] then drops the LABEL token)."""
+    fx = {}
+    for tag, params, with_y in (("u", TINY, False), ("c", TINY_CLS, True)):
+        torch.manual_seed(41)
+        m = EarlyExitUViT(UViT(**params), "attention_probe").eval()
+        heat(m, 42)
+        g = torch.Generator().manual_seed(43)
+        with torch.no_grad():
+            for i in range(params["depth"]):
+                m.matrix[f"{i}"].q.copy_(torch.randn(m.matrix[f"{i}"].q.shape, generator=g) * 2.0)
+        x = torch.randn(3, params["in_chans"], 8, 8)
+        t = torch.tensor([321.0, 321.0, 321.0])
+        y = torch.tensor([1, 7, 3]) if with_y else None
+        with torch.no_grad():
+            eps, cls, outs = m(x, t, y)
+        fx.update({f"{tag}::x": x.numpy(), f"{tag}::t": t.numpy(), f"{tag}::eps": eps.numpy(),
+                   f"{tag}::cls": torch.stack(cls).numpy(), f"{tag}::outs": torch.stack(outs).numpy()})
+        if with_y:
+            fx[f"{tag}::y"] = y.numpy()
+        fx.update({f"{tag}::p::{k}": np.asarray(v) for k, v in params.items()})
+        fx.update(sd_np(m, f"{tag}::w::"))
+        print("ee_attention_probe", tag, torch.stack(cls).numpy().round(3).tolist())
+    np.savez_compressed(OUT / "ee_attention_probe_tiny.npz", **fx)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "attention_probe":
+        ee_attention_probe_fixture()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "probe_types":  # add the probe-layout fixture without touching the others
         ee_probe_types_fixture()
         sys.exit(0)
@@ -267,3 +298,4 @@ if __name__ == "__main__":
     ee_sampler_fixture(ee_model)
     ae_decode_fixture()
     ee_probe_types_fixture()
+    ee_attention_probe_fixture()

@@ -526,6 +526,68 @@ def test_ee_timestep_indexed_probes(dev, ctype):
     assert (err0[500] - err0[499]).abs().max().item() > 1e-3
 
 
+@pytest.mark.parametrize("name", ["celeba_3", "imagenet64_3"])
+def test_ee_attention_probe(dev, name):
+    """classifier_type = "attention_probe" (models/early_exit.py:40-80, the reference constructor's default): the library
+    computes it without the key / value GEMM (u = Wk^T q / sqrt(D) folded into the probe dot products, Wc = W1 Wv applied
+    to the softmax-pooled block input).  Scores (no sigmoid), heads and eps vs the oracle (pinned to the reference by
+    tests/golden/ee_attention_probe_tiny.npz); selection under the margin rule; compact == simulate bit for bit, also
+    through the sampler.  imagenet64_3 is class-conditional: x[:, 1:] drops the LABEL token and keeps the time token."""
+    import duodiff_b200 as ddb
+    from duodiff_b200 import eesampler as ES
+    torch.manual_seed(35)
+    cfg = CONFIGS[name]
+    depth, C, H = cfg["depth"], cfg["in_chans"], cfg["img_size"]
+    net = ddb.EarlyExitUViT(ddb.UViT(**cfg), "attention_probe")
+    heat_(net, 36, scale=2.0)
+    g = torch.Generator().manual_seed(37)
+    with torch.no_grad():
+        for i in range(depth):  # zero-initialised in the reference: uniform attention would not test the softmax
+            net.matrix[f"{i}"].q.copy_(torch.randn(net.matrix[f"{i}"].q.shape, generator=g))
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(cfg)
+    B = 5
+    x = torch.randn(B, C, H, H, generator=g).to(dev)
+    t = torch.full((B,), 321.0, device=dev)
+    y = torch.randint(0, cfg["num_classes"], (B,), generator=g).to(dev) if cfg["num_classes"] > 0 else None
+    eng = net.engine(B)
+    with torch.no_grad():
+        r_eps, r_cls, r_outs = O.ee_forward(sd, spec, x, t, y, classifier_type="attention_probe")
+    r_cls_t = torch.stack([c.reshape(-1) for c in r_cls])
+    _, _, cls, outs = eng.ee_forward(x, t, y, threshold=0.0, mode=0)
+    eps = outs[depth]  # the full model's output (the selected eps depends on the threshold)
+    margin = 3e-2 * (1.0 + r_cls_t.abs().max().item())
+    dev_max = (cls - r_cls_t).abs().max().item()
+    print(f"{name}: attention-probe scores in [{r_cls_t.min().item():.2f}, {r_cls_t.max().item():.2f}], "
+          f"max deviation {dev_max:.2e} (margin {margin:.2e})")
+    assert dev_max <= margin
+    assert r_cls_t.std().item() > 10 * margin / 3, "scores too flat for the selection test to mean anything"
+    assert rel_l2(eps, r_eps) <= EPS_REL_L2
+    for i in range(depth):
+        assert rel_l2(outs[i], r_outs[i]) <= EPS_REL_L2, i
+    qs = torch.quantile(r_cls_t.flatten(), torch.tensor([0.0, 0.25, 0.5, 0.75, 1.0], device=dev)).tolist()
+    exits = set()
+    for thr in [qs[0] - 1.0] + qs[1:4] + [qs[4] + 1.0]:
+        e0, i0, _, _ = eng.ee_forward(x, t, y, threshold=thr, mode=0)
+        e1, i1, _, _ = eng.ee_forward(x, t, y, threshold=thr, mode=1)
+        assert torch.equal(i0, i1) and torch.equal(e0, e1), (thr, i0.tolist(), i1.tolist())
+        r_sel, r_idx, scores = O.ee_select(r_eps, r_cls, r_outs, thr)
+        near = ((scores[:-1] - thr).abs() < margin).any(0)
+        same = i0.long() == r_idx
+        assert bool((same | near).all()), (thr, i0.tolist(), r_idx.tolist())
+        ok = same.nonzero().flatten()
+        assert rel_l2(e0[ok], r_sel[ok]) <= EPS_REL_L2
+        exits |= set(i0.tolist())
+    assert len(exits) >= 2, exits
+    # sampler (graph replay), both modes
+    noise = torch.randn(1000, B, C, H, H, generator=g)
+    kw = dict(seed=3, num_channels=C, sample_height=H, sample_width=H, threshold=qs[2], depth=depth, noise=noise, y=y)
+    s0, _e0, idx0 = ES.get_samples(net, B, mode=0, **kw)
+    s1, _e1, idx1 = ES.get_samples(net, B, mode=1, **kw)
+    assert np.array_equal(s0, s1) and torch.equal(idx0, idx1)
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
     from duodiff_b200.ddpm import Sampler

@@ -127,6 +127,11 @@ def test_state_dict_layout_matches_reference_checkpoints():
     from duodiff_b200.early_exit import probe_keys
     keys = probe_keys("mlp_probe_per_layer_per_timestep", 3)
     assert keys[:4] == ["0, 0", "1, 0", "2, 0", "0, 1"] and len(keys) == 3000
+    ap = ddb.EarlyExitUViT(d3, "attention_probe").state_dict()  # the reference's default classifier_type
+    fa = load_fixture("ee_attention_probe_tiny")
+    ref_keys = {k[len("u::w::"):] for k in fa if k.startswith("u::w::matrix.0.")}
+    assert ref_keys == {k for k in ap if k.startswith("matrix.0.")} and len(ref_keys) == 7
+    assert tuple(ap["matrix.0.q"].shape) == (1, 1, 1, 512) and tuple(ap["matrix.2.weight_kv.weight"].shape) == (1024, 512)
     fx = load_fixture("ee_probe_types_tiny")  # key spelling as saved by the reference's own state_dict()
     assert "plt::w::matrix.2, 321.classifier.0.bias" in fx and "pt::w::matrix.7.classifier.0.weight" in fx
 
@@ -137,8 +142,10 @@ def test_unsupported_options_raise():
         ddb.UViT(**dict(CONFIGS["celeba_3"], mlp_time_embed=True))
     with pytest.raises(NotImplementedError):
         ddb.UViT(**CONFIGS["celeba_3"], skip=False)
+    with pytest.raises(ValueError):
+        ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["celeba_3"]), "linear_probe")
     with pytest.raises(NotImplementedError):
-        ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["celeba_3"]), "attention_probe")
+        ddb.AttentionProbe(512, num_heads=2)
 
 
 def test_config_filter_drops_stray_keys(tmp_path):

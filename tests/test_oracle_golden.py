@@ -66,6 +66,21 @@ def test_ee_forward_timestep_indexed_probes(tag, ctype):
     assert np.abs(fx[f"{tag}::cls0"] - fx[f"{tag}::cls1"]).max() > 1e-2
 
 
+@pytest.mark.parametrize("tag", ["u", "c"])
+def test_ee_forward_attention_probe(tag):
+    """models/early_exit.py:40-80 through EarlyExitUViT(..., "attention_probe"): unconditional and class-conditional
+    (where x[:, 1:] drops the label token and keeps the time token)."""
+    fx = load_fixture("ee_attention_probe_tiny")
+    sd, params = split_fixture(fx, f"{tag}::w::", f"{tag}::p::")
+    spec = O.UViTSpec.from_params(params)
+    y = torch.from_numpy(fx[f"{tag}::y"]) if f"{tag}::y" in fx else None
+    eps, cls, outs = O.ee_forward(sd, spec, torch.from_numpy(fx[f"{tag}::x"]), torch.from_numpy(fx[f"{tag}::t"]), y,
+                                  classifier_type="attention_probe")
+    np.testing.assert_allclose(eps.numpy(), fx[f"{tag}::eps"], atol=ATOL, rtol=1e-5)
+    np.testing.assert_allclose(torch.stack(cls).numpy(), fx[f"{tag}::cls"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(torch.stack(outs).numpy(), fx[f"{tag}::outs"], atol=ATOL, rtol=1e-5)
+
+
 def _replay_reference_rng(seed, shape):
     """seed_everything + x_T draw of sampler.py:99-100; z_t drawn lazily from the same global CPU stream."""
     torch.manual_seed(seed)
