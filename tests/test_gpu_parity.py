@@ -588,6 +588,23 @@ def test_ee_attention_probe(dev, name):
     assert np.array_equal(s0, s1) and torch.equal(idx0, idx1)
 
 
+@pytest.mark.parametrize("classifier_type", ["attention_probe", "mlp_probe_per_layer", "mlp_probe_per_timestep",
+                                             "mlp_probe_per_layer_per_timestep"])
+def test_reference_early_exit_forward_contract(dev, classifier_type):
+    """The forward half of the reference's own tests/models/test_early_exit.py:98-115 (its `test_backward`; training is
+    out of scope): CIFAR-10 config, zero images, t = 1, all four classifier types -> y.shape == x.shape and
+    len(outputs) == len(classifier_outputs) == depth."""
+    import duodiff_b200 as ddb
+    torch.manual_seed(0)
+    model = ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["cifar10"]), classifier_type=classifier_type).eval().to(dev)
+    x = torch.zeros(8, 3, 32, 32, device=dev)
+    t = torch.ones(8, device=dev)
+    y, classifier_outputs, outputs = model(x, t)
+    assert y.shape == x.shape and bool(torch.isfinite(y).all())
+    assert len(outputs) == len(classifier_outputs) == model.uvit.depth
+    assert all(c.shape == (8,) for c in classifier_outputs) and all(o.shape == x.shape for o in outputs)
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
     from duodiff_b200.ddpm import Sampler
