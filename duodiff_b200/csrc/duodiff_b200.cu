@@ -546,6 +546,9 @@ struct ddb_model {
     Buf probe_w, probe_b, probe_tab_w, probe_tab_b, ap_wc, ap_bc, ap_w2, ap_b2;
     float* pw(int i) const { return probe_w->as<float>() + (size_t)i * D; }
     float* pb(int i) const { return probe_b->as<float>() + i; }
+    // mlp_time_embed = True (models/uvit.py:264-272): the MLP's weights, the table of the 1000 integer timesteps' time
+    // tokens (what the sampler's steps use) and a [max_batch, D] scratch for a caller's arbitrary timesteps
+    Buf te_w1, te_b1, te_w2, te_b2, time_tab, time_tok;
     // workspace
     Buf x0, xs, xm, qkv, ao, hbuf, stats, stats_p, img_pre, probe_p, scores, outputs, exit_idx;
     // early-exit compaction (mode 1): device-side live counts, slot maps, gather lists, scratch batch of leavers
@@ -617,8 +620,10 @@ static int load_block(ddb_model* m, const TensorMap& tm, const std::string& pfx,
     DDB_TRY(get_tensor(tm, pfx + "mlp.fc2.weight", (int64_t)D * Hd, &w));
     DDB_TRY(get_tensor(tm, pfx + "mlp.fc2.bias", D, &b));
     DDB_TRY(pack_linear(bw.fc2, w, b, nullptr, nullptr, D, D, Hd, false));
-    bw.has_skip = skip;
-    if (skip) {
+    // UViT(skip=False) (models/uvit.py:200-204): the out-blocks have no skip_linear and ignore the popped skip
+    if (skip) DDB_TRY(get_tensor(tm, pfx + "skip_linear.weight", (int64_t)2 * D * D, &w, true));
+    bw.has_skip = skip && w != nullptr;
+    if (bw.has_skip) {
         DDB_TRY(get_tensor(tm, pfx + "skip_linear.weight", (int64_t)2 * D * D, &w));
         DDB_TRY(get_tensor(tm, pfx + "skip_linear.bias", D, &b));
         DDB_TRY(pack_linear(bw.skip, w, b, nullptr, nullptr, D, D, 2 * D, false));
@@ -634,11 +639,20 @@ static int load_head(ddb_model* m, const TensorMap& tm, const std::string& pfx, 
     DDB_TRY(get_tensor(tm, pfx + "decoder_pred.weight", (int64_t)m->pd * D, &w));
     DDB_TRY(get_tensor(tm, pfx + "decoder_pred.bias", m->pd, &wb));
     DDB_TRY(pack_linear(hw.dec, w, wb, g, b, m->pd, 64, D, true));
-    DDB_TRY(get_tensor(tm, pfx + "final_layer.weight", (int64_t)C * C * 9, &cw));
-    DDB_TRY(get_tensor(tm, pfx + "final_layer.bias", C, &cb));
+    DDB_TRY(get_tensor(tm, pfx + "final_layer.weight", (int64_t)C * C * 9, &cw, true));
     hw.conv_w.reset(new DevMem), hw.conv_b.reset(new DevMem);
     DDB_TRY(hw.conv_w->alloc((size_t)C * C * 9 * 4));
     DDB_TRY(hw.conv_b->alloc((size_t)C * 4));
+    if (!cw) {
+        // conv=False (models/uvit.py:329-333, early_exit.py:17-21): final_layer is nn.Identity().  The conv kernels run
+        // with the identity stencil (centre tap 1 on the channel diagonal, zero bias): fma(1, x, 0 + 0*..) == x exactly
+        std::vector<float> idw((size_t)C * C * 9, 0.f);
+        for (int ch = 0; ch < C; ++ch) idw[((size_t)ch * C + ch) * 9 + 4] = 1.f;
+        CUDA_TRY(cudaMemcpy(hw.conv_w->p, idw.data(), idw.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemset(hw.conv_b->p, 0, (size_t)C * 4));
+        return DDB_OK;
+    }
+    DDB_TRY(get_tensor(tm, pfx + "final_layer.bias", C, &cb));
     CUDA_TRY(cudaMemcpy(hw.conv_w->p, cw, (size_t)C * C * 9 * 4, cudaMemcpyDeviceToDevice));
     CUDA_TRY(cudaMemcpy(hw.conv_b->p, cb, (size_t)C * 4, cudaMemcpyDeviceToDevice));
     return DDB_OK;
@@ -754,6 +768,30 @@ static int model_create_impl(const ddb_uvit_config* cfg, const ddb_tensor* tenso
         DDB_TRY(get_tensor(tm, up + "label_emb.weight", (int64_t)cfg->num_classes * D, &lab));
         DDB_TRY(new_buf(m->label_emb, (size_t)cfg->num_classes * D * 4));
         CUDA_TRY(cudaMemcpy(m->label_emb->p, lab, (size_t)cfg->num_classes * D * 4, cudaMemcpyDeviceToDevice));
+    }
+    {
+        const float *w1, *b1, *w2, *b2;
+        DDB_TRY(get_tensor(tm, up + "time_embed.0.weight", (int64_t)4 * D * D, &w1, true));
+        if (w1) {
+            DDB_TRY(get_tensor(tm, up + "time_embed.0.bias", 4 * D, &b1));
+            DDB_TRY(get_tensor(tm, up + "time_embed.2.weight", (int64_t)4 * D * D, &w2));
+            DDB_TRY(get_tensor(tm, up + "time_embed.2.bias", D, &b2));
+            DDB_TRY(new_buf(m->te_w1, (size_t)4 * D * D * 4));
+            DDB_TRY(new_buf(m->te_b1, (size_t)4 * D * 4));
+            DDB_TRY(new_buf(m->te_w2, (size_t)4 * D * D * 4));
+            DDB_TRY(new_buf(m->te_b2, (size_t)D * 4));
+            CUDA_TRY(cudaMemcpy(m->te_w1->p, w1, (size_t)4 * D * D * 4, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(m->te_b1->p, b1, (size_t)4 * D * 4, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(m->te_w2->p, w2, (size_t)4 * D * D * 4, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(m->te_b2->p, b2, (size_t)D * 4, cudaMemcpyDeviceToDevice));
+            DDB_TRY(new_buf(m->time_tab, (size_t)1000 * D * 4));
+            DDB_TRY(new_buf(m->time_tok, (size_t)cfg->max_batch * D * 4));
+            time_mlp_kernel<<<1000, 256, (size_t)5 * D * 4>>>(nullptr, (int)cfg->normalize_timesteps, D,
+                                                              m->te_w1->as<float>(), m->te_b1->as<float>(),
+                                                              m->te_w2->as<float>(), m->te_b2->as<float>(),
+                                                              m->time_tab->as<float>());
+            LAUNCH_CHECK();
+        }
     }
     // ---- blocks
     const int half = cfg->depth / 2;
@@ -1006,11 +1044,23 @@ static int launch_patch_gather(const ddb_model* m, const float* x, int B, cudaSt
 }
 static int launch_token_extras(const ddb_model* m, const float* t_vec, const int* t_dev, const int64_t* y, int B,
                                cudaStream_t st) {
+    const float *rows = nullptr, *tab = nullptr;
+    if (m->time_tab) {  // mlp_time_embed: table row of the step, or the MLP on the caller's timesteps
+        tab = m->time_tab->as<float>();
+        if (!t_dev) {
+            rows = m->time_tok->as<float>();
+            CUDA_TRY(launch_pdl(time_mlp_kernel, dim3(B), dim3(256), (size_t)5 * m->D * 4, st, t_vec,
+                                (int)m->cfg.normalize_timesteps, m->D, (const float*)m->te_w1->as<float>(),
+                                (const float*)m->te_b1->as<float>(), (const float*)m->te_w2->as<float>(),
+                                (const float*)m->te_b2->as<float>(), m->time_tok->as<float>()));
+            LAUNCH_CHECK();
+        }
+    }
     CUDA_TRY(launch_pdl(token_extras_kernel, dim3(B), dim3(256), 0, st, t_vec, t_dev,
                         reinterpret_cast<const long long*>(y), (const float*)m->pos->as<float>(),
                         (const float*)(m->label_emb ? m->label_emb->as<float>() : nullptr),
                         m->x0->as<__nv_bfloat16>(), m->stats_p->as<float2>(), m->D, m->L, m->extras,
-                        (int)m->cfg.normalize_timesteps, (int)m->cfg.num_classes));
+                        (int)m->cfg.normalize_timesteps, (int)m->cfg.num_classes, rows, tab));
     LAUNCH_CHECK();
     return DDB_OK;
 }
@@ -1412,6 +1462,7 @@ static void tail_target(TailTarget& tg, const ddb_model* m) {
     tg.stats_p = m->stats_p->as<float2>();
     tg.pos = m->pos->as<float>();
     tg.label_emb = m->label_emb ? m->label_emb->as<float>() : nullptr;
+    tg.time_tab = m->time_tab ? m->time_tab->as<float>() : nullptr;
     tg.P = m->cfg.patch_size, tg.D = m->D, tg.L = m->L, tg.extras = m->extras;
     tg.normalize_t = m->cfg.normalize_timesteps, tg.num_classes = m->cfg.num_classes;
 }

@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
 __device__ __forceinline__ void write_token_extras(int b, float tau, const long long* __restrict__ y,
                                                    const float* __restrict__ pos, const float* __restrict__ label_emb,
                                                    __nv_bfloat16* __restrict__ tokens, float2* __restrict__ stats_p,
-                                                   int D, int L, int extras, int normalize_t, int num_classes) {
+                                                   int D, int L, int extras, int normalize_t, int num_classes,
+                                                   const float* __restrict__ time_row = nullptr) {
+    // time_row (mlp_time_embed = True, models/uvit.py:264-272): the time token after its MLP, from time_mlp_kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int half = D / 2;
     if (normalize_t) tau = tau / 1000.f;
@@ -116,7 +118,9 @@ __device__ __forceinline__ void write_token_extras(int b, float tau, const long 
             for (int u = 0; u < 2; ++u) {
                 const int e = ch * 64 + lane * 2 + u;
                 float x;
-                if (is_time) {
+                if (is_time && time_row) {
+                    x = time_row[e];
+                } else if (is_time) {
                     // time token: [cos(tau f_i) | sin(tau f_i)], f_i = exp(-ln(1e4) i / half)
                     const int i = (e < half) ? e : e - half;
                     const float f = expf((-9.210340371976184f * (float)i) / (float)half);
@@ -147,12 +151,55 @@ __global__ void __launch_bounds__(256) token_extras_kernel(const float* __restri
                                                            const float* __restrict__ label_emb,
                                                            __nv_bfloat16* __restrict__ tokens,
                                                            float2* __restrict__ stats_p, int D, int L, int extras,
-                                                           int normalize_t, int num_classes) {
+                                                           int normalize_t, int num_classes,
+                                                           const float* __restrict__ time_rows /*[B, D] or null*/,
+                                                           const float* __restrict__ time_tab /*[1000, D] or null*/) {
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.x;
     const float tau = t_dev ? (float)ld_state(t_dev) : tsteps[b];
-    write_token_extras(b, tau, y, pos, label_emb, tokens, stats_p, D, L, extras, normalize_t, num_classes);
+    const float* tr = nullptr;  // mlp_time_embed: per-sample rows (caller's timesteps) or the table row of the step
+    if (time_rows && !t_dev) tr = time_rows + (size_t)b * D;
+    else if (time_tab && t_dev) tr = time_tab + (size_t)min(max((int)tau, 0), 999) * D;
+    write_token_extras(b, tau, y, pos, label_emb, tokens, stats_p, D, L, extras, normalize_t, num_classes, tr);
+}
+
+// mlp_time_embed = True (models/uvit.py:264-272, 358): time token = Linear(4D, D)(SiLU(Linear(D, 4D)(emb(tau)))).
+// Row r: tau = tsteps[r] (the caller's timesteps) or, with tsteps == null, tau = r (the table of the 1000 integer
+// timesteps, built once at model creation: inside the sampler the time token is a table row).  The same kernel fills
+// both, so a table row and a per-sample row of the same timestep are the same bits.  256 threads, smem 5 D floats.
+__global__ void __launch_bounds__(256) time_mlp_kernel(const float* __restrict__ tsteps, int normalize_t, int D,
+                                                       const float* __restrict__ w1 /*[4D, D]*/,
+                                                       const float* __restrict__ b1, const float* __restrict__ w2 /*[D, 4D]*/,
+                                                       const float* __restrict__ b2, float* __restrict__ out /*[rows, D]*/) {
+    extern __shared__ float tm_smem[];
+    float* emb = tm_smem;      // [D]
+    float* hid = tm_smem + D;  // [4D]
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = D / 2;
+    float tau = tsteps ? tsteps[r] : (float)r;
+    if (normalize_t) tau = tau / 1000.f;
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+        const int i = (e < half) ? e : e - half;
+        const float f = expf((-9.210340371976184f * (float)i) / (float)half);
+        emb[e] = (e < half) ? cosf(tau * f) : sinf(tau * f);
+    }
+    __syncthreads();
+    for (int j = warp; j < 4 * D; j += 8) {
+        float d = 0.f;
+        for (int k = lane; k < D; k += 32) d = fmaf(w1[(size_t)j * D + k], emb[k], d);
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        const float z = d + b1[j];
+        if (lane == 0) hid[j] = z / (1.f + expf(-z));
+    }
+    __syncthreads();
+    for (int j = warp; j < D; j += 8) {
+        float d = 0.f;
+        for (int k = lane; k < 4 * D; k += 32) d = fmaf(w2[(size_t)j * 4 * D + k], hid[k], d);
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (lane == 0) out[(size_t)r * D + j] = d + b2[j];
+    }
 }
 
 // W_pe [D, pd] fp32 (conv weight flattened (c, p1, p2)) -> [D, 128] bf16: [W | 0 | W | 0]
@@ -430,6 +477,7 @@ struct TailTarget {
     float2* stats_p;         // [B * L, D / 64]
     const float* pos;        // [L, D]
     const float* label_emb;  // [num_classes, D] or null
+    const float* time_tab;   // [1000, D] time tokens after their MLP (mlp_time_embed = True) or null
     int P, D, L, extras, normalize_t, num_classes;
 };
 struct TailArgs {
@@ -529,7 +577,8 @@ __global__ void __launch_bounds__(256, 4) step_tail_kernel(const __grid_constant
     }
     if (y0 == 0)  // one CTA per sample also writes the next step's time / label token rows
         write_token_extras(b, (float)t_next, a.y, tg.pos, tg.label_emb, tg.tokens, tg.stats_p, tg.D, tg.L, tg.extras,
-                           tg.normalize_t, tg.num_classes);
+                           tg.normalize_t, tg.num_classes,
+                           tg.time_tab ? tg.time_tab + (size_t)min(max(t_next, 0), 999) * tg.D : nullptr);
     // every CTA has read t above; the last one to get here advances the step counter
     __syncthreads();
     if (threadIdx.x == 0) {

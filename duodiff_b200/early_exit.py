@@ -18,12 +18,10 @@ from .uvit import UViT
 class OutputHead(nn.Module):  # parameter names of models/early_exit.py:9-20
     def __init__(self, embed_dim: int, patch_dim: int, in_chans: int, conv: bool = True):
         super().__init__()
-        if not conv:
-            raise NotImplementedError("OutputHead(conv=False) has no kernel")
         self.in_chans = in_chans
         self.norm = nn.LayerNorm(embed_dim)
         self.decoder_pred = nn.Linear(embed_dim, patch_dim, bias=True)
-        self.final_layer = nn.Conv2d(in_chans, in_chans, 3, padding=1)
+        self.final_layer = nn.Conv2d(in_chans, in_chans, 3, padding=1) if conv else nn.Identity()
 
 
 class MLPProbe(nn.Module):  # models/early_exit.py:31-34

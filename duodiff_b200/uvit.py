@@ -53,19 +53,11 @@ class UViT(nn.Module):
                  num_classes, normalize_timesteps, qk_scale=None, norm_layer=nn.LayerNorm, mlp_time_embed=False,
                  use_checkpoint=False, conv=True, skip=True, max_batch: int | None = None):
         super().__init__()
-        unsupported = []
-        if qk_scale is not None:
-            unsupported.append("qk_scale (the reference ignores it too: SDPA default scale, models/uvit.py:163)")
+        # qk_scale: accepted and ignored, like the reference (its attention always uses SDPA's default 1/sqrt(head_dim),
+        # models/uvit.py:158-163); use_checkpoint: a training-time memory trade, no effect on the forward.
         if norm_layer is not nn.LayerNorm:
-            unsupported.append("norm_layer != nn.LayerNorm")
-        if mlp_time_embed:
-            unsupported.append("mlp_time_embed=True (False in every configs/*.yaml)")
-        if not conv:
-            unsupported.append("conv=False")
-        if not skip:
-            unsupported.append("skip=False")
-        if unsupported:
-            raise NotImplementedError("duodiff_b200.UViT: " + "; ".join(unsupported))
+            raise NotImplementedError("duodiff_b200.UViT: norm_layer != nn.LayerNorm has no kernel")
+        del qk_scale, use_checkpoint
         self.num_features = self.embed_dim = embed_dim
         self.normalize_timesteps = normalize_timesteps
         self.num_classes = num_classes
@@ -79,17 +71,19 @@ class UViT(nn.Module):
         self.max_batch = max_batch
 
         self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)
-        self.time_embed = nn.Identity()
+        # models/uvit.py:264-272 (the library serves the MLP from a table of the 1000 integer timesteps)
+        self.time_embed = (nn.Sequential(_linear(embed_dim, 4 * embed_dim), nn.SiLU(), _linear(4 * embed_dim, embed_dim))
+                           if mlp_time_embed else nn.Identity())
         self.label_emb = nn.Embedding(num_classes, embed_dim) if num_classes > 0 else None
         self.pos_embed = nn.Parameter(torch.zeros(1, self.extras + self.num_patches, embed_dim))
         half = depth // 2
-        mk = lambda long_skip: _Block(embed_dim, self.mlp_hidden, qkv_bias, long_skip)  # noqa: E731
+        mk = lambda long_skip: _Block(embed_dim, self.mlp_hidden, qkv_bias, long_skip and skip)  # noqa: E731
         self.in_blocks = nn.ModuleList([mk(False) for _ in range(half)])
         self.mid_block = mk(False)
         self.out_blocks = nn.ModuleList([mk(True) for _ in range(half)])
         self.norm = nn.LayerNorm(embed_dim)
         self.decoder_pred = _linear(embed_dim, self.patch_dim)
-        self.final_layer = nn.Conv2d(in_chans, in_chans, 3, padding=1)
+        self.final_layer = nn.Conv2d(in_chans, in_chans, 3, padding=1) if conv else nn.Identity()
         self._reset_parameters()
         self._engine: Engine | None = None
         self._engine_key = None

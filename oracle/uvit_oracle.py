@@ -112,6 +112,8 @@ def output_head(sd: dict, pfx: str, x: torch.Tensor, spec: UViTSpec) -> torch.Te
     h = F.layer_norm(x, (D,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5)
     h = F.linear(h, sd[pfx + "decoder_pred.weight"], sd[pfx + "decoder_pred.bias"])
     h = unpatchify(h[:, spec.extras:, :], spec.in_chans)
+    if pfx + "final_layer.weight" not in sd:  # conv=False: final_layer is nn.Identity() (models/uvit.py:329-333)
+        return h
     return F.conv2d(h, sd[pfx + "final_layer.weight"], sd[pfx + "final_layer.bias"], padding=1)
 
 
@@ -121,8 +123,11 @@ def embed_tokens(sd: dict, pfx: str, spec: UViTSpec, x: torch.Tensor, timesteps:
     if spec.normalize_timesteps:
         timesteps = timesteps.float() / 1000
     tok = patch_embed(x, sd[pfx + "patch_embed.proj.weight"], sd[pfx + "patch_embed.proj.bias"], spec.patch_size)
-    time_token = timestep_embedding(timesteps, spec.embed_dim).unsqueeze(1)
-    tok = torch.cat((time_token, tok), dim=1)
+    time_token = timestep_embedding(timesteps, spec.embed_dim)
+    if pfx + "time_embed.0.weight" in sd:  # mlp_time_embed=True (models/uvit.py:264-272): Linear -> SiLU -> Linear
+        time_token = F.linear(F.silu(F.linear(time_token, sd[pfx + "time_embed.0.weight"], sd[pfx + "time_embed.0.bias"])),
+                              sd[pfx + "time_embed.2.weight"], sd[pfx + "time_embed.2.bias"])
+    tok = torch.cat((time_token.unsqueeze(1), tok), dim=1)
     if y is not None and (pfx + "label_emb.weight") in sd:
         tok = torch.cat((sd[pfx + "label_emb.weight"][y].unsqueeze(1), tok), dim=1)
     return tok + sd[pfx + "pos_embed"]

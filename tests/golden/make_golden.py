@@ -247,6 +247,30 @@ def ee_probe_types_fixture():
     np.savez_compressed(OUT / "ee_probe_types_tiny.npz", **params_np(TINY), **fx)
 
 
+def uvit_variants_fixture():
+    """The constructor options no shipped config switches on (models/uvit.py:229-247): A = mlp_time_embed=True with a
+    fractional timestep in the batch; B = conv=False + skip=False (+ qk_scale, which the reference ignores),
+    class-conditional with raw timesteps."""
+    fx = {}
+    for tag, params, with_y in (("a", dict(TINY_FULL, mlp_time_embed=True), False),
+                                ("b", dict(TINY_CLS, conv=False, skip=False, qk_scale=0.3), True)):
+        torch.manual_seed(51)
+        m = UViT(**params).eval()
+        heat(m, 52)
+        x = torch.randn(3, params["in_chans"], 8, 8)
+        t = torch.tensor([999.0, 12.5, 3.0])
+        y = torch.tensor([2, 9, 0]) if with_y else None
+        with torch.no_grad():
+            out = m(x, t, y)
+        fx.update({f"{tag}::x": x.numpy(), f"{tag}::t": t.numpy(), f"{tag}::out": out.numpy()})
+        if with_y:
+            fx[f"{tag}::y"] = y.numpy()
+        fx.update({f"{tag}::p::{k}": np.asarray(v) for k, v in params.items()})
+        fx.update(sd_np(m, f"{tag}::w::"))
+        print("uvit_variants", tag, tuple(out.shape), float(out.abs().max()), len(m.state_dict()))
+    np.savez_compressed(OUT / "uvit_variants_tiny.npz", **fx)
+
+
 def ee_attention_probe_fixture():
     """classifier_type = "attention_probe" (models/early_exit.py:40-80, the constructor's default).  The learned query
     is zero-initialised (uniform attention): it is given random values so that the softmax matters; one unconditional
@@ -277,6 +301,9 @@ def ee_attention_probe_fixture():
 
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if len(sys.argv) > 2 and sys.argv[2] == "variants":
+        uvit_variants_fixture()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "attention_probe":
         ee_attention_probe_fixture()
         sys.exit(0)
@@ -299,3 +326,4 @@ if __name__ == "__main__":
     ae_decode_fixture()
     ee_probe_types_fixture()
     ee_attention_probe_fixture()
+    uvit_variants_fixture()

@@ -605,6 +605,51 @@ def test_reference_early_exit_forward_contract(dev, classifier_type):
     assert all(c.shape == (8,) for c in classifier_outputs) and all(o.shape == x.shape for o in outputs)
 
 
+@pytest.mark.parametrize("name,extra", [
+    ("celeba_3", dict(mlp_time_embed=True)),
+    ("imagenet64_3", dict(conv=False, skip=False, qk_scale=0.5, use_checkpoint=True)),
+    ("cifar10_3", dict(mlp_time_embed=True, conv=False)),
+])
+def test_uvit_constructor_variants(dev, name, extra):
+    """The constructor options no shipped config switches on (models/uvit.py:229-247): mlp_time_embed=True (time token
+    through Linear -> SiLU -> Linear; served from a table of the 1000 integer timesteps inside the sampler), conv=False
+    (final_layer = Identity), skip=False (no skip_linear), qk_scale / use_checkpoint (no effect on the forward, as in the
+    reference).  Forward vs the oracle (pinned by tests/golden/uvit_variants_tiny.npz) with integral and fractional
+    timesteps; the sampler's fused step == forward + ddb_ddpm_step bit for bit (table row == per-sample MLP)."""
+    import duodiff_b200 as ddb
+    from duodiff_b200.ddpm import Sampler, step_coefficients
+    lib, L = _lib()
+    torch.manual_seed(71)
+    cfg = dict(CONFIGS[name], **extra)
+    net = ddb.UViT(**cfg)
+    heat_(net, 72)
+    net = net.eval().to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    spec = O.UViTSpec.from_params(cfg)
+    B, C, H = 4, cfg["in_chans"], cfg["img_size"]
+    g = torch.Generator().manual_seed(73)
+    x = torch.randn(B, C, H, H, generator=g).to(dev)
+    y = torch.randint(0, cfg["num_classes"], (B,), generator=g).to(dev) if cfg["num_classes"] > 0 else None
+    for t in (torch.tensor([999.0, 12.5, 3.0, 500.0]), torch.full((B,), 250.0)):
+        t = t.to(dev)
+        with torch.no_grad():
+            ref = O.uvit_forward(sd, spec, x, t, y)
+        got = net(x, t, y)
+        assert rel_l2(got, ref) <= EPS_REL_L2, (name, rel_l2(got, ref))
+    table, mode = step_coefficients("predict_noise")
+    coef = table.to(dev)
+    ref = x.clone()
+    for t in range(702, 696, -1):
+        eps = net(ref, torch.full((B,), float(t), device=dev), y)
+        lib.check(L.ddb_ddpm_step(ref.data_ptr(), eps.data_ptr(), None, coef.data_ptr(), t, mode, 5, ref.numel(),
+                                  lib.current_stream_ptr()))
+    smp = Sampler(net.engine(B), None, float("inf"), B)
+    for use_graph in (True, False):
+        xs = x.clone()
+        smp.run(xs, y=y, seed=5, t_first=702, t_last=697, use_graph=use_graph)
+        assert torch.equal(xs, ref), (name, use_graph)
+
+
 # ------------------------------------------------------------------------------------------------ sampler
 def test_duodiff_trajectory_teacher_forced_and_free_running(dev):
     from duodiff_b200.ddpm import Sampler

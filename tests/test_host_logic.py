@@ -136,12 +136,25 @@ def test_state_dict_layout_matches_reference_checkpoints():
     assert "plt::w::matrix.2, 321.classifier.0.bias" in fx and "pt::w::matrix.7.classifier.0.weight" in fx
 
 
+def test_constructor_variants_have_the_reference_parameter_tree():
+    """mlp_time_embed / conv / skip / qk_scale / use_checkpoint of models/uvit.py:229-247: same state_dict keys and shapes
+    as the reference's own modules (fixture written from their state_dict())."""
+    import duodiff_b200 as ddb
+    fx = load_fixture("uvit_variants_tiny")
+    for tag in ("a", "b"):
+        ref = {k[len(f"{tag}::w::"):]: v.shape for k, v in fx.items() if k.startswith(f"{tag}::w::")}
+        params = {k[len(f"{tag}::p::"):]: v.item() for k, v in fx.items() if k.startswith(f"{tag}::p::")}
+        own = {k: tuple(v.shape) for k, v in ddb.UViT(**params, use_checkpoint=True).state_dict().items()}
+        assert own == {k: tuple(s) for k, s in ref.items()}, tag
+    assert "final_layer.weight" not in ddb.UViT(**dict(CONFIGS["celeba_3"], conv=False)).state_dict()
+    head = ddb.OutputHead(512, 48, 3, conv=False)
+    assert isinstance(head.final_layer, torch.nn.Identity)
+
+
 def test_unsupported_options_raise():
     import duodiff_b200 as ddb
     with pytest.raises(NotImplementedError):
-        ddb.UViT(**dict(CONFIGS["celeba_3"], mlp_time_embed=True))
-    with pytest.raises(NotImplementedError):
-        ddb.UViT(**CONFIGS["celeba_3"], skip=False)
+        ddb.UViT(**CONFIGS["celeba_3"], norm_layer=torch.nn.BatchNorm1d)
     with pytest.raises(ValueError):
         ddb.EarlyExitUViT(ddb.UViT(**CONFIGS["celeba_3"]), "linear_probe")
     with pytest.raises(NotImplementedError):

@@ -66,6 +66,18 @@ def test_ee_forward_timestep_indexed_probes(tag, ctype):
     assert np.abs(fx[f"{tag}::cls0"] - fx[f"{tag}::cls1"]).max() > 1e-2
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_uvit_forward_constructor_variants(tag):
+    """a: mlp_time_embed=True (fractional timestep in the batch); b: conv=False + skip=False (+ qk_scale, ignored by the
+    reference), class-conditional (models/uvit.py:229-247, 264-272, 200-204, 329-333)."""
+    fx = load_fixture("uvit_variants_tiny")
+    sd, params = split_fixture(fx, f"{tag}::w::", f"{tag}::p::")
+    spec = O.UViTSpec.from_params(params)
+    y = torch.from_numpy(fx[f"{tag}::y"]) if f"{tag}::y" in fx else None
+    out = O.uvit_forward(sd, spec, torch.from_numpy(fx[f"{tag}::x"]), torch.from_numpy(fx[f"{tag}::t"]), y)
+    np.testing.assert_allclose(out.numpy(), fx[f"{tag}::out"], atol=ATOL, rtol=1e-5)
+
+
 @pytest.mark.parametrize("tag", ["u", "c"])
 def test_ee_forward_attention_probe(tag):
     """models/early_exit.py:40-80 through EarlyExitUViT(..., "attention_probe"): unconditional and class-conditional
