@@ -15,19 +15,24 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parents[1]
 
 
-def _write(tmp: Path, name: str, params: dict, seed: int, wrap: bool, ee: bool = False, extra=None):
+def _write(tmp: Path, name: str, params: dict, seed: int, wrap: bool, ee: bool = False, extra=None,
+           ctype: str = "mlp_probe_per_layer"):
     """Random-init checkpoint (bare state_dict, or a training checkpoint carrying `model_state_dict`) + yaml config."""
     import duodiff_b200 as ddb
     torch.manual_seed(seed)
     net = ddb.UViT(**params)
     mp = dict(params)
     if ee:
-        net = ddb.EarlyExitUViT(net, "mlp_probe_per_layer")
+        net = ddb.EarlyExitUViT(net, ctype)
         heat_(net, seed)
         with torch.no_grad():
-            for i in range(params["depth"]):
-                net.matrix[f"{i}"].classifier[0].bias.fill_(1.5 - 3.0 * i / params["depth"])
-        mp["classifier_type"] = "mlp_probe_per_layer"
+            if ctype == "mlp_probe_per_layer":
+                for i in range(params["depth"]):
+                    net.matrix[f"{i}"].classifier[0].bias.fill_(1.5 - 3.0 * i / params["depth"])
+            elif ctype == "attention_probe":
+                for i in range(params["depth"]):
+                    net.matrix[f"{i}"].q.normal_()
+        mp["classifier_type"] = ctype
     if extra:
         mp.update(extra)
     sd = net.state_dict()
@@ -114,6 +119,24 @@ def test_eesampler_cli(tmp_path):
     assert 0 <= float(idx.min()) and float(idx.max()) <= 13 and float(idx.min()) < 13  # exits happened
     assert torch.isfinite(err).all() and 0 < float(err.min()) and float(err.max()) < 1
     assert _png(out / "2.png").shape == (32, 32, 4)
+
+
+@pytest.mark.parametrize("ctype,thr", [("attention_probe", "0.0"), ("mlp_probe_per_timestep", "0.5")])
+def test_eesampler_cli_other_classifier_types(tmp_path, ctype, thr):
+    """eesampler.py:157 hands config["model_params"]["classifier_type"] to EarlyExitUViT: the other probe layouts run
+    through the same command line (checkpoint -> yaml -> 1000 steps -> PNGs + logs)."""
+    from duodiff_b200 import eesampler as ES
+    ck, cfg = _write(tmp_path, "ee", CONFIGS["cifar10_3"], 8, wrap=True, ee=True, ctype=ctype)
+    out = tmp_path / "ee_out"
+    ES.main(["--checkpoint_path", ck, "--config_path", cfg, "--threshold", thr, "--batch_size", "2",
+             "--output_folder", str(out), "--seed", "3"])
+    assert sorted(p.name for p in out.iterdir()) == sorted(
+        ["0.png", "1.png", "statistics.txt", "error_prediction_by_timestep.pt", "indices_by_timestep.pt"])
+    err = torch.load(out / "error_prediction_by_timestep.pt")
+    idx = torch.load(out / "indices_by_timestep.pt")
+    assert err.shape == (1000, 3) and idx.shape == (1000, 2) and torch.isfinite(err).all()
+    assert 0 <= float(idx.min()) and float(idx.max()) <= 3
+    assert _png(out / "1.png").shape == (32, 32, 4)
 
 
 def test_top_level_scripts_run_like_the_reference(tmp_path):
