@@ -86,12 +86,14 @@ int ddb_profile_forward(ddb_model* m, const float* x_dev, const float* t_dev, co
 
 /* EarlyExitUViT.forward (models/early_exit.py:268-320) fused with the selection of eesampler.py:62-68.
  *   eps_dev      [B,C,H,W] f32   eps of the first layer whose probe <= threshold (full model if none)
- *   exit_idx_dev [B] i32         that layer index (depth = no exit)
+ *   exit_idx_dev [B] i32         that layer index (depth = no exit; with threshold < 0: 0 = no probe matched, like the
+ *                                reference's argmax over an all-false mask)
  *   scores_dev   [depth,B] f32   classifier_outputs (NULL to skip)
  *   outputs_dev  [depth+1,B,C,H,W] f32 all head outputs + full-model output (NULL to skip)
  * mode 0 = simulate (reference semantics: every layer, probe and head is evaluated);
- * mode 1 = compact: a sample that exits at layer i takes head i's output and is squeezed out of the batch (in-place
- *          row compaction of the block input and the pending long skips), so later kernels run on fewer rows.  eps and
+ * mode 1 = compact: a sample that exits at layer i takes head i's output and leaves the batch (a stayer from the end
+ *          of the batch takes its place in the block input and the pending long skips), so later kernels run on fewer
+ *          rows.  eps and
  *          exit_idx are bit-identical to mode 0; scores past a sample's exit are NaN ("not produced"), outputs_dev
  *          must be NULL, and the sampler's batch-mean probe log averages over the samples still in the batch. */
 int ddb_ee_forward(ddb_model* m, const float* x_dev, const float* t_dev, const int64_t* y_dev, int32_t B,
